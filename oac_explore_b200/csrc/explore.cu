@@ -1,0 +1,372 @@
+// Optimistic exploration (optimistic_exploration.py:14-196) and the batch-1 inference
+// calls around it (policy.get_action, trainer.predict) as fused per-observation kernels:
+// one CTA per observation runs policy forward -> critics forward -> closed-form
+// dQ_UB/d(pre-tanh mean) (no autograd tape) -> KL-constrained mean shift -> sample, with
+// every activation in shared memory.  The reference issues ~120 launches for the same
+// 1.3 MFLOP; at batch 1 the work is bounded by reading the ~2 MB
+// of weights once.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "device_util.cuh"
+#include "../../include/oac_b200.h"
+#include "oac_error.h"
+
+namespace oac {
+
+constexpr int EX_THREADS = 512;
+constexpr int EX_WARPS = EX_THREADS / 32;
+constexpr int EX_MAX_H = 512;
+
+// out[n] = act(sum_k W[n*ld + k] x[k] + b[n]) for n in [0,N): one warp per output row
+__device__ __forceinline__ void gemv_rows(const float* __restrict__ W, int ld, const float* __restrict__ b,
+                                          const float* x, int K, int N, float* out, bool relu_) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    const int K4 = vec ? (K & ~3) : 0;
+    for (int n = warp; n < N; n += EX_WARPS) {
+        const float* w = W + (long long)n * ld;
+        float acc = 0.f;
+        for (int k = lane * 4; k < K4; k += 128) {
+            float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+            acc = fmaf(wv.x, x[k], acc); acc = fmaf(wv.y, x[k + 1], acc);
+            acc = fmaf(wv.z, x[k + 2], acc); acc = fmaf(wv.w, x[k + 3], acc);
+        }
+        for (int k = K4 + lane; k < K; k += 32) acc = fmaf(__ldg(w + k), x[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc + __ldg(b + n);
+            out[n] = relu_ ? fmaxf(v, 0.f) : v;
+        }
+    }
+}
+
+// out[k] (+)= mask[k] > 0 ? sum_n v[n] W[n*ld + col0 + k] : 0  for k in [0,K); rows n in [0,N)
+// part: scratch [EX_WARPS][K]
+__device__ __forceinline__ void gemv_cols(const float* __restrict__ W, int ld, int col0, const float* v, int N, int K,
+                                          const float* mask, float* out, float* part, bool accumulate) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[EX_MAX_H / 32];
+#pragma unroll
+    for (int c = 0; c < EX_MAX_H / 32; ++c) acc[c] = 0.f;
+    for (int n = warp; n < N; n += EX_WARPS) {
+        const float vn = v[n];
+        if (vn == 0.f) continue;                       // ReLU-masked rows contribute nothing
+        const float* w = W + (long long)n * ld + col0;
+#pragma unroll
+        for (int c = 0; c < EX_MAX_H / 32; ++c) {
+            int k = c * 32 + lane;
+            if (k < K) acc[c] = fmaf(vn, __ldg(w + k), acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < EX_MAX_H / 32; ++c) {
+        int k = c * 32 + lane;
+        if (k < K) part[warp * K + k] = acc[c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += EX_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < EX_WARPS; ++w) s += part[w * K + k];
+        if (mask && !(mask[k] > 0.f)) s = 0.f;
+        out[k] = accumulate ? out[k] + s : s;
+    }
+    __syncthreads();
+}
+
+struct NetPtrs {
+    const float *w0, *b0, *w1, *b1, *w2, *b2;
+    int in_dim, in_ld, H, n_out;
+};
+__host__ __device__ inline NetPtrs net_ptrs(const float* base, const OacNetLayout& l) {
+    NetPtrs p;
+    p.w0 = base + l.off_w0; p.b0 = base + l.off_b0; p.w1 = base + l.off_w1; p.b1 = base + l.off_b1;
+    p.w2 = base + l.off_w2; p.b2 = base + l.off_b2;
+    p.in_dim = l.in_dim; p.in_ld = l.in_ld; p.H = l.hidden; p.n_out = l.n_out;
+    return p;
+}
+
+constexpr int EX_MAX_Q = 16;
+
+struct ExploreParams {
+    NetPtrs policy;
+    NetPtrs q[EX_MAX_Q];
+    int n_q, mode, deterministic, quantile_index;
+    unsigned exp_mask;
+    float beta, sqrt_2delta;
+    int O, A, H;
+    const float* obs; const float* eps;
+    unsigned long long rng_seed, rng_offset;
+    float *action, *mu_E, *grad;
+};
+
+// dyn smem layout (floats): x[O+A pad] | h1[H] | h2[H] | head[2A] | qh1[n_q][H] | qh2[n_q][H] |
+//                           qv[64] | cf[64] | g2[H] | g1[H] | da[A] | part[EX_WARPS*max(H,A)]
+__global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int O = p.O, A = p.A, H = p.H;
+    const int ob = blockIdx.x;
+    float* x = sm;
+    float* h1 = x + ((O + A + 3) & ~3);
+    float* h2 = h1 + H;
+    float* head = h2 + H;
+    float* qh1 = head + ((2 * A + 3) & ~3);
+    float* qh2 = qh1 + p.n_q * H;
+    float* qv = qh2 + p.n_q * H;
+    float* cf = qv + 64;
+    float* g2 = cf + 64;
+    float* g1 = g2 + H;
+    float* da = g1 + H;
+    float* part = da + ((A + 3) & ~3);
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < O; i += EX_THREADS) x[i] = p.obs[(long long)ob * O + i];
+    __syncthreads();
+    // ---- policy forward (trainer/policies.py:260-283), deterministic head: a = tanh(mean) ----
+    gemv_rows(p.policy.w0, p.policy.in_ld, p.policy.b0, x, O, H, h1, true);
+    __syncthreads();
+    gemv_rows(p.policy.w1, H, p.policy.b1, h1, H, H, h2, true);
+    __syncthreads();
+    gemv_rows(p.policy.w2, H, p.policy.b2, h2, H, 2 * A, head, false);
+    __syncthreads();
+    for (int j = tid; j < A; j += EX_THREADS) x[O + j] = tanhf(head[j]);
+    __syncthreads();
+    // ---- critics forward ----
+    int n_vals = 0;
+    for (int q = 0; q < p.n_q; ++q) {
+        const NetPtrs& N = p.q[q];
+        gemv_rows(N.w0, N.in_ld, N.b0, x, O + A, H, qh1 + q * H, true);
+        __syncthreads();
+        gemv_rows(N.w1, H, N.b1, qh1 + q * H, H, H, qh2 + q * H, true);
+        __syncthreads();
+        gemv_rows(N.w2, H, N.b2, qh2 + q * H, H, N.n_out, qv + n_vals, false);
+        n_vals += N.n_out;
+    }
+    __syncthreads();
+    // ---- dQ_UB / d(head outputs) ----
+    if (tid == 0) {
+        const int n_heads = p.q[0].n_out;
+        for (int i = 0; i < n_vals; ++i)
+            if ((p.exp_mask >> (i % n_heads)) & 1u) qv[i] = expf(qv[i]);       // networks.py:69-75
+        if (p.mode == OAC_EXPLORE_TWIN) {
+            // Q_UB = (Q1+Q2)/2 + beta |Q1-Q2|/2     (optimistic_exploration.py:42-46,60)
+            float dlt = qv[0] - qv[n_heads];
+            float sg = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+            for (int i = 0; i < n_vals; ++i) cf[i] = 0.f;
+            cf[0] = 0.5f + 0.5f * p.beta * sg;
+            cf[n_heads] = 0.5f - 0.5f * p.beta * sg;
+        } else if (p.mode == OAC_EXPLORE_ENSEMBLE) {
+            // mean + beta * std (unbiased)           (:47-58)
+            float mean = 0.f;
+            for (int i = 0; i < n_vals; ++i) mean += qv[i];
+            mean /= (float)n_vals;
+            float var = 0.f;
+            for (int i = 0; i < n_vals; ++i) var += (qv[i] - mean) * (qv[i] - mean);
+            var /= (float)(n_vals - 1);
+            float sd = sqrtf(var);
+            for (int i = 0; i < n_vals; ++i)
+                cf[i] = 1.f / (float)n_vals + p.beta * (qv[i] - mean) / ((float)(n_vals - 1) * sd);
+        } else {
+            // sorted particle at quantile_index (ParticleTrainer.predict, particle_trainer_oac.py:147-167)
+            for (int i = 0; i < n_vals; ++i) {
+                int r = 0;
+                for (int j = 0; j < n_vals; ++j) r += (qv[j] < qv[i]) || (qv[j] == qv[i] && j < i);
+                cf[i] = (r == p.quantile_index) ? 1.f : 0.f;
+            }
+        }
+        for (int i = 0; i < n_vals; ++i)
+            if ((p.exp_mask >> (i % n_heads)) & 1u) cf[i] *= qv[i];            // d exp(u)/du
+    }
+    for (int j = tid; j < A; j += EX_THREADS) da[j] = 0.f;
+    __syncthreads();
+    // ---- backward to the action, per critic ----
+    int v0 = 0;
+    for (int q = 0; q < p.n_q; ++q) {
+        const NetPtrs& N = p.q[q];
+        for (int n = tid; n < H; n += EX_THREADS) {
+            float s = 0.f;
+            for (int hd = 0; hd < N.n_out; ++hd) s = fmaf(cf[v0 + hd], __ldg(N.w2 + (long long)hd * H + n), s);
+            g2[n] = qh2[q * H + n] > 0.f ? s : 0.f;
+        }
+        __syncthreads();
+        gemv_cols(N.w1, H, 0, g2, H, H, qh1 + q * H, g1, part, false);
+        gemv_cols(N.w0, N.in_ld, O, g1, H, A, nullptr, da, part, true);
+        v0 += N.n_out;
+    }
+    // ---- shift + sample (one warp) ----
+    if (tid < 32) {
+        float num = 0.f;
+        for (int j = tid; j < A; j += 32) {
+            float a = x[O + j];
+            float g = da[j] * (1.f - a * a);                // d tanh(mu)/d mu
+            float sd = expf(fminf(fmaxf(head[A + j], LOG_SIG_MIN_F), LOG_SIG_MAX_F));
+            float S = p.deterministic ? 1.f : sd * sd;      // :71 / L2 variant :160
+            num += g * g * S;
+        }
+        num = warp_sum(num);
+        const float denom = sqrtf(num) + 10e-6f;            // :76-80
+        for (int j = tid; j < A; j += 32) {
+            float a = x[O + j];
+            float g = da[j] * (1.f - a * a);
+            float sd = expf(fminf(fmaxf(head[A + j], LOG_SIG_MIN_F), LOG_SIG_MAX_F));
+            float S = p.deterministic ? 1.f : sd * sd;
+            float muE = head[j] + (p.sqrt_2delta * (S * g)) / denom;      // :83-87
+            float out;
+            if (p.deterministic) {
+                out = muE;                                  // un-squashed (:181)
+            } else {
+                float e = p.eps ? p.eps[(long long)ob * A + j]
+                                : philox_normal(p.rng_seed, 7u, (uint32_t)p.rng_offset, (uint32_t)(p.rng_offset >> 32) + ob, j);
+                out = tanhf(fmaf(sd, e, muE));              // TanhNormal(mu_E, std).sample() (:92-94)
+            }
+            p.action[(long long)ob * A + j] = out;
+            if (p.mu_E) p.mu_E[(long long)ob * A + j] = muE;
+            if (p.grad) p.grad[(long long)ob * A + j] = g;
+        }
+    }
+}
+
+// ---- TanhGaussianPolicy.forward on n rows (one CTA per row) ----
+struct PolicyFwdParams {
+    NetPtrs net;
+    const float* obs; int obs_ld; const float* eps;
+    float *action, *mean, *log_std, *std, *pre_tanh, *log_prob;
+};
+__global__ void __launch_bounds__(EX_THREADS) policy_forward_kernel(PolicyFwdParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int O = p.net.in_dim, H = p.net.H, A = p.net.n_out / 2;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    float* x = sm;
+    float* h1 = x + ((O + 3) & ~3);
+    float* h2 = h1 + H;
+    float* head = h2 + H;
+    for (int i = tid; i < O; i += EX_THREADS) x[i] = p.obs[(long long)r * p.obs_ld + i];
+    __syncthreads();
+    gemv_rows(p.net.w0, p.net.in_ld, p.net.b0, x, O, H, h1, true);
+    __syncthreads();
+    gemv_rows(p.net.w1, H, p.net.b1, h1, H, H, h2, true);
+    __syncthreads();
+    gemv_rows(p.net.w2, H, p.net.b2, h2, H, 2 * A, head, false);
+    __syncthreads();
+    if (tid < 32) {
+        float lp = 0.f;
+        for (int j = tid; j < A; j += 32) {
+            float mean = head[j];
+            float ls = fminf(fmaxf(head[A + j], LOG_SIG_MIN_F), LOG_SIG_MAX_F);
+            float sd = expf(ls);
+            float z = mean, a;
+            if (p.eps) {
+                z = fmaf(sd, p.eps[(long long)r * A + j], mean);
+                a = tanhf(z);
+                float d = z - mean;
+                lp += -(d * d) / (2.f * sd * sd) - logf(sd) - 0.91893853320467274178f - logf(1.f - a * a + TANH_EPS_F);
+            } else {
+                a = tanhf(mean);
+            }
+            long long o = (long long)r * A + j;
+            if (p.action) p.action[o] = a;
+            if (p.mean) p.mean[o] = mean;
+            if (p.log_std) p.log_std[o] = ls;
+            if (p.std) p.std[o] = sd;
+            if (p.pre_tanh) p.pre_tanh[o] = z;
+        }
+        lp = warp_sum(lp);
+        if (tid == 0 && p.log_prob) p.log_prob[r] = lp;
+    }
+}
+
+// ---- FlattenMlp.forward on n rows ----
+struct QFwdParams {
+    NetPtrs net;
+    const float* x; int x_ld; unsigned exp_mask; float* out;
+};
+__global__ void __launch_bounds__(EX_THREADS) q_forward_kernel(QFwdParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int K = p.net.in_dim, H = p.net.H, NO = p.net.n_out;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    float* x = sm;
+    float* h1 = x + ((K + 3) & ~3);
+    float* h2 = h1 + H;
+    float* out = h2 + H;
+    for (int i = tid; i < K; i += EX_THREADS) x[i] = p.x[(long long)r * p.x_ld + i];
+    __syncthreads();
+    gemv_rows(p.net.w0, p.net.in_ld, p.net.b0, x, K, H, h1, true);
+    __syncthreads();
+    gemv_rows(p.net.w1, H, p.net.b1, h1, H, H, h2, true);
+    __syncthreads();
+    gemv_rows(p.net.w2, H, p.net.b2, h2, H, NO, out, false);
+    __syncthreads();
+    for (int i = tid; i < NO; i += EX_THREADS) {
+        float v = out[i];
+        if ((p.exp_mask >> i) & 1u) v = expf(v);
+        p.out[(long long)r * NO + i] = v;
+    }
+}
+
+template <typename K>
+static int ensure_smem(K kernel, size_t bytes) {
+    if (bytes > 200 * 1024) return set_error(OAC_E_UNSUPPORTED, "network too large for the per-observation kernels");
+    if (bytes > 48 * 1024) OAC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+}  // namespace oac
+
+using namespace oac;
+
+extern "C" int oac_explore(const OacExploreArgs* a, void* stream) {
+    if (!a || !a->policy || !a->obs || !a->action || a->n_obs < 1 || a->n_q < 1 || a->n_q > EX_MAX_Q)
+        return set_error(OAC_E_INVALID, "oac_explore: bad argument");
+    const int O = a->policy_lay.in_dim, A = a->policy_lay.n_out / 2, H = a->policy_lay.hidden;
+    if (H > EX_MAX_H || A > EX_MAX_H) return set_error(OAC_E_UNSUPPORTED, "oac_explore: hidden > 512");
+    if (a->q_lay.in_dim != O + A || a->q_lay.hidden != H) return set_error(OAC_E_INVALID, "oac_explore: critic shape");
+    const int n_vals = a->n_q * a->q_lay.n_out;
+    if (n_vals > 64) return set_error(OAC_E_UNSUPPORTED, "oac_explore: more than 64 critic outputs");
+    if (a->mode == OAC_EXPLORE_TWIN && a->n_q < 2) return set_error(OAC_E_INVALID, "oac_explore: twin mode needs 2 critics");
+    if (a->mode == OAC_EXPLORE_ENSEMBLE && n_vals < 2) return set_error(OAC_E_INVALID, "oac_explore: ensemble of one");
+    ExploreParams p;
+    p.policy = net_ptrs(a->policy, a->policy_lay);
+    p.n_q = a->mode == OAC_EXPLORE_TWIN ? 2 : a->n_q;      // twin: only q[0], q[1] (dispatch quirk :42-46)
+    for (int i = 0; i < p.n_q; ++i) {
+        if (!a->q[i]) return set_error(OAC_E_INVALID, "oac_explore: null critic");
+        p.q[i] = net_ptrs(a->q[i], a->q_lay);
+    }
+    p.mode = a->mode; p.deterministic = a->deterministic; p.quantile_index = a->quantile_index;
+    p.exp_mask = a->exp_mask; p.beta = a->beta_UB;
+    p.sqrt_2delta = (float)sqrt(2.0 * (double)a->delta);
+    p.O = O; p.A = A; p.H = H; p.obs = a->obs; p.eps = a->eps;
+    p.rng_seed = a->rng_seed; p.rng_offset = a->rng_offset;
+    p.action = a->action; p.mu_E = a->mu_E; p.grad = a->grad;
+    size_t fl = ((O + A + 3) & ~3) + 2 * H + ((2 * A + 3) & ~3) + 2 * (size_t)p.n_q * H + 128 + 2 * H +
+                ((A + 3) & ~3) + (size_t)EX_WARPS * (H > A ? H : A);
+    if (int e = ensure_smem(explore_kernel, fl * sizeof(float))) return e;
+    explore_kernel<<<a->n_obs, EX_THREADS, fl * sizeof(float), (cudaStream_t)stream>>>(p);
+    OAC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int oac_policy_forward(const float* net, const OacNetLayout* lay, const float* obs, int32_t obs_ld,
+                                  int32_t n, const float* eps, float* action, float* mean, float* log_std,
+                                  float* std, float* pre_tanh, float* log_prob, void* stream) {
+    if (!net || !lay || !obs || n < 1) return set_error(OAC_E_INVALID, "oac_policy_forward: bad argument");
+    if (lay->hidden > EX_MAX_H) return set_error(OAC_E_UNSUPPORTED, "oac_policy_forward: hidden > 512");
+    PolicyFwdParams p{net_ptrs(net, *lay), obs, obs_ld, eps, action, mean, log_std, std, pre_tanh, log_prob};
+    size_t fl = ((lay->in_dim + 3) & ~3) + 2 * (size_t)lay->hidden + lay->n_out + 4;
+    if (int e = ensure_smem(policy_forward_kernel, fl * sizeof(float))) return e;
+    policy_forward_kernel<<<n, EX_THREADS, fl * sizeof(float), (cudaStream_t)stream>>>(p);
+    OAC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int oac_q_forward(const float* net, const OacNetLayout* lay, const float* x, int32_t x_ld, int32_t n,
+                             uint32_t exp_mask, float* out, void* stream) {
+    if (!net || !lay || !x || !out || n < 1) return set_error(OAC_E_INVALID, "oac_q_forward: bad argument");
+    if (lay->hidden > EX_MAX_H) return set_error(OAC_E_UNSUPPORTED, "oac_q_forward: hidden > 512");
+    QFwdParams p{net_ptrs(net, *lay), x, x_ld, exp_mask, out};
+    size_t fl = ((lay->in_dim + 3) & ~3) + 2 * (size_t)lay->hidden + lay->n_out + 4;
+    if (int e = ensure_smem(q_forward_kernel, fl * sizeof(float))) return e;
+    q_forward_kernel<<<n, EX_THREADS, fl * sizeof(float), (cudaStream_t)stream>>>(p);
+    OAC_CUDA(cudaGetLastError());
+    return 0;
+}

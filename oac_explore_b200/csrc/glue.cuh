@@ -1,0 +1,422 @@
+// Per-sample "glue" kernels between the GEMM stages: policy heads + TanhNormal
+// rsample/log_prob (+ the entropy-temperature Adam step), critic heads + the
+// algorithm-specific targets / loss gradients (SAC twin-min, P-OAC sorted
+// particles, G-OAC mean/std), and the policy-loss gradient w.r.t. the policy
+// outputs.  One warp per sample; everything is fp32.
+#pragma once
+#include "gemm_simt.cuh"
+#include "device_util.cuh"
+
+namespace oac {
+
+// =====================================================================================
+// policy heads: mean / log_std GEMV + TanhNormal.rsample + log_prob  (trainer/policies.py:260-316)
+// =====================================================================================
+struct PolicyHeadTask {
+    Ref h2;             // [rows, H] last hidden activation
+    Ref w, b;           // heads [2A, H] (mean rows then log_std rows), [2A]
+    int rows;           // B or 2B
+    int out_row0;       // first row in the io outputs (log_pi [.], mean/log_std [., A])
+    int dst_block[2];   // X row block (units of B rows) receiving tanh actions, per B-row block
+    int eps_slot[2];    // io eps slot per block
+    Ref save;           // [rows, 4, A]: action, std, raw log_std, eps  (for the backward glue)
+};
+
+struct AlphaUpdate {
+    int enabled;        // use_automatic_entropy_tuning
+    int task, block;    // which policy-head rows feed it (out rows out_row0 + block*B .. +B)
+    Ref log_alpha;      // AR_PARAM
+    long long adam_off; // in the Adam arenas
+    float lr, target_entropy;
+    int counter;
+};
+
+struct PolicyHeadParams {
+    const PolicyHeadTask* tasks;
+    ArenaSet as;
+    AdamHyper hyper;
+    AlphaUpdate alpha;
+    long long off_x, off_eps, off_log_pi, off_mean, off_log_std, off_scalars;
+    int x_ld, O, A, H, B;
+    int deterministic, use_external_eps;
+    unsigned long long rng_seed;
+    int n_opt_counters;      // counters CNT_OPT0 .. CNT_OPT0+n-1 are bumped once per step here
+};
+
+__global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
+    const PolicyHeadTask& T = p.tasks[blockIdx.y];
+    const int seed = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * GLUE_WARPS + warp;
+    const int A = p.A, H = p.H, B = p.B;
+    float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
+    int32_t* cnt = p.as.counters + seed * p.as.n_counters;
+    const int step = cnt[CNT_TRAIN_STEPS];
+
+    if (row < T.rows) {
+        const float* __restrict__ h = resolve(p.as, T.h2, seed) + (long long)row * H;
+        const float* __restrict__ w = resolve(p.as, T.w, seed);
+        const float* __restrict__ bias = resolve(p.as, T.b, seed);
+        float* save = resolve(p.as, T.save, seed) + (long long)row * 4 * A;
+        const int blk = row / B, b = row % B;
+        float lp_acc = 0.f;
+        for (int j0 = 0; j0 < A; j0 += 32) {
+            // each pass handles up to 32 action dims; lane j keeps dim j0+j
+            float my_mean = 0.f, my_raw = 0.f;
+            const int jn = min(32, A - j0);
+            for (int j = 0; j < jn; ++j) {
+                const float* wm = w + (long long)(j0 + j) * H;
+                const float* ws = w + (long long)(A + j0 + j) * H;
+                float sm = 0.f, ss = 0.f;
+                for (int k = lane; k < H; k += 32) {
+                    float hv = h[k];
+                    sm = fmaf(hv, wm[k], sm);
+                    ss = fmaf(hv, ws[k], ss);
+                }
+                sm = warp_sum(sm); ss = warp_sum(ss);
+                if (lane == j) { my_mean = sm + bias[j0 + j]; my_raw = ss + bias[A + j0 + j]; }
+            }
+            if (lane < jn) {
+                const int j = j0 + lane;
+                float log_std = fminf(fmaxf(my_raw, LOG_SIG_MIN_F), LOG_SIG_MAX_F);
+                float std = expf(log_std);
+                float action, eps = 0.f, lp = 0.f;
+                if (p.deterministic) {
+                    action = tanhf(my_mean);
+                } else {
+                    if (p.use_external_eps)
+                        eps = io[p.off_eps + ((long long)T.eps_slot[blk] * B + b) * A + j];
+                    else
+                        eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)seed,
+                                            (uint32_t)T.eps_slot[blk], (uint32_t)step, (uint32_t)b, (uint32_t)j);
+                    float z = fmaf(std, eps, my_mean);
+                    action = tanhf(z);
+                    // Normal(mean,std).log_prob(z) - log(1 - a^2 + eps)   (policies.py:147-160)
+                    float d = z - my_mean;
+                    float var = std * std;
+                    lp = -(d * d) / (2.f * var) - logf(std) - 0.91893853320467274178f
+                         - logf(1.f - action * action + TANH_EPS_F);
+                }
+                lp_acc += lp;
+                const int orow = T.out_row0 + row;
+                io[p.off_mean + (long long)orow * A + j] = my_mean;
+                io[p.off_log_std + (long long)orow * A + j] = log_std;
+                io[p.off_x + ((long long)T.dst_block[blk] * B + b) * p.x_ld + p.O + j] = action;
+                save[0 * A + j] = action; save[1 * A + j] = std;
+                save[2 * A + j] = my_raw; save[3 * A + j] = eps;
+            }
+        }
+        lp_acc = warp_sum(lp_acc);
+        if (lane == 0) io[p.off_log_pi + T.out_row0 + row] = lp_acc;
+    }
+
+    // ---- last CTA of this seed: bump step counters, entropy-temperature Adam step ----
+    __shared__ int s_last;
+    __shared__ float s_red[GLUE_THREADS];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = gridDim.x * gridDim.y;
+        int prev = atomicAdd(&cnt[CNT_TICKET0], 1);
+        s_last = (prev == total - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float part = 0.f;
+    if (p.alpha.enabled) {
+        const PolicyHeadTask& TA = p.tasks[p.alpha.task];
+        const volatile float* lp = io + p.off_log_pi + TA.out_row0 + (long long)p.alpha.block * B;
+        for (int i = threadIdx.x; i < B; i += GLUE_THREADS) part += lp[i];
+    }
+    s_red[threadIdx.x] = part;
+    __syncthreads();
+    for (int s = GLUE_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cnt[CNT_TICKET0] = 0;
+        cnt[CNT_TRAIN_STEPS] = step + 1;
+        for (int i = 0; i < p.n_opt_counters; ++i) cnt[CNT_OPT0 + i] += 1;
+        float* sc = io + p.off_scalars;
+        if (p.alpha.enabled) {
+            // alpha_loss = -(log_alpha * (log_pi + target_entropy).detach()).mean()  (trainer.py:140-146)
+            float mean_lp = s_red[0] / (float)B;
+            float* la = resolve(p.as, p.alpha.log_alpha, seed);
+            float* m1 = p.as.base[AR_ADAM_M] + (long long)seed * p.as.stride[AR_ADAM_M] + p.alpha.adam_off;
+            float* m2 = p.as.base[AR_ADAM_V] + (long long)seed * p.as.stride[AR_ADAM_V] + p.alpha.adam_off;
+            float tgt = mean_lp + p.alpha.target_entropy;
+            sc[SC_ALPHA_LOSS] = -(la[0] * tgt);
+            sc[SC_MEAN_LOGPI] = mean_lp;
+            AdamScalars s = make_adam_scalars(p.hyper, p.alpha.lr, cnt[CNT_OPT0 + p.alpha.counter], step + 1);
+            adam_update(-tgt, la, m1, m2, nullptr, s);
+            sc[SC_ALPHA] = expf(la[0]);      // POST-step alpha (trainer.py:147)
+        } else {
+            sc[SC_ALPHA] = 0.f;              // the fork's choice (trainer.py:148-149)
+            sc[SC_ALPHA_LOSS] = 0.f;
+        }
+    }
+}
+
+// =====================================================================================
+// critic heads + per-algorithm targets / loss gradients
+// =====================================================================================
+constexpr int MAX_HEAD_SRC = 40;
+constexpr int MAX_VALS = 40;
+
+struct HeadSrc {
+    Ref h2;          // [*, H] hidden activations; sample b uses row row0 + b
+    int row0;
+    Ref w3, b3;      // [n_heads, H], [n_heads]
+    int n_heads;
+    Ref dq;          // [B, n_heads] gradient w.r.t. the (pre-exp) head outputs, written here
+};
+
+enum CriticMode {
+    CM_SAC = 0,         // srcs: qf1(a_pi) qf2(a_pi) qf1(data) qf2(data) tq1 tq2
+    CM_POAC_Q = 1,      // srcs: qfs(data) x n, tfs(next) x n
+    CM_POAC_PI = 2,     // srcs: qfs(a_pi) x n
+    CM_GOAC_Q = 3,      // srcs: q(data) [std(data)] q_target(next) [std_target(next)]
+    CM_GOAC_PI = 4      // srcs: q(a_pi) [std(a_pi)] q(a_tp) [std(a_tp)]
+};
+
+struct CriticHeadParams {
+    HeadSrc src[MAX_HEAD_SRC];
+    int n_src;
+    int mode;
+    ArenaSet as;
+    long long off_rewards, off_terminals, off_counts, off_log_pi, off_q_pred, off_q_target, off_q_new, off_scalars;
+    int B, H, P;          // P: particles (P-OAC) / heads per sample
+    int nq;               // io row width of q_pred / q_target / q_new
+    int n_nets;           // P-OAC / G-OAC: critic nets per group (1 shared, P or 2 separate)
+    int share_layers, counts;
+    float discount, reward_scale, standard_bound, std_init;
+};
+
+__global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+    const CriticHeadParams& p = *pp;
+    __shared__ float s_vals[GLUE_WARPS][MAX_VALS];
+    const int seed = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GLUE_WARPS + warp;
+    const int B = p.B, H = p.H;
+    if (b >= B) return;
+    float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
+    float* vals = s_vals[warp];
+
+    // ---- all head outputs of this sample: vals[g], g enumerates (src, head) ----
+    int g = 0;
+    for (int s = 0; s < p.n_src; ++s) {
+        const HeadSrc& S = p.src[s];
+        const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
+        const float* __restrict__ w = resolve(p.as, S.w3, seed);
+        const float* __restrict__ bias = resolve(p.as, S.b3, seed);
+        for (int hd = 0; hd < S.n_heads; ++hd, ++g) {
+            float acc = 0.f;
+            for (int k = lane; k < H; k += 32) acc = fmaf(h[k], w[(long long)hd * H + k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) vals[g] = acc + bias[hd];
+        }
+    }
+    __syncwarp();
+    if (lane != 0) return;
+
+    const float invB = 1.0f / (float)B;
+    const float r = io[p.off_rewards + b];
+    const float d = io[p.off_terminals + b];
+    const float nd = (1.f - d) * p.discount;       // (1 - terminals) * discount
+
+    if (p.mode == CM_SAC) {
+        const float alpha = io[p.off_scalars + SC_ALPHA];
+        const float q1n = vals[0], q2n = vals[1], q1 = vals[2], q2 = vals[3], t1 = vals[4], t2 = vals[5];
+        const float lp_next = io[p.off_log_pi + B + b];
+        // trainer.py:178-184
+        float tq = fminf(t1, t2) - alpha * lp_next;
+        float y = p.reward_scale * r + nd * tq;
+        io[p.off_q_pred + b * 2 + 0] = q1; io[p.off_q_pred + b * 2 + 1] = q2;
+        io[p.off_q_target + b * 2 + 0] = y; io[p.off_q_target + b * 2 + 1] = y;
+        io[p.off_q_new + b * 2 + 0] = q1n; io[p.off_q_new + b * 2 + 1] = q2n;
+        // MSELoss mean over B: d/dq = 2 (q - y) / B          (trainer.py:194-195)
+        resolve(p.as, p.src[2].dq, seed)[b] = 2.f * (q1 - y) * invB;
+        resolve(p.as, p.src[3].dq, seed)[b] = 2.f * (q2 - y) * invB;
+        // policy loss -mean(min(q1,q2)): gradient to the smaller one (first arg on ties)
+        const bool sel1 = q1n <= q2n;
+        resolve(p.as, p.src[0].dq, seed)[b] = sel1 ? -invB : 0.f;
+        resolve(p.as, p.src[1].dq, seed)[b] = sel1 ? 0.f : -invB;
+    } else if (p.mode == CM_POAC_Q) {
+        // vals[0..P) current particles, vals[P..2P) target particles (particle_trainer_oac.py:185-208)
+        const int P = p.P;
+        const float* q = vals;
+        const float* tq = vals + P;
+        float sq[16], st[16];
+        int rank_q[16];
+        for (int i = 0; i < P; ++i) {
+            int rq = 0, rt = 0;
+            for (int j = 0; j < P; ++j) {
+                rq += (q[j] < q[i]) || (q[j] == q[i] && j < i);
+                rt += (tq[j] < tq[i]) || (tq[j] == tq[i] && j < i);
+            }
+            rank_q[i] = rq; sq[rq] = q[i]; st[rt] = tq[i];
+        }
+        float T[16];
+        float mean_sq = 0.f, mean_T = 0.f;
+        for (int i = 0; i < P; ++i) {
+            T[i] = p.reward_scale * r + nd * st[i];
+            mean_sq += sq[i]; mean_T += T[i];
+        }
+        if (p.counts) {      // :220-224
+            mean_sq /= (float)P; mean_T /= (float)P;
+            const float f = io[p.off_counts + b] == 0.f ? 1.f : 0.f;
+            for (int i = 0; i < P; ++i) T[i] = T[i] * f + (1.f - f) * (sq[i] - mean_sq + mean_T);
+        }
+        for (int i = 0; i < P; ++i) {
+            io[p.off_q_pred + (long long)b * p.nq + i] = sq[i];
+            io[p.off_q_target + (long long)b * p.nq + i] = T[i];
+        }
+        // each head regresses to the target at its current rank; with separate nets a net only
+        // receives gradient where it sits at its own rank (:247-264)
+        for (int i = 0; i < P; ++i) {
+            float gq = 2.f * (q[i] - T[rank_q[i]]) * invB;
+            if (p.share_layers) resolve(p.as, p.src[0].dq, seed)[(long long)b * P + i] = gq;
+            else resolve(p.as, p.src[i].dq, seed)[b] = (rank_q[i] == i) ? gq : 0.f;
+        }
+    } else if (p.mode == CM_POAC_PI) {
+        // policy loss uses the lowest particle (:291-295)
+        const int P = p.P;
+        int best = 0;
+        for (int i = 1; i < P; ++i) if (vals[i] < vals[best]) best = i;
+        for (int i = 0; i < P; ++i) {
+            io[p.off_q_new + (long long)b * p.nq + i] = vals[i];
+            float gq = (i == best) ? -invB : 0.f;
+            if (p.share_layers) resolve(p.as, p.src[0].dq, seed)[(long long)b * P + i] = gq;
+            else resolve(p.as, p.src[i].dq, seed)[b] = gq;
+        }
+    } else if (p.mode == CM_GOAC_Q) {
+        // shared: vals = q0, raw1 | tq0, traw1 ; separate: q0 | raw1 | tq0 | traw1  (same order)
+        const float q0 = vals[0], sig = expf(vals[1]), t0 = vals[2], tsig = expf(vals[3]);
+        float std_t = nd * tsig;                                    // gaussian_trainer.py:217
+        if (p.counts) {
+            const float f = io[p.off_counts + b] == 0.f ? 1.f : 0.f;
+            std_t = std_t * f + (1.f - f) * sig;                    // :224-228
+        }
+        const float y = p.reward_scale * r + nd * t0;               // :231-232
+        std_t = fminf(fmaxf(std_t, 0.f), p.std_init);               // :233
+        io[p.off_q_pred + b * 2 + 0] = q0; io[p.off_q_pred + b * 2 + 1] = sig;
+        io[p.off_q_target + b * 2 + 0] = y; io[p.off_q_target + b * 2 + 1] = std_t;
+        const float g0 = 2.f * (q0 - y) * invB;
+        const float g1 = 2.f * (sig - std_t) * invB * sig;          // through exp
+        if (p.share_layers) {
+            float* dq = resolve(p.as, p.src[0].dq, seed);
+            dq[b * 2 + 0] = g0; dq[b * 2 + 1] = g1;
+        } else {
+            resolve(p.as, p.src[0].dq, seed)[b] = g0;
+            resolve(p.as, p.src[1].dq, seed)[b] = g1;
+        }
+    } else {   // CM_GOAC_PI
+        // policy: -(q + z*sigma).mean() (:344-356); target policy: -(q).mean() (:361-373)
+        const float q0 = vals[0], sig = expf(vals[1]);
+        io[p.off_q_new + b * 2 + 0] = q0; io[p.off_q_new + b * 2 + 1] = sig;
+        const float g0 = -invB, g1 = -invB * p.standard_bound * sig;
+        if (p.share_layers) {
+            float* dq = resolve(p.as, p.src[0].dq, seed);
+            dq[b * 2 + 0] = g0; dq[b * 2 + 1] = g1;
+            float* dt = resolve(p.as, p.src[1].dq, seed);
+            dt[b * 2 + 0] = -invB; dt[b * 2 + 1] = 0.f;
+        } else {
+            resolve(p.as, p.src[0].dq, seed)[b] = g0;
+            resolve(p.as, p.src[1].dq, seed)[b] = g1;
+            resolve(p.as, p.src[2].dq, seed)[b] = -invB;
+            resolve(p.as, p.src[3].dq, seed)[b] = 0.f;
+        }
+    }
+}
+
+// =====================================================================================
+// policy-loss gradient w.r.t. the policy head outputs
+// =====================================================================================
+struct PolicyGradSrc {
+    Ref dh1;          // [B, H] gradient at the critic's first hidden layer (rows of this policy)
+    Ref w1;           // critic fc0.weight [H, in_ld]; action columns start at O
+    int ld;
+};
+
+struct PolicyGradTask {
+    PolicyGradSrc src[20];
+    int n_src;
+    Ref save;         // [., 4, A] from policy_head (rows of this policy start at save_row0)
+    int save_row0;
+    Ref dhead;        // out: [B, 2A]  d loss / d(mean), d loss / d(raw log_std)
+    int entropy;      // 1: alpha*log_pi term present (stochastic policy)
+};
+
+struct PolicyGradParams {
+    const PolicyGradTask* tasks;
+    ArenaSet as;
+    long long off_scalars;
+    int O, A, H, B;
+};
+
+// dyn smem: w1 action columns of one source, [H][A]
+__global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
+    extern __shared__ float s_wa[];
+    const PolicyGradTask& T = p.tasks[blockIdx.y];
+    const int seed = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GLUE_WARPS + warp;
+    const int A = p.A, H = p.H, B = p.B, O = p.O;
+    float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
+
+    // g_a[j] = sum_src sum_n dh1[b,n] * W1[n, O+j]; lane j (+32 i) keeps action dim j
+    float ga[4] = {0.f, 0.f, 0.f, 0.f};      // A <= 128
+    for (int s = 0; s < T.n_src; ++s) {
+        const float* __restrict__ w1 = resolve(p.as, T.src[s].w1, seed);
+        const int ld = T.src[s].ld;
+        __syncthreads();
+        for (int i = threadIdx.x; i < H * A; i += GLUE_THREADS) {
+            int n = i / A, j = i % A;
+            s_wa[i] = w1[(long long)n * ld + O + j];
+        }
+        __syncthreads();
+        if (b < B) {
+            const float* __restrict__ dh = resolve(p.as, T.src[s].dh1, seed) + (long long)b * H;
+            for (int n = 0; n < H; ++n) {
+                float dv = dh[n];         // broadcast load
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int j = lane + 32 * i;
+                    if (j < A) ga[i] = fmaf(dv, s_wa[n * A + j], ga[i]);
+                }
+            }
+        }
+    }
+    if (b >= B) return;
+    const float alpha = io[p.off_scalars + SC_ALPHA];
+    const float invB = 1.0f / (float)B;
+    const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
+    float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * 2 * A;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int j = lane + 32 * i;
+        if (j >= A) continue;
+        float a = save[0 * A + j];
+        float one_m_a2 = 1.f - a * a;
+        float dmean, draw;
+        if (T.entropy) {
+            float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
+            float u = one_m_a2 + TANH_EPS_F;
+            // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
+            dmean = alpha * invB * (2.f * a * one_m_a2 / u) + ga[i] * one_m_a2;
+            float dstd = dmean * eps - alpha * invB / std;
+            bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
+            draw = inside ? dstd * std : 0.f;
+        } else {
+            dmean = ga[i] * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
+            draw = 0.f;
+        }
+        dhead[j] = dmean;
+        dhead[A + j] = draw;
+    }
+}
+
+}  // namespace oac

@@ -1,0 +1,673 @@
+// Host-side "program" builder: turns an OacConfig into the stage list of one
+// train_from_torch (GEMM stages + glue kernels), uploads the task tables once and
+// replays the whole step as one CUDA graph.
+//
+// Stage order follows the reference's update order where it defines the numerics
+// (SURVEY.md section 3.3 / 8c):
+//   SAC   : policy fwd(obs,next) -> alpha step -> Q fwd x6 -> targets/dq -> Q bwd ->
+//           Q Adam(+Polyak) -> policy-loss dX through the (mode A: post-step) Q weights ->
+//           policy bwd -> policy Adam.                         trainer/trainer.py:126-224
+//   P-OAC : Q fwd(data), policy(next) , target fwd, sort, per-rank targets -> Q bwd/Adam ->
+//           policy(obs), alpha step, fresh Q fwd with updated weights, min particle ->
+//           policy bwd/Adam.                                   trainer/particle_trainer_oac.py:169-324
+//   G-OAC : mean/std critic regression -> Adam -> upper-bound policy and mean target-policy
+//           updates through the updated critic.               trainer/gaussian_trainer.py:177-388
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "glue.cuh"
+#include "oac_error.h"
+
+namespace oac {
+
+static inline int pad4(int x) { return (x + 3) & ~3; }
+static inline long long pad4ll(long long x) { return (x + 3) & ~3ll; }
+
+// ------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------
+static void net_layout(OacNetLayout& n, int kind, int in_dim, int hidden, int n_out, int trainable,
+                       long long& cursor) {
+    memset(&n, 0, sizeof(n));
+    n.kind = kind; n.in_dim = in_dim; n.in_ld = pad4(in_dim); n.hidden = hidden; n.n_out = n_out;
+    n.trainable = trainable;
+    long long start = cursor;
+    if (kind == OAC_NET_SCALAR) {
+        n.off_w0 = cursor; cursor += 4;
+        n.off_b0 = n.off_w1 = n.off_b1 = n.off_w2 = n.off_b2 = n.off_w0;
+    } else {
+        n.off_w0 = cursor; cursor += pad4ll((long long)hidden * n.in_ld);
+        n.off_b0 = cursor; cursor += pad4(hidden);
+        n.off_w1 = cursor; cursor += pad4ll((long long)hidden * hidden);
+        n.off_b1 = cursor; cursor += pad4(hidden);
+        n.off_w2 = cursor; cursor += pad4ll((long long)n_out * hidden);
+        n.off_b2 = cursor; cursor += pad4(n_out);
+    }
+    n.size = cursor - start;
+}
+
+struct NetIds {       // indices into OacLayout::nets
+    int policy = -1, target_policy = -1, log_alpha = -1;
+    std::vector<int> qf, tf;          // critics and their Polyak targets
+};
+
+static int validate(const OacConfig& c) {
+    if (c.obs_dim < 1 || c.act_dim < 1 || c.hidden < 1 || c.batch < 1 || c.n_seeds < 1)
+        return set_error(OAC_E_INVALID, "dims must be positive");
+    if (c.act_dim > 128) return set_error(OAC_E_UNSUPPORTED, "act_dim > 128");
+    if (c.algo == OAC_ALGO_POAC && (c.n_particles < 2 || c.n_particles > 16))
+        return set_error(OAC_E_UNSUPPORTED, "P-OAC needs 2 <= n_particles <= 16");
+    if (c.algo < 0 || c.algo > OAC_ALGO_GOAC) return set_error(OAC_E_INVALID, "unknown algo");
+    return 0;
+}
+
+static int build_layout(const OacConfig& c, OacLayout& L, NetIds& ids) {
+    if (int e = validate(c)) return e;
+    memset(&L, 0, sizeof(L));
+    const int O = c.obs_dim, A = c.act_dim, H = c.hidden, B = c.batch;
+    long long cur = 0;
+    int n = 0;
+    auto add = [&](int kind, int in_dim, int n_out, int trainable) {
+        net_layout(L.nets[n], kind, in_dim, H, n_out, trainable, cur);
+        return n++;
+    };
+    int n_crit = 1, heads = 1;
+    if (c.algo == OAC_ALGO_SAC) { n_crit = 2; heads = 1; L.nq = 2; }
+    else if (c.algo == OAC_ALGO_POAC) {
+        n_crit = c.share_layers ? 1 : c.n_particles; heads = c.share_layers ? c.n_particles : 1;
+        L.nq = c.n_particles;
+    } else { n_crit = c.share_layers ? 1 : 2; heads = c.share_layers ? 2 : 1; L.nq = 2; }
+    ids.policy = add(OAC_NET_POLICY, O, 2 * A, 1);
+    if (c.algo == OAC_ALGO_GOAC) ids.target_policy = add(OAC_NET_POLICY, O, 2 * A, 1);
+    for (int i = 0; i < n_crit; ++i) ids.qf.push_back(add(OAC_NET_Q, O + A, heads, 1));
+    ids.log_alpha = add(OAC_NET_SCALAR, 1, 1, 1);
+    L.n_trainable = n;
+    L.adam_floats = cur;
+    for (int i = 0; i < n_crit; ++i) ids.tf.push_back(add(OAC_NET_Q, O + A, heads, 0));
+    L.n_nets = n;
+    L.param_floats = cur;
+
+    // IO slice
+    long long io = 0;
+    L.x_rows = 4 * B; L.x_ld = pad4(O + A);
+    L.off_x = io; io += (long long)L.x_rows * L.x_ld;
+    L.off_rewards = io; io += pad4(B);
+    L.off_terminals = io; io += pad4(B);
+    L.off_counts = io; io += pad4(B);
+    L.off_eps = io; io += pad4ll(2ll * B * A);
+    L.off_log_pi = io; io += pad4(3 * B);
+    L.off_mean = io; io += pad4ll(3ll * B * A);
+    L.off_log_std = io; io += pad4ll(3ll * B * A);
+    L.off_q_pred = io; io += pad4ll((long long)B * L.nq);
+    L.off_q_target = io; io += pad4ll((long long)B * L.nq);
+    L.off_q_new = io; io += pad4ll((long long)B * L.nq);
+    L.off_scalars = io; io += SC_COUNT;
+    L.io_floats = io;
+    L.n_counters = CNT_TOTAL;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// program
+// ------------------------------------------------------------------------------------
+enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3 };
+
+struct Stage {
+    int kind;
+    std::vector<GemmTask> gemm;
+    std::vector<PolicyHeadTask> ph;
+    PolicyHeadParams php;
+    CriticHeadParams chp;
+    std::vector<PolicyGradTask> pg;
+    PolicyGradParams pgp;
+    // launch
+    void* dev = nullptr;        // task table / params on the device
+    int small_tiles = 0;
+    int max_tiles = 0;
+    int max_rows = 0;
+    const char* name = "";
+};
+
+}  // namespace oac
+
+using namespace oac;
+
+struct OacTrainer {
+    OacConfig cfg;
+    OacLayout lay;
+    NetIds ids;
+    ArenaSet as;
+    AdamHyper hyper;
+    std::vector<Stage> stages;
+    std::vector<void*> dev_allocs;
+    long long work_cursor = 0;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    bool use_graph = true;
+    int n_opt = 0;
+};
+
+namespace oac {
+
+struct Builder {
+    OacTrainer& t;
+    const OacConfig& c;
+    const OacLayout& L;
+    int O, A, H, B;
+    explicit Builder(OacTrainer& tr) : t(tr), c(tr.cfg), L(tr.lay) {
+        O = c.obs_dim; A = c.act_dim; H = c.hidden; B = c.batch;
+    }
+    Ref work(long long n) {
+        Ref r{AR_WORK, t.work_cursor};
+        t.work_cursor += pad4ll(n);
+        return r;
+    }
+    Ref P(long long off) const { return Ref{AR_PARAM, off}; }
+    Ref X(int block, int col = 0) const { return Ref{AR_IO, L.off_x + (long long)block * B * L.x_ld + col}; }
+    const OacNetLayout& net(int i) const { return L.nets[i]; }
+
+    Stage& add_stage(int kind, const char* name) {
+        t.stages.emplace_back();
+        Stage& s = t.stages.back();
+        s.kind = kind; s.name = name;
+        return s;
+    }
+    GemmTask base_task() {
+        GemmTask g;
+        memset(&g, 0, sizeof(g));
+        g.target_off = g.target_bias_off = -1;
+        g.train_bias = 1;
+        return g;
+    }
+    // Y[M,N] = act(X[M,K] W[N,K]^T + b)
+    void fwd(Stage& s, Ref x, int ldx, int M, int K, Ref w, int ldw, Ref b, int N, Ref y, int ldy, bool relu_) {
+        GemmTask g = base_task();
+        g.A = x; g.lda = ldx; g.a_trans = 0;
+        g.B = w; g.ldb = ldw; g.b_trans = 0;
+        g.C = y; g.ldc = ldy; g.M = M; g.N = N; g.K = K;
+        g.epi = relu_ ? EPI_BIAS_RELU : EPI_BIAS; g.bias = b;
+        s.gemm.push_back(g);
+    }
+    // dX[M,Kin] = (dY[M,Nout] W[Nout,Kin]) * (mask > 0)      (mask.arena < 0: no mask)
+    void dx(Stage& s, Ref dy, int ldy, int M, int Nout, Ref w, int ldw, int Kin, Ref out, int ldo, Ref mask, int ldmask, bool use_mask) {
+        GemmTask g = base_task();
+        g.A = dy; g.lda = ldy; g.a_trans = 0;
+        g.B = w; g.ldb = ldw; g.b_trans = 1;
+        g.C = out; g.ldc = ldo; g.M = M; g.N = Kin; g.K = Nout;
+        g.epi = use_mask ? EPI_MASK : EPI_STORE; g.mask = mask; g.ldmask = ldmask;
+        s.gemm.push_back(g);
+    }
+    // W[Nout,Kin] <- Adam(dY[rows,Nout]^T X[rows,Kin]); bias <- Adam(colsum dY)
+    void dw(Stage& s, Ref dy, int ldy, Ref x, int ldx, int rows, int Nout, int Kin, long long w_off, int ldw,
+            long long b_off, long long tw_off, long long tb_off, float lr, int counter, int train_bias) {
+        GemmTask g = base_task();
+        g.A = dy; g.lda = ldy; g.a_trans = 1;
+        g.B = x; g.ldb = ldx; g.b_trans = 1;
+        g.C = P(w_off); g.ldc = ldw; g.M = Nout; g.N = Kin; g.K = rows;
+        g.epi = EPI_ADAM; g.bias = P(b_off); g.has_bias = 1; g.train_bias = train_bias;
+        g.adam_off = w_off; g.adam_bias_off = b_off;
+        g.target_off = tw_off; g.target_bias_off = tb_off;
+        g.lr = lr; g.counter = CNT_OPT0 + counter;
+        s.gemm.push_back(g);
+    }
+
+    // ---- policy forward (trunk) for rows of X blocks [blk0, blk0+nblk) ----
+    struct PolAct { Ref h1, h2, save; int rows; };
+    PolAct alloc_pol(int nblk) {
+        PolAct a; a.rows = nblk * B;
+        a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
+        a.save = work((long long)a.rows * 4 * A);
+        return a;
+    }
+    struct CritAct { Ref h1, h2, dq, dh2, dh1; int rows; };
+    CritAct alloc_crit(int nblk, int heads) {
+        CritAct a; a.rows = nblk * B;
+        a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
+        a.dq = work((long long)a.rows * heads);
+        a.dh2 = work((long long)a.rows * H); a.dh1 = work((long long)a.rows * H);
+        return a;
+    }
+    void pol_l1(Stage& s, int ni, int blk0, const PolAct& a) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, X(blk0), L.x_ld, a.rows, O, P(n.off_w0), n.in_ld, P(n.off_b0), H, a.h1, H, true);
+    }
+    void pol_l2(Stage& s, int ni, const PolAct& a) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, a.h1, H, a.rows, H, P(n.off_w1), H, P(n.off_b1), H, a.h2, H, true);
+    }
+    void crit_l1(Stage& s, int ni, int blk0, const CritAct& a) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, X(blk0), L.x_ld, a.rows, O + A, P(n.off_w0), n.in_ld, P(n.off_b0), H, a.h1, H, true);
+    }
+    void crit_l2(Stage& s, int ni, const CritAct& a) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, a.h1, H, a.rows, H, P(n.off_w1), H, P(n.off_b1), H, a.h2, H, true);
+    }
+    HeadSrc head_src(int ni, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        HeadSrc h; h.h2 = a.h2; h.row0 = row0; h.w3 = P(n.off_w2); h.b3 = P(n.off_b2); h.n_heads = n.n_out;
+        h.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * n.n_out};
+        return h;
+    }
+    // dh2 = (dq W3) * (h2>0) for rows [row0, row0+B) of a critic activation set
+    void crit_dh2(Stage& s, int ni, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        long long ro = (long long)row0 * H;
+        dx(s, Ref{a.dq.arena, a.dq.off + (long long)row0 * n.n_out}, n.n_out, B, n.n_out, P(n.off_w2), H, H,
+           Ref{a.dh2.arena, a.dh2.off + ro}, H, Ref{a.h2.arena, a.h2.off + ro}, H, true);
+    }
+    void crit_dh1(Stage& s, int ni, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        long long ro = (long long)row0 * H;
+        dx(s, Ref{a.dh2.arena, a.dh2.off + ro}, H, B, H, P(n.off_w1), H, H,
+           Ref{a.dh1.arena, a.dh1.off + ro}, H, Ref{a.h1.arena, a.h1.off + ro}, H, true);
+    }
+    // Adam on all three layers of a critic from rows [row0,row0+B) (inputs: X block xblk)
+    void crit_adam(Stage& s, int ni, int ti, const CritAct& a, int row0, int xblk, float lr, int counter) {
+        const OacNetLayout& n = net(ni);
+        const OacNetLayout* tn = ti >= 0 ? &net(ti) : nullptr;
+        long long ro = (long long)row0 * H;
+        Ref dh1{a.dh1.arena, a.dh1.off + ro}, dh2{a.dh2.arena, a.dh2.off + ro};
+        Ref h1{a.h1.arena, a.h1.off + ro}, h2{a.h2.arena, a.h2.off + ro};
+        Ref dq{a.dq.arena, a.dq.off + (long long)row0 * n.n_out};
+        dw(s, dh1, H, X(xblk), L.x_ld, B, H, O + A, n.off_w0, n.in_ld, n.off_b0,
+           tn ? tn->off_w0 : -1, tn ? tn->off_b0 : -1, lr, counter, 1);
+        dw(s, dh2, H, h1, H, B, H, H, n.off_w1, H, n.off_b1, tn ? tn->off_w1 : -1, tn ? tn->off_b1 : -1, lr, counter, 1);
+        dw(s, dq, n.n_out, h2, H, B, n.n_out, H, n.off_w2, H, n.off_b2, tn ? tn->off_w2 : -1, tn ? tn->off_b2 : -1,
+           lr, counter, c.train_bias);
+    }
+    // policy backward from dhead [B,2A] at rows [row0,row0+B) of a policy activation set
+    struct PolGrad { Ref dhead, dh2, dh1; };
+    PolGrad alloc_polgrad() {
+        PolGrad g; g.dhead = work((long long)B * 2 * A); g.dh2 = work((long long)B * H); g.dh1 = work((long long)B * H);
+        return g;
+    }
+    void pol_dh2(Stage& s, int ni, const PolAct& a, int row0, const PolGrad& g) {
+        const OacNetLayout& n = net(ni);
+        dx(s, g.dhead, 2 * A, B, 2 * A, P(n.off_w2), H, H, g.dh2, H, Ref{a.h2.arena, a.h2.off + (long long)row0 * H}, H, true);
+    }
+    void pol_dh1(Stage& s, int ni, const PolAct& a, int row0, const PolGrad& g) {
+        const OacNetLayout& n = net(ni);
+        dx(s, g.dh2, H, B, H, P(n.off_w1), H, H, g.dh1, H, Ref{a.h1.arena, a.h1.off + (long long)row0 * H}, H, true);
+    }
+    void pol_adam(Stage& s, int ni, const PolAct& a, int row0, int xblk, const PolGrad& g, float lr, int counter) {
+        const OacNetLayout& n = net(ni);
+        long long ro = (long long)row0 * H;
+        dw(s, g.dh1, H, X(xblk), L.x_ld, B, H, O, n.off_w0, n.in_ld, n.off_b0, -1, -1, lr, counter, 1);
+        dw(s, g.dh2, H, Ref{a.h1.arena, a.h1.off + ro}, H, B, H, H, n.off_w1, H, n.off_b1, -1, -1, lr, counter, 1);
+        dw(s, g.dhead, 2 * A, Ref{a.h2.arena, a.h2.off + ro}, H, B, 2 * A, H, n.off_w2, H, n.off_b2, -1, -1, lr, counter, 1);
+    }
+    PolicyHeadTask ph_task(int ni, const PolAct& a, int out_row0, int dst0, int dst1, int eps0, int eps1) {
+        const OacNetLayout& n = net(ni);
+        PolicyHeadTask p;
+        memset(&p, 0, sizeof(p));
+        p.h2 = a.h2; p.w = P(n.off_w2); p.b = P(n.off_b2); p.rows = a.rows; p.out_row0 = out_row0;
+        p.dst_block[0] = dst0; p.dst_block[1] = dst1; p.eps_slot[0] = eps0; p.eps_slot[1] = eps1;
+        p.save = a.save;
+        return p;
+    }
+    void fill_php(Stage& s, int alpha_task, int alpha_block, int alpha_counter) {
+        PolicyHeadParams& p = s.php;
+        memset(&p, 0, sizeof(p));
+        p.off_x = L.off_x; p.off_eps = L.off_eps; p.off_log_pi = L.off_log_pi; p.off_mean = L.off_mean;
+        p.off_log_std = L.off_log_std; p.off_scalars = L.off_scalars;
+        p.x_ld = L.x_ld; p.O = O; p.A = A; p.H = H; p.B = B;
+        p.deterministic = c.deterministic; p.rng_seed = c.rng_seed;
+        p.n_opt_counters = t.n_opt;
+        p.alpha.enabled = c.auto_alpha; p.alpha.task = alpha_task; p.alpha.block = alpha_block;
+        const OacNetLayout& la = net(t.ids.log_alpha);
+        p.alpha.log_alpha = P(la.off_w0); p.alpha.adam_off = la.off_w0;
+        p.alpha.lr = c.policy_lr; p.alpha.target_entropy = c.target_entropy; p.alpha.counter = alpha_counter;
+    }
+    void fill_chp(Stage& s, int mode, int n_nets) {
+        CriticHeadParams& p = s.chp;
+        p.mode = mode;
+        p.off_rewards = L.off_rewards; p.off_terminals = L.off_terminals; p.off_counts = L.off_counts;
+        p.off_log_pi = L.off_log_pi; p.off_q_pred = L.off_q_pred; p.off_q_target = L.off_q_target;
+        p.off_q_new = L.off_q_new; p.off_scalars = L.off_scalars;
+        p.B = B; p.H = H; p.P = c.n_particles; p.nq = L.nq; p.n_nets = n_nets;
+        p.share_layers = c.share_layers; p.counts = c.counts;
+        p.discount = c.discount; p.reward_scale = c.reward_scale;
+        p.standard_bound = c.standard_bound; p.std_init = c.std_init;
+    }
+    void fill_pgp(Stage& s) {
+        PolicyGradParams& p = s.pgp;
+        memset(&p, 0, sizeof(p));
+        p.off_scalars = L.off_scalars; p.O = O; p.A = A; p.H = H; p.B = B;
+    }
+
+    // X blocks: 0 [obs|a_tp] (G-OAC), 1 [obs|a_pi], 2 [obs|actions], 3 [next_obs|a_next]
+    void build_sac();
+    void build_poac();
+    void build_goac();
+};
+
+void Builder::build_sac() {
+    // optimizers: 0 policy, 1 qf1, 2 qf2, 3 alpha
+    t.n_opt = 4;
+    const int pol = t.ids.policy, q1 = t.ids.qf[0], q2 = t.ids.qf[1], t1 = t.ids.tf[0], t2 = t.ids.tf[1];
+    PolAct pa = alloc_pol(2);                     // rows [0,B) obs (block 2), [B,2B) next_obs (block 3)
+    CritAct ca1 = alloc_crit(2, 1), ca2 = alloc_crit(2, 1);   // rows [0,B) a_pi (block 1), [B,2B) data (block 2)
+    CritAct ta1 = alloc_crit(1, 1), ta2 = alloc_crit(1, 1);   // block 3
+    PolGrad pg = alloc_polgrad();
+    { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
+    { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+alpha");
+      s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
+    { Stage& s = add_stage(ST_GEMM, "critic_l1");
+      crit_l1(s, q1, 1, ca1); crit_l1(s, q2, 1, ca2); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
+    { Stage& s = add_stage(ST_GEMM, "critic_l2");
+      crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_sac");
+      memset(&s.chp, 0, sizeof(s.chp));
+      s.chp.src[0] = head_src(q1, ca1, 0); s.chp.src[1] = head_src(q2, ca2, 0);
+      s.chp.src[2] = head_src(q1, ca1, B); s.chp.src[3] = head_src(q2, ca2, B);
+      s.chp.src[4] = head_src(t1, ta1, 0); s.chp.src[5] = head_src(t2, ta2, 0);
+      s.chp.n_src = 6; fill_chp(s, CM_SAC, 2); }
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh2"); crit_dh2(s, q1, ca1, B); crit_dh2(s, q2, ca2, B); }
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); crit_dh1(s, q1, ca1, B); crit_dh1(s, q2, ca2, B); }
+    if (c.stale_graph_mode == 1) {
+        // mode B: the policy-loss dX uses PRE-step critic weights -> run it before the critic Adam
+        { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
+        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
+    }
+    // NB mode B reads fc0.weight's action columns in policy_grad AFTER the Adam stage; to keep
+    // B exact the policy_grad stage is placed before the critic Adam in that mode.
+    auto policy_grad_stage = [&]() {
+        Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
+        PolicyGradTask g; memset(&g, 0, sizeof(g));
+        g.src[0].dh1 = ca1.dh1; g.src[0].w1 = P(net(q1).off_w0); g.src[0].ld = net(q1).in_ld;
+        g.src[1].dh1 = ca2.dh1; g.src[1].w1 = P(net(q2).off_w0); g.src[1].ld = net(q2).in_ld;
+        g.n_src = 2; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = !c.deterministic;
+        s.pg.push_back(g); fill_pgp(s);
+    };
+    if (c.stale_graph_mode == 1) policy_grad_stage();
+    { Stage& s = add_stage(ST_GEMM, "critic_adam");
+      crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
+    if (c.stale_graph_mode == 0) {
+        { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
+        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
+        policy_grad_stage();
+    }
+    { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
+    { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
+    { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
+}
+
+void Builder::build_poac() {
+    // optimizers: 0 policy, 1 alpha, 2.. critics
+    const int n = (int)t.ids.qf.size();
+    t.n_opt = 2 + n;
+    const int pol = t.ids.policy;
+    const int heads = net(t.ids.qf[0]).n_out;
+    PolAct pa = alloc_pol(2);
+    std::vector<CritAct> qa, ta, pa_q;      // data rows (block 2), next rows (block 3), a_pi rows (block 1)
+    for (int i = 0; i < n; ++i) { qa.push_back(alloc_crit(1, heads)); ta.push_back(alloc_crit(1, heads)); pa_q.push_back(alloc_crit(1, heads)); }
+    PolGrad pg = alloc_polgrad();
+    { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
+    { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    // eps slots are named by meaning (0: obs draw, 1: next_obs draw); the reference draws the
+    // next_obs noise FIRST here (:193 then :271) -- the host wrapper maps call order to slots
+    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+alpha");
+      s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 1); }
+    { Stage& s = add_stage(ST_GEMM, "critic_l1");
+      for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
+    { Stage& s = add_stage(ST_GEMM, "critic_l2");
+      for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_poac_q");
+      memset(&s.chp, 0, sizeof(s.chp));
+      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0);
+      for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.tf[i], ta[i], 0);
+      s.chp.n_src = 2 * n; fill_chp(s, CM_POAC_Q, n); }
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], qa[i], 0); }
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], qa[i], 0); }
+    { Stage& s = add_stage(ST_GEMM, "critic_adam");
+      for (int i = 0; i < n; ++i) crit_adam(s, t.ids.qf[i], t.ids.tf[i], qa[i], 0, 2, c.qf_lr, 2 + i); }
+    // policy phase through the UPDATED critics
+    { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 1, pa_q[i]); }
+    { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pa_q[i]); }
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_poac_pi");
+      memset(&s.chp, 0, sizeof(s.chp));
+      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], pa_q[i], 0);
+      s.chp.n_src = n; fill_chp(s, CM_POAC_PI, n); }
+    { Stage& s = add_stage(ST_GEMM, "pi_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], pa_q[i], 0); }
+    { Stage& s = add_stage(ST_GEMM, "pi_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], pa_q[i], 0); }
+    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
+      PolicyGradTask g; memset(&g, 0, sizeof(g));
+      for (int i = 0; i < n; ++i) {
+          g.src[i].dh1 = pa_q[i].dh1; g.src[i].w1 = P(net(t.ids.qf[i]).off_w0); g.src[i].ld = net(t.ids.qf[i]).in_ld;
+      }
+      g.n_src = n; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = !c.deterministic;
+      s.pg.push_back(g); fill_pgp(s); }
+    { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
+    { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
+    { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
+}
+
+void Builder::build_goac() {
+    // optimizers: 0 policy, 1 target_policy, 2 q, 3 std (separate nets), alpha never steps
+    const int n = (int)t.ids.qf.size();       // 1 shared, 2 separate (q, std)
+    t.n_opt = 2 + n;
+    const int pol = t.ids.policy, tpol = t.ids.target_policy;
+    const int heads = net(t.ids.qf[0]).n_out;
+    PolAct pa = alloc_pol(2);                  // policy on obs (block 2), next_obs (block 3)
+    PolAct tpa = alloc_pol(1);                 // target policy on obs (block 2)
+    std::vector<CritAct> qa, ta, pq;           // data (block 2) | next (block 3) | policy phase blocks 0,1 (2B rows)
+    for (int i = 0; i < n; ++i) { qa.push_back(alloc_crit(1, heads)); ta.push_back(alloc_crit(1, heads)); pq.push_back(alloc_crit(2, heads)); }
+    PolGrad pg = alloc_polgrad(), tpg = alloc_polgrad();
+    { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); pol_l1(s, tpol, 2, tpa); }
+    { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); pol_l2(s, tpol, tpa); }
+    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head");
+      s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1));
+      s.ph.push_back(ph_task(tpol, tpa, 2 * B, 0, 0, 0, 0));
+      fill_php(s, 0, 0, 0); s.php.alpha.enabled = 0; s.php.deterministic = 1; }
+    { Stage& s = add_stage(ST_GEMM, "critic_l1");
+      for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
+    { Stage& s = add_stage(ST_GEMM, "critic_l2");
+      for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_goac_q");
+      memset(&s.chp, 0, sizeof(s.chp));
+      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0);
+      for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.tf[i], ta[i], 0);
+      s.chp.n_src = 2 * n; fill_chp(s, CM_GOAC_Q, n); }
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], qa[i], 0); }
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], qa[i], 0); }
+    { Stage& s = add_stage(ST_GEMM, "critic_adam");
+      for (int i = 0; i < n; ++i)
+          crit_adam(s, t.ids.qf[i], t.ids.tf[i], qa[i], 0, 2, i == 0 ? c.qf_lr : c.std_lr, 2 + i); }
+    // policy (rows [B,2B) = block 1) and target policy (rows [0,B) = block 0) through the updated critic
+    { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 0, pq[i]); }
+    { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pq[i]); }
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_goac_pi");
+      memset(&s.chp, 0, sizeof(s.chp));
+      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], pq[i], B);        // a_pi rows
+      for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.qf[i], pq[i], 0);    // a_tp rows
+      s.chp.n_src = 2 * n; fill_chp(s, CM_GOAC_PI, n); }
+    { Stage& s = add_stage(ST_GEMM, "pi_dh2");
+      for (int i = 0; i < n; ++i) { crit_dh2(s, t.ids.qf[i], pq[i], 0); crit_dh2(s, t.ids.qf[i], pq[i], B); } }
+    { Stage& s = add_stage(ST_GEMM, "pi_dh1");
+      for (int i = 0; i < n; ++i) { crit_dh1(s, t.ids.qf[i], pq[i], 0); crit_dh1(s, t.ids.qf[i], pq[i], B); } }
+    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
+      PolicyGradTask g; memset(&g, 0, sizeof(g));
+      PolicyGradTask gt; memset(&gt, 0, sizeof(gt));
+      for (int i = 0; i < n; ++i) {
+          const OacNetLayout& qn = net(t.ids.qf[i]);
+          g.src[i].dh1 = Ref{pq[i].dh1.arena, pq[i].dh1.off + (long long)B * H}; g.src[i].w1 = P(qn.off_w0); g.src[i].ld = qn.in_ld;
+          gt.src[i].dh1 = pq[i].dh1; gt.src[i].w1 = P(qn.off_w0); gt.src[i].ld = qn.in_ld;
+      }
+      g.n_src = n; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = 0;
+      gt.n_src = n; gt.save = tpa.save; gt.save_row0 = 0; gt.dhead = tpg.dhead; gt.entropy = 0;
+      s.pg.push_back(g); s.pg.push_back(gt); fill_pgp(s); }
+    { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); pol_dh2(s, tpol, tpa, 0, tpg); }
+    { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); pol_dh1(s, tpol, tpa, 0, tpg); }
+    { Stage& s = add_stage(ST_GEMM, "policy_adam");
+      pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); pol_adam(s, tpol, tpa, 0, 2, tpg, c.policy_lr, 1); }
+}
+
+// ------------------------------------------------------------------------------------
+// finalize: tile counts, device tables
+// ------------------------------------------------------------------------------------
+template <typename T>
+static int upload(OacTrainer& t, const T* host, size_t count, void** dev) {
+    OAC_CUDA(cudaMalloc(dev, sizeof(T) * count));
+    t.dev_allocs.push_back(*dev);
+    OAC_CUDA(cudaMemcpy(*dev, host, sizeof(T) * count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int finalize(OacTrainer& t) {
+    const int seeds = t.cfg.n_seeds;
+    for (Stage& s : t.stages) {
+        if (s.kind == ST_GEMM) {
+            long long tiles64 = 0;
+            for (auto& g : s.gemm) tiles64 += (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
+            s.small_tiles = (tiles64 * seeds < 200);
+            const int bm = s.small_tiles ? 32 : 64;
+            s.max_tiles = 0;
+            for (auto& g : s.gemm) {
+                g.tiles_m = (g.M + bm - 1) / bm; g.tiles_n = (g.N + bm - 1) / bm;
+                s.max_tiles = std::max(s.max_tiles, g.tiles_m * g.tiles_n);
+            }
+            if (int e = upload(t, s.gemm.data(), s.gemm.size(), &s.dev)) return e;
+        } else if (s.kind == ST_POLICY_HEAD) {
+            s.max_rows = 0;
+            for (auto& p : s.ph) s.max_rows = std::max(s.max_rows, p.rows);
+            if (int e = upload(t, s.ph.data(), s.ph.size(), &s.dev)) return e;
+            s.php.tasks = (const PolicyHeadTask*)s.dev;
+            s.php.as = t.as; s.php.hyper = t.hyper;
+        } else if (s.kind == ST_CRITIC_HEAD) {
+            s.chp.as = t.as;
+            if (int e = upload(t, &s.chp, 1, &s.dev)) return e;
+        } else if (s.kind == ST_POLICY_GRAD) {
+            if (int e = upload(t, s.pg.data(), s.pg.size(), &s.dev)) return e;
+            s.pgp.tasks = (const PolicyGradTask*)s.dev;
+            s.pgp.as = t.as;
+        }
+    }
+    return 0;
+}
+
+static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
+    const int seeds = t.cfg.n_seeds;
+    for (Stage& s : t.stages) {
+        if (s.kind == ST_GEMM) {
+            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper;
+            dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
+            if (s.small_tiles) gemm_stage_kernel<32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(sp);
+            else gemm_stage_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(sp);
+        } else if (s.kind == ST_POLICY_HEAD) {
+            PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps;
+            dim3 grid((s.max_rows + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.ph.size(), seeds);
+            policy_head_kernel<<<grid, GLUE_THREADS, 0, st>>>(p);
+        } else if (s.kind == ST_CRITIC_HEAD) {
+            dim3 grid((t.cfg.batch + GLUE_WARPS - 1) / GLUE_WARPS, seeds, 1);
+            critic_head_kernel<<<grid, GLUE_THREADS, 0, st>>>((const CriticHeadParams*)s.dev);
+        } else {
+            dim3 grid((t.cfg.batch + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.pg.size(), seeds);
+            size_t smem = sizeof(float) * (size_t)t.cfg.hidden * t.cfg.act_dim;
+            policy_grad_kernel<<<grid, GLUE_THREADS, smem, st>>>(s.pgp);
+        }
+        OAC_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace oac
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" int oac_trainer_layout(const OacConfig* cfg, OacLayout* out) {
+    if (!cfg || !out) return set_error(OAC_E_INVALID, "null argument");
+    OacTrainer tmp;
+    tmp.cfg = *cfg;
+    NetIds ids;
+    if (int e = build_layout(*cfg, tmp.lay, ids)) return e;
+    tmp.ids = ids;
+    Builder b(tmp);
+    if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
+    else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
+    else b.build_goac();
+    tmp.lay.work_floats = tmp.work_cursor;
+    *out = tmp.lay;
+    return 0;
+}
+
+extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, OacTrainer** out) {
+    if (!cfg || !buf || !out) return set_error(OAC_E_INVALID, "null argument");
+    if (!buf->params || !buf->adam_m || !buf->adam_v || !buf->work || !buf->io || !buf->counters)
+        return set_error(OAC_E_INVALID, "null buffer");
+    if (cfg->gemm_path != OAC_GEMM_FP32) return set_error(OAC_E_UNSUPPORTED, "gemm_path: only OAC_GEMM_FP32 is built");
+    OacTrainer* t = new OacTrainer();
+    t->cfg = *cfg;
+    if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
+    Builder b(*t);
+    if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
+    else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
+    else b.build_goac();
+    t->lay.work_floats = t->work_cursor;
+    const OacLayout& L = t->lay;
+    if (cfg->hidden * cfg->act_dim * sizeof(float) > 200 * 1024) { delete t; return set_error(OAC_E_UNSUPPORTED, "hidden*act_dim too large"); }
+    t->as.base[AR_PARAM] = buf->params;  t->as.stride[AR_PARAM] = L.param_floats;
+    t->as.base[AR_ADAM_M] = buf->adam_m; t->as.stride[AR_ADAM_M] = L.adam_floats;
+    t->as.base[AR_ADAM_V] = buf->adam_v; t->as.stride[AR_ADAM_V] = L.adam_floats;
+    t->as.base[AR_WORK] = buf->work;     t->as.stride[AR_WORK] = L.work_floats;
+    t->as.base[AR_IO] = buf->io;         t->as.stride[AR_IO] = L.io_floats;
+    t->as.counters = buf->counters;      t->as.n_counters = L.n_counters;
+    t->hyper.beta1 = cfg->adam_beta1; t->hyper.beta2 = cfg->adam_beta2; t->hyper.eps = cfg->adam_eps;
+    t->hyper.tau = cfg->soft_target_tau;
+    t->hyper.one_minus_tau = (float)(1.0 - (double)cfg->soft_target_tau);
+    t->hyper.target_period = cfg->target_update_period > 0 ? cfg->target_update_period : 1;
+    {   // the Python double tau (e.g. 5e-3) is not representable in fp32: recover it like the betas
+        double tau = rint((double)cfg->soft_target_tau * 1e9) * 1e-9;
+        t->hyper.one_minus_tau = (float)(1.0 - tau);
+    }
+    size_t pg_smem = sizeof(float) * (size_t)cfg->hidden * cfg->act_dim;
+    if (pg_smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(policy_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pg_smem);
+        if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
+    }
+    if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
+    const char* ng = getenv("OAC_NO_GRAPH");
+    t->use_graph = !(ng && ng[0] == '1');
+    *out = t;
+    return 0;
+}
+
+extern "C" int oac_trainer_destroy(OacTrainer* t) {
+    if (!t) return 0;
+    for (int i = 0; i < 2; ++i) if (t->graph[i]) cudaGraphExecDestroy(t->graph[i]);
+    for (void* p : t->dev_allocs) cudaFree(p);
+    delete t;
+    return 0;
+}
+
+extern "C" int oac_trainer_launches_per_step(const OacTrainer* t) {
+    return t ? (int)t->stages.size() : 0;
+}
+
+extern "C" int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* stream) {
+    if (!t) return set_error(OAC_E_INVALID, "null trainer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gi = use_external_eps ? 1 : 0;
+    if (!t->use_graph) return launch_stages(*t, gi, st);
+    if (!t->graph[gi]) {
+        // capture on a private stream so the caller's stream state is untouched
+        cudaStream_t cs;
+        OAC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { cudaStreamDestroy(cs); return set_cuda_error(e, "cudaStreamBeginCapture"); }
+        int rc = launch_stages(*t, gi, cs);
+        e = cudaStreamEndCapture(cs, &g);
+        cudaStreamDestroy(cs);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamEndCapture");
+        e = cudaGraphInstantiate(&t->graph[gi], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaGraphInstantiate");
+    }
+    OAC_CUDA(cudaGraphLaunch(t->graph[gi], st));
+    return 0;
+}

@@ -1,0 +1,194 @@
+// GPU-resident replay buffer: ReplayBuffer.random_batch as one coalesced row-gather
+// (replay_buffer.py:106-115), ReplayBufferCount counts (:180-197) and the ring append
+// (:88-104).  HBM-bound byte movement: one CTA per sampled transition, 128-bit loads and
+// stores when the row bases are 16-byte aligned, scalar otherwise.  The f64->f32 cast of
+// utils/core.py:45 is done once at insert time, so gathered batches are bit-exact copies
+// of float32(store rows).
+#include <cuda_runtime.h>
+
+#include "oac_error.h"
+#include "../../include/oac_b200.h"
+
+namespace oac {
+
+constexpr int GATHER_THREADS = 128;
+
+__device__ __forceinline__ void copy_row(float* __restrict__ dst, const float* __restrict__ src, int n,
+                                         int tid, int nthreads) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+    if (vec) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < n4; i += nthreads) d4[i] = __ldg(s4 + i);
+        for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
+    }
+}
+
+// one source row feeding up to three destinations (the obs copies of X blocks 0/1/2)
+__device__ __forceinline__ void copy_row3(float* d0, float* d1, float* d2, const float* __restrict__ src, int n,
+                                          int tid, int nthreads) {
+    uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(d0);
+    if (d1) al |= reinterpret_cast<uintptr_t>(d1);
+    if (d2) al |= reinterpret_cast<uintptr_t>(d2);
+    if ((al & 15) == 0) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int i = tid; i < n4; i += nthreads) {
+            float4 v = __ldg(s4 + i);
+            reinterpret_cast<float4*>(d0)[i] = v;
+            if (d1) reinterpret_cast<float4*>(d1)[i] = v;
+            if (d2) reinterpret_cast<float4*>(d2)[i] = v;
+        }
+        for (int i = (n4 << 2) + tid; i < n; i += nthreads) {
+            float v = __ldg(src + i);
+            d0[i] = v; if (d1) d1[i] = v; if (d2) d2[i] = v;
+        }
+    } else {
+        for (int i = tid; i < n; i += nthreads) {
+            float v = __ldg(src + i);
+            d0[i] = v; if (d1) d1[i] = v; if (d2) d2[i] = v;
+        }
+    }
+}
+
+struct GatherArgs {
+    OacReplayStore st;
+    OacBatchDst dst;
+    const int64_t* idx;
+    int batch;
+};
+
+__global__ void __launch_bounds__(GATHER_THREADS) replay_gather_kernel(GatherArgs a) {
+    const int i = blockIdx.x;                 // sample within the batch
+    const int s = blockIdx.y;                 // seed
+    const int B = a.batch, O = a.st.obs_dim, A = a.st.act_dim;
+    const long long r = a.idx[(long long)s * B + i];
+    const long long so = (long long)s * a.dst.seed_stride;
+    float* x = a.dst.x + so;
+    const int ld = a.dst.x_ld;
+    auto xrow = [&](int block) -> float* { return block < 0 ? nullptr : x + ((long long)block * B + i) * ld; };
+    float* d0 = xrow(a.dst.obs_blocks[0]);
+    float* d1 = xrow(a.dst.obs_blocks[1]);
+    float* d2 = xrow(a.dst.obs_blocks[2]);
+    copy_row3(d0, d1, d2, a.st.obs + r * O, O, threadIdx.x, GATHER_THREADS);
+    copy_row(xrow(a.dst.next_block), a.st.next_obs + r * O, O, threadIdx.x, GATHER_THREADS);
+    {
+        float* da = xrow(a.dst.act_block) + O;
+        const float* sa = a.st.actions + r * A;
+        for (int j = threadIdx.x; j < A; j += GATHER_THREADS) da[j] = __ldg(sa + j);
+    }
+    if (threadIdx.x == 0) {
+        a.dst.rewards[so + i] = __ldg(a.st.rewards + r);
+        a.dst.terminals[so + i] = __ldg(a.st.terminals + r);
+        if (a.st.counts && a.dst.counts) a.dst.counts[so + i] = a.st.counts[r];
+    }
+}
+
+// counts[idx] += 1 once per DISTINCT index (numpy fancy-index "+=", replay_buffer.py:195)
+__global__ void replay_counts_bump_kernel(float* counts, const int64_t* idx, int batch) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const long long r = idx[i];
+    for (int j = 0; j < i; ++j)
+        if (idx[j] == r) return;          // an earlier occurrence owns the increment
+    counts[r] += 1.0f;
+}
+
+struct DenseArgs {
+    OacReplayStore st;
+    const int64_t* idx;
+    float *obs, *actions, *rewards, *terminals, *next_obs, *counts_out;
+    int batch;
+};
+
+__global__ void __launch_bounds__(GATHER_THREADS) replay_gather_dense_kernel(DenseArgs a) {
+    const int i = blockIdx.x;
+    const int O = a.st.obs_dim, A = a.st.act_dim;
+    const long long r = a.idx[i];
+    copy_row(a.obs + (long long)i * O, a.st.obs + r * O, O, threadIdx.x, GATHER_THREADS);
+    copy_row(a.next_obs + (long long)i * O, a.st.next_obs + r * O, O, threadIdx.x, GATHER_THREADS);
+    copy_row(a.actions + (long long)i * A, a.st.actions + r * A, A, threadIdx.x, GATHER_THREADS);
+    if (threadIdx.x == 0) {
+        a.rewards[i] = __ldg(a.st.rewards + r);
+        a.terminals[i] = __ldg(a.st.terminals + r);
+        if (a.st.counts && a.counts_out) a.counts_out[i] = a.st.counts[r];
+    }
+}
+
+struct AddArgs {
+    float *obs, *next_obs, *actions, *rewards, *terminals, *counts;
+    const float* rows;
+    long long capacity, top;
+    int O, A, n;
+};
+
+__global__ void __launch_bounds__(GATHER_THREADS) replay_add_kernel(AddArgs a) {
+    const int i = blockIdx.x;
+    const long long slot = (a.top + i) % a.capacity;
+    const int W = 2 * a.O + a.A + 2;
+    const float* row = a.rows + (long long)i * W;
+    // n > capacity: a later row overwrites an earlier one; only the last writer of a slot may run
+    if ((long long)i + a.capacity < (long long)a.n) return;
+    for (int j = threadIdx.x; j < a.O; j += GATHER_THREADS) {
+        a.obs[slot * a.O + j] = row[j];
+        a.next_obs[slot * a.O + j] = row[a.O + a.A + 2 + j];
+    }
+    for (int j = threadIdx.x; j < a.A; j += GATHER_THREADS) a.actions[slot * a.A + j] = row[a.O + j];
+    if (threadIdx.x == 0) {
+        a.rewards[slot] = row[a.O + a.A];
+        a.terminals[slot] = row[a.O + a.A + 1];
+        if (a.counts) a.counts[slot] = 0.f;
+    }
+}
+
+}  // namespace oac
+
+using namespace oac;
+
+extern "C" int oac_replay_gather(const OacReplayStore* store, const int64_t* indices, int32_t batch,
+                                 const OacBatchDst* dst, void* stream) {
+    if (!store || !indices || !dst || batch < 1) return set_error(OAC_E_INVALID, "oac_replay_gather: bad argument");
+    if (dst->obs_blocks[0] < 0 || dst->act_block < 0 || dst->next_block < 0)
+        return set_error(OAC_E_INVALID, "oac_replay_gather: destination blocks unset");
+    const int seeds = dst->n_seeds > 0 ? dst->n_seeds : 1;
+    if (store->counts && seeds > 1) return set_error(OAC_E_UNSUPPORTED, "counts with a store shared by several seeds");
+    GatherArgs a{*store, *dst, indices, batch};
+    cudaStream_t st = (cudaStream_t)stream;
+    replay_gather_kernel<<<dim3(batch, seeds), GATHER_THREADS, 0, st>>>(a);
+    OAC_CUDA(cudaGetLastError());
+    if (store->counts) {
+        replay_counts_bump_kernel<<<(batch + 127) / 128, 128, 0, st>>>(store->counts, indices, batch);
+        OAC_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int oac_replay_gather_dense(const OacReplayStore* store, const int64_t* indices, int32_t batch,
+                                       float* obs, float* actions, float* rewards, float* terminals,
+                                       float* next_obs, float* counts_out, void* stream) {
+    if (!store || !indices || batch < 1 || !obs || !actions || !rewards || !terminals || !next_obs)
+        return set_error(OAC_E_INVALID, "oac_replay_gather_dense: bad argument");
+    DenseArgs a{*store, indices, obs, actions, rewards, terminals, next_obs, counts_out, batch};
+    cudaStream_t st = (cudaStream_t)stream;
+    replay_gather_dense_kernel<<<batch, GATHER_THREADS, 0, st>>>(a);
+    OAC_CUDA(cudaGetLastError());
+    if (store->counts) {
+        replay_counts_bump_kernel<<<(batch + 127) / 128, 128, 0, st>>>(store->counts, indices, batch);
+        OAC_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int oac_replay_add(float* obs, float* next_obs, float* actions, float* rewards, float* terminals,
+                              float* counts, int64_t capacity, int32_t obs_dim, int32_t act_dim,
+                              const float* rows, int32_t n, int64_t top, void* stream) {
+    if (!obs || !next_obs || !actions || !rewards || !terminals || !rows || n < 1 || capacity < 1)
+        return set_error(OAC_E_INVALID, "oac_replay_add: bad argument");
+    AddArgs a{obs, next_obs, actions, rewards, terminals, counts, rows, capacity, top, obs_dim, act_dim, n};
+    replay_add_kernel<<<n, GATHER_THREADS, 0, (cudaStream_t)stream>>>(a);
+    OAC_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,256 @@
+"""GPU-resident replay buffer: drop-in for the reference's ``replay_buffer.py``.
+
+Same constructor and methods (``add_sample``, ``add_path(s)``, ``random_batch``,
+``num_steps_can_sample``, ``get_dataset``, ``get_diagnostics``, ``end_epoch``,
+``get_snapshot``, ``restore_from_snapshot``; replay_buffer.py:8-148, 151-203).  The store is
+struct-of-arrays fp32 in HBM (the f64->f32 cast of utils/core.py:45 happens once, at insert);
+``random_batch`` draws its indices from the SAME global numpy stream as the reference
+(``np.random.randint(0, size, B)``, replay_buffer.py:107) and gathers them with one coalesced
+kernel (``oac_replay_gather``), straight into the attached trainer's batch rows when there is
+one.  Without an attached trainer it returns the reference's numpy dict (f64 / uint8), so the
+reference's own trainers keep working.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OacReplayStore, OacBatchDst
+from .networks import _device
+
+
+def get_dim(space):
+    """utils/env_utils.py:8-18 (Box / Discrete / Tuple / flat_dim)."""
+    if hasattr(space, 'low') and hasattr(space.low, 'size'):
+        return space.low.size
+    if hasattr(space, 'n'):
+        return space.n
+    if hasattr(space, 'spaces'):
+        return sum(get_dim(s) for s in space.spaces)
+    if hasattr(space, 'flat_dim'):
+        return space.flat_dim
+    raise TypeError("Unknown space: {}".format(space))
+
+
+class ReplayBuffer(object):
+    STAGE_ROWS = 4096
+
+    def __init__(self, max_replay_buffer_size, ob_space, action_space):
+        self._ob_space, self._action_space = ob_space, action_space
+        O, A = get_dim(ob_space), get_dim(action_space)
+        N = int(max_replay_buffer_size)
+        self._ob_dim, self._ac_dim = O, A
+        self._max_replay_buffer_size = N
+        self._lib = _lib.lib()
+        dev = _device()
+        self._device = dev
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self._observations, self._next_obs, self._actions = z(N, O), z(N, O), z(N, A)
+        self._rewards, self._terminals = z(N, 1), z(N, 1)
+        self._counts_dev = None
+        self._top = 0
+        self._size = 0
+        # host staging for add_sample: rows = obs | action | reward | terminal | next_obs
+        self._W = 2 * O + A + 2
+        self._stage = torch.zeros((self.STAGE_ROWS, self._W), dtype=torch.float32).pin_memory()
+        self._stage_np = self._stage.numpy()
+        self._stage_dev = torch.zeros((self.STAGE_ROWS, self._W), dtype=torch.float32, device=dev)
+        self._n_staged = 0
+        self._stage_top = 0
+        self._idx_host = None
+        self._idx_dev = None
+        self._trainer = None
+
+    # ---- insert path (replay_buffer.py:50-104) -------------------------------------
+    def add_path(self, path):
+        for obs, action, reward, next_obs, terminal, agent_info, env_info in zip(
+                path["observations"], path["actions"], path["rewards"], path["next_observations"],
+                path["terminals"], path["agent_infos"], path["env_infos"]):
+            self.add_sample(observation=obs, action=action, reward=reward, next_observation=next_obs,
+                            terminal=terminal, agent_info=agent_info, env_info=env_info)
+
+    def add_paths(self, paths):
+        for path in paths:
+            self.add_path(path)
+
+    def add_sample(self, observation, action, reward, next_observation, terminal, env_info=None, **kwargs):
+        if hasattr(self._action_space, 'n') and not hasattr(self._action_space, 'low'):
+            raise AssertionError("discrete action spaces are not supported (replay_buffer.py:91)")
+        if self._n_staged == 0:
+            self._stage_top = self._top
+        O, A = self._ob_dim, self._ac_dim
+        row = self._stage_np[self._n_staged]
+        row[:O] = np.asarray(observation, dtype=np.float64).reshape(-1)
+        row[O:O + A] = np.asarray(action, dtype=np.float64).reshape(-1)
+        row[O + A] = np.asarray(reward, dtype=np.float64).reshape(-1)[0]
+        row[O + A + 1] = np.uint8(np.asarray(terminal).reshape(-1)[0])   # uint8 store (replay_buffer.py:45)
+        row[O + A + 2:] = np.asarray(next_observation, dtype=np.float64).reshape(-1)
+        self._n_staged += 1
+        self._advance()
+        if self._n_staged == self.STAGE_ROWS:
+            self._flush()
+
+    def _advance(self):
+        self._top = (self._top + 1) % self._max_replay_buffer_size
+        if self._size < self._max_replay_buffer_size:
+            self._size += 1
+
+    def _flush(self):
+        n = self._n_staged
+        if n == 0:
+            return
+        stream = torch.cuda.current_stream()
+        self._stage_dev[:n].copy_(self._stage[:n], non_blocking=True)
+        _lib.check(self._lib.oac_replay_add(
+            _lib.ptr(self._observations), _lib.ptr(self._next_obs), _lib.ptr(self._actions),
+            _lib.ptr(self._rewards), _lib.ptr(self._terminals), _lib.ptr(self._counts_dev),
+            self._max_replay_buffer_size, self._ob_dim, self._ac_dim, _lib.ptr(self._stage_dev), n,
+            self._stage_top, C.c_void_p(stream.cuda_stream)), "oac_replay_add")
+        stream.synchronize()          # the pinned staging rows are reused by the next add_sample
+        self._n_staged = 0
+
+    # ---- sample path (replay_buffer.py:106-115) ----------------------------------------
+    def attach(self, trainer):
+        """Later ``random_batch`` calls gather straight into ``trainer``'s batch rows."""
+        self._trainer = trainer
+
+    def _store(self):
+        return OacReplayStore(_lib.ptr(self._observations), _lib.ptr(self._next_obs), _lib.ptr(self._actions),
+                              _lib.ptr(self._rewards), _lib.ptr(self._terminals), _lib.ptr(self._counts_dev),
+                              self._max_replay_buffer_size, self._ob_dim, self._ac_dim)
+
+    def _draw_indices(self, batch_size):
+        return np.random.randint(0, self._size, batch_size)
+
+    def _upload_indices(self, indices):
+        n = len(indices)
+        if self._idx_host is None or self._idx_host.shape[0] < n:
+            self._idx_host = torch.zeros(n, dtype=torch.int64).pin_memory()
+            self._idx_dev = torch.zeros(n, dtype=torch.int64, device=self._device)
+        self._idx_host.numpy()[:n] = indices
+        self._idx_dev[:n].copy_(self._idx_host[:n], non_blocking=True)
+        return self._idx_dev
+
+    def gather_into(self, engine, indices_dev, batch_size, seed=0, n_seeds=1):
+        L = engine.lay
+        dst = OacBatchDst()
+        dst.x = engine.io[seed, L.off_x:].data_ptr()
+        dst.x_ld = L.x_ld
+        goac = engine.cfg.algo == _lib.ALGO_GOAC
+        dst.obs_blocks[0], dst.obs_blocks[1], dst.obs_blocks[2] = 1, 2, (0 if goac else -1)
+        dst.act_block, dst.next_block = 2, 3
+        dst.rewards = engine.io[seed, L.off_rewards:].data_ptr()
+        dst.terminals = engine.io[seed, L.off_terminals:].data_ptr()
+        dst.counts = engine.io[seed, L.off_counts:].data_ptr() if self._counts_dev is not None else None
+        dst.n_seeds, dst.seed_stride = n_seeds, L.io_floats
+        st = self._store()
+        _lib.check(self._lib.oac_replay_gather(C.byref(st), _lib.ptr(indices_dev), batch_size, C.byref(dst),
+                                               _lib.current_stream()), "oac_replay_gather")
+
+    def random_batch(self, batch_size):
+        self._flush()
+        indices = self._draw_indices(batch_size)
+        idx_dev = self._upload_indices(indices)
+        tr = self._trainer
+        if tr is not None:
+            tr._ensure_engine(batch_size)
+            e = tr._engine
+            self.gather_into(e, idx_dev, batch_size)
+            O, A = self._ob_dim, self._ac_dim
+            xb2, L = e.x_block(2), e.lay
+            batch = dict(observations=xb2[:, :O], actions=xb2[:, O:O + A],
+                         rewards=e.io_view(L.off_rewards, (batch_size, 1)),
+                         terminals=e.io_view(L.off_terminals, (batch_size, 1)),
+                         next_observations=e.x_block(3)[:, :O], _oac_resident=e)
+            if self._counts_dev is not None:
+                batch['counts'] = e.io_view(L.off_counts, (batch_size, 1))
+            return batch
+        return self._numpy_batch(self.gather_dense(idx_dev, batch_size))
+
+    def gather_dense(self, idx_dev, batch_size):
+        """Five dense fp32 device tensors (the "fast" return type of SURVEY.md section 8b)."""
+        O, A, dev = self._ob_dim, self._ac_dim, self._device
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        out = dict(observations=mk(batch_size, O), actions=mk(batch_size, A), rewards=mk(batch_size, 1),
+                   terminals=mk(batch_size, 1), next_observations=mk(batch_size, O))
+        if self._counts_dev is not None:
+            out['counts'] = mk(batch_size, 1)
+        st = self._store()
+        _lib.check(self._lib.oac_replay_gather_dense(
+            C.byref(st), _lib.ptr(idx_dev), batch_size, _lib.ptr(out['observations']), _lib.ptr(out['actions']),
+            _lib.ptr(out['rewards']), _lib.ptr(out['terminals']), _lib.ptr(out['next_observations']),
+            _lib.ptr(out.get('counts')), _lib.current_stream()), "oac_replay_gather_dense")
+        return out
+
+    @staticmethod
+    def _numpy_batch(dev_batch):
+        """The reference's return type: float64 arrays, uint8 terminals (replay_buffer.py:32-45)."""
+        out = {}
+        for k, v in dev_batch.items():
+            a = v.to('cpu').numpy()
+            out[k] = a.astype(np.uint8) if k == 'terminals' else a.astype(np.float64)
+        return out
+
+    # ---- misc (replay_buffer.py:117-148) -----------------------------------------------
+    def get_dataset(self):
+        self._flush()
+        return self._observations[:self._size].to('cpu').numpy().astype(np.float64)
+
+    def num_steps_can_sample(self):
+        return self._size
+
+    def get_diagnostics(self):
+        return OrderedDict([('size', self._size)])
+
+    def end_epoch(self, epoch):
+        return
+
+    _SNAP = ('_observations', '_next_obs', '_actions', '_rewards', '_terminals')
+
+    def get_snapshot(self):
+        self._flush()
+        ss = {k: getattr(self, k).to('cpu').numpy() for k in self._SNAP}
+        ss['_terminals'] = ss['_terminals'].astype(np.uint8)
+        ss['_top'], ss['_size'] = self._top, self._size
+        return ss
+
+    def restore_from_snapshot(self, ss):
+        self._n_staged = 0
+        for key in ss.keys():
+            assert hasattr(self, key) or key == '_counts'
+            if key in ('_top', '_size'):
+                setattr(self, key, int(ss[key]))
+            elif key == '_counts':
+                self._counts_dev.copy_(torch.as_tensor(np.asarray(ss[key], dtype=np.float32)).to(self._device))
+            else:
+                dst = getattr(self, key)
+                dst.copy_(torch.as_tensor(np.asarray(ss[key], dtype=np.float32)).to(self._device).reshape(dst.shape))
+
+
+class ReplayBufferCount(ReplayBuffer):
+    """replay_buffer.py:151-203: per-slot sample counts, returned with the batch and bumped
+    once per distinct sampled slot; ``add_sample`` zeroes the slot."""
+
+    def __init__(self, max_replay_buffer_size, ob_space, action_space, priority_sample=False):
+        super().__init__(max_replay_buffer_size, ob_space, action_space)
+        self._counts_dev = torch.zeros((int(max_replay_buffer_size), 1), dtype=torch.float32, device=self._device)
+        self.priority_sample = priority_sample
+
+    @property
+    def _counts(self):
+        return self._counts_dev.to('cpu').numpy().astype(np.float64)
+
+    def _draw_indices(self, batch_size):
+        if self.priority_sample:
+            # replay_buffer.py:181-185 (host-side: needs the whole count vector)
+            probs = 1 / (self._counts[:self._size] + 1)
+            probs /= probs.sum()
+            return np.random.choice(np.arange(self._size), size=batch_size, p=probs[:, 0])
+        return np.random.randint(0, self._size, batch_size)
+
+    def get_snapshot(self):
+        ss = super().get_snapshot()
+        ss['_counts'] = self._counts
+        return ss
