@@ -183,6 +183,12 @@ int oac_trainer_destroy(OacTrainer* t);
 int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* stream);
 /* Number of kernel launches one step issues (for bench.py's gpu_launches). */
 int oac_trainer_launches_per_step(const OacTrainer* t);
+/* Measurement aid: runs `iters` steps stage by stage (no graph) with a CUDA event between
+ * stages and returns the mean duration of each stage in milliseconds (ms[n_stages]) and, per
+ * stage, whether it is a GEMM stage (is_gemm) and its algorithmic FLOPs per seed (flops).
+ * names: n_stages pointers to static strings.  Synchronises the stream. */
+int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_stages, float* ms, int32_t* is_gemm,
+                        double* flops, const char** names, int32_t* n_stages, void* stream);
 
 /* ---- inference ---- */
 /* TanhGaussianPolicy.forward on n rows: obs [n, obs_ld]; eps [n,A] or NULL (deterministic).

@@ -4,11 +4,14 @@
 //     C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
 // with either operand stored K-contiguous or M/N-contiguous, so the same kernel
 // runs forward (X W^T), dX (dY W) and dW (dY^T X) products without transposed
-// copies.  Epilogues fuse bias+ReLU, the ReLU-derivative mask and, for dW tasks,
-// the Adam update of the weight block (+ its bias from the column sums of A) and
-// the Polyak update of the target copy, so every weight / moment is touched once
-// per step (reference: 26 addmm + 29 mm + ~150 Adam + 48 Polyak launches,
-// SURVEY.md section 2.2).
+// copies.  The contraction lengths on this path are short (K <= 400), so a CTA
+// stages the WHOLE K extent of its A and B tiles in shared memory with one burst of
+// cp.async (every byte in flight at once: one DRAM/L2 latency per stage instead of
+// one per k-tile), then runs the FFMA loop without further barriers.  Epilogues fuse
+// bias+ReLU, the ReLU-derivative mask and, for dW tasks, the Adam update of the
+// weight block (+ its bias from the column sums of A) and the Polyak update of the
+// target copy, so every weight / moment is touched once per step (reference:
+// 26 addmm + 29 mm + ~150 Adam + 48 Polyak launches).
 #pragma once
 #include "oac_internal.h"
 
@@ -18,6 +21,7 @@ struct StageParams {
     const GemmTask* tasks;    // device
     ArenaSet as;
     AdamHyper hyper;
+    int kc;                   // K chunk staged per pass (multiple of 4; >= K when it fits)
 };
 
 __device__ __forceinline__ float relu(float x) { return x > 0.f ? x : 0.f; }
@@ -67,45 +71,65 @@ __device__ __forceinline__ void adam_update(float g, float* __restrict__ p, floa
     }
 }
 
-// Loads a ROWSxCOLS tile slice as float4 along the contiguous dimension.
-// contiguous index c in [0,C), strided index r in [0,R): element at src[r*ld + c].
-__device__ __forceinline__ float4 load4_guard(const float* __restrict__ src, int ld, int r, int c,
-                                              int R, int C, bool vec_ok) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < R) {
-        const float* p = src + (long long)r * ld + c;
-        if (vec_ok && c + 3 < C) {
-            v = *reinterpret_cast<const float4*>(p);
-        } else {
-            if (c + 0 < C) v.x = p[0];
-            if (c + 1 < C) v.y = p[1];
-            if (c + 2 < C) v.z = p[2];
-            if (c + 3 < C) v.w = p[3];
+// ---- cp.async helpers ----
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// row stride (floats) of a K-contiguous operand tile: a multiple of 4 that is 4 mod 8, so that 8
+// consecutive rows' float4 at the same k fall into 8 distinct 4-bank groups (conflict-free LDS.128)
+__host__ __device__ inline int kpad_of(int kc) { int p = (kc + 3) & ~3; return (p & 4) ? p : p + 4; }
+
+// Stages rows [r0, r0+R) x contiguous [c0, c0+CW) of a strided matrix (element (r,c) at src[r*ld+c])
+// into smem (row stride sld).  Out-of-range elements are zero-filled.
+template <int NT>
+__device__ __forceinline__ void stage_tile(float* __restrict__ sm, int sld, const float* __restrict__ src, int ld,
+                                           int r0, int R, int rmax, int c0, int CW, int cmax, bool vec_ok) {
+    const int tid = threadIdx.x;
+    if (vec_ok) {
+        const int cpr = (CW + 3) >> 2;
+        const int total = R * cpr;
+        for (int c = tid; c < total; c += NT) {
+            const int r = c / cpr, q = (c - r * cpr) << 2;
+            const int gr = r0 + r, gc = c0 + q;
+            int bytes = 0;
+            const float* p = src;
+            if (gr < rmax && gc < cmax) {
+                bytes = min(16, (cmax - gc) * 4);
+                p = src + (long long)gr * ld + gc;
+            }
+            cp_async16_zfill(sm + r * sld + q, p, bytes);
+        }
+    } else {
+        const int cw4 = (CW + 3) & ~3;
+        const int total = R * cw4;
+        for (int c = tid; c < total; c += NT) {
+            const int r = c / cw4, q = c - r * cw4;
+            const int gr = r0 + r, gc = c0 + q;
+            if (gr < rmax && gc < cmax) cp_async4(sm + r * sld + q, src + (long long)gr * ld + gc);
+            else sm[r * sld + q] = 0.f;
         }
     }
-    return v;
 }
 
-template <int BM, int BN, int BK, int TM, int TN>
+template <int BM, int BN, int TM, int TN, bool AT, bool BT>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_stage_kernel(StageParams sp) {
-    constexpr int NT = (BM / TM) * (BN / TN);
-    constexpr int TX = BN / TN;
-    static_assert(BK % 4 == 0 && BM % 4 == 0 && BN % 4 == 0, "tile dims");
-    constexpr int A_VECS = BM * BK / 4;     // float4 per A tile
-    constexpr int B_VECS = BN * BK / 4;
-    static_assert(A_VECS + B_VECS <= 2 * NT && A_VECS <= NT && B_VECS <= NT, "one float4 per thread per operand");
-    constexpr int PADM = BM + 4, PADN = BN + 4;
-
-    __shared__ __align__(16) float As[2][BK][PADM];
-    __shared__ __align__(16) float Bs[2][BK][PADN];
+    constexpr int TY = BM / TM, TX = BN / TN, NT = TX * TY;
+    extern __shared__ __align__(16) float smem[];
     __shared__ AdamScalars s_adam;
 
     const GemmTask& T = sp.tasks[blockIdx.y];
     const int tile = blockIdx.x;
     if (tile >= T.tiles_m * T.tiles_n) return;
     const int seed = blockIdx.z;
-    const int tm = tile / T.tiles_n, tn = tile % T.tiles_n;
+    const int tm = tile / T.tiles_n, tn = tile - tm * T.tiles_n;
     const int m0 = tm * BM, n0 = tn * BN;
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
@@ -114,66 +138,22 @@ gemm_stage_kernel(StageParams sp) {
     const float* __restrict__ B = resolve(sp.as, T.B, seed);
     const int M = T.M, N = T.N, K = T.K;
     const int lda = T.lda, ldb = T.ldb;
-    const bool a_trans = T.a_trans != 0, b_trans = T.b_trans != 0;
     const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
-    if (T.epi == EPI_ADAM && tid == 0) {
+    const int kc = sp.kc;
+    const int kp = kpad_of(kc);
+    const int a_ld = AT ? BM : kp;                 // smem row stride
+    const int b_ld = BT ? BN : kp;
+    float* As = smem;
+    float* Bs = smem + (AT ? kc * BM : BM * kp);
+
+    const bool is_adam = T.epi == EPI_ADAM;
+    if (is_adam && tid == 0) {
         int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
         int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
         s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
     }
-
-    // per-thread load coordinates
-    // A, K-contiguous:  thread -> (m = v / (BK/4), k4 = (v % (BK/4))*4)
-    // A, M-contiguous:  thread -> (k = v / (BM/4), m4 = (v % (BM/4))*4)
-    const bool loads_a = tid < A_VECS;
-    const int vb = (A_VECS + B_VECS <= NT) ? tid - A_VECS : tid;   // B loader index
-    const bool loads_b = (A_VECS + B_VECS <= NT) ? (tid >= A_VECS && vb < B_VECS) : (tid < B_VECS);
-
-    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-    auto fetch = [&](int k0) {
-        if (loads_a) {
-            if (!a_trans) {
-                int m = tid / (BK / 4), k4 = (tid % (BK / 4)) * 4;
-                ra = load4_guard(A, lda, m0 + m, k0 + k4, M, K, a_vec);
-            } else {
-                int k = tid / (BM / 4), m4 = (tid % (BM / 4)) * 4;
-                ra = load4_guard(A, lda, k0 + k, m0 + m4, K, M, a_vec);
-            }
-        }
-        if (loads_b) {
-            if (!b_trans) {
-                int n = vb / (BK / 4), k4 = (vb % (BK / 4)) * 4;
-                rb = load4_guard(B, ldb, n0 + n, k0 + k4, N, K, b_vec);
-            } else {
-                int k = vb / (BN / 4), n4 = (vb % (BN / 4)) * 4;
-                rb = load4_guard(B, ldb, k0 + k, n0 + n4, K, N, b_vec);
-            }
-        }
-    };
-    auto stash = [&](int buf) {
-        if (loads_a) {
-            if (!a_trans) {
-                int m = tid / (BK / 4), k4 = (tid % (BK / 4)) * 4;
-                As[buf][k4 + 0][m] = ra.x; As[buf][k4 + 1][m] = ra.y;
-                As[buf][k4 + 2][m] = ra.z; As[buf][k4 + 3][m] = ra.w;
-            } else {
-                int k = tid / (BM / 4), m4 = (tid % (BM / 4)) * 4;
-                *reinterpret_cast<float4*>(&As[buf][k][m4]) = ra;
-            }
-        }
-        if (loads_b) {
-            if (!b_trans) {
-                int n = vb / (BK / 4), k4 = (vb % (BK / 4)) * 4;
-                Bs[buf][k4 + 0][n] = rb.x; Bs[buf][k4 + 1][n] = rb.y;
-                Bs[buf][k4 + 2][n] = rb.z; Bs[buf][k4 + 3][n] = rb.w;
-            } else {
-                int k = vb / (BN / 4), n4 = (vb % (BN / 4)) * 4;
-                *reinterpret_cast<float4*>(&Bs[buf][k][n4]) = rb;
-            }
-        }
-    };
 
     float acc[TM][TN];
 #pragma unroll
@@ -183,63 +163,106 @@ gemm_stage_kernel(StageParams sp) {
     float bsum[TM];
 #pragma unroll
     for (int i = 0; i < TM; ++i) bsum[i] = 0.f;
-    const float bias_on = (T.epi == EPI_ADAM && T.has_bias && tn == 0) ? 1.f : 0.f;
+    const bool bias_on = AT && is_adam && T.has_bias && tn == 0;
 
-    const int nk = (K + BK - 1) / BK;
-    fetch(0);
-    stash(0);
-    __syncthreads();
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) fetch((kt + 1) * BK);
+    for (int k0 = 0; k0 < K; k0 += kc) {
+        const int kn = min(kc, K - k0);
+        if (k0 > 0) __syncthreads();
+        const int kn4 = (kn + 3) & ~3;            // k tails are zero-filled (rows / columns beyond K)
+        if (!AT) stage_tile<NT>(As, a_ld, A, lda, m0, BM, M, k0, kn, K, a_vec);
+        else     stage_tile<NT>(As, a_ld, A, lda, k0, kn4, K, m0, BM, M, a_vec);
+        if (!BT) stage_tile<NT>(Bs, b_ld, B, ldb, n0, BN, N, k0, kn, K, b_vec);
+        else     stage_tile<NT>(Bs, b_ld, B, ldb, k0, kn4, K, n0, BN, N, b_vec);
+        cp_async_wait_all();
+        __syncthreads();
+        if (!AT && !BT) {
+#pragma unroll 2
+            for (int k = 0; k < kn4; k += 4) {
+                float4 a[TM], b[TN];
 #pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            float a[TM], b[TN];
+                for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + i * TY) * a_ld + k);
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[buf][k][ty * TM + i];
+                for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (tx + j * TX) * b_ld + k);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[buf][k][tx * TN + j];
+                for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                bsum[i] = fmaf(bias_on, a[i], bsum[i]);
+                    for (int j = 0; j < TN; ++j) {
+                        acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+                    }
+            }
+        } else if (!AT && BT) {
+#pragma unroll 2
+            for (int k = 0; k < kn4; k += 4) {
+                float4 a[TM];
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + i * TY) * a_ld + k);
+                float b[4][TN];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) b[kk][j] = Bs[(k + kk) * b_ld + tx + j * TX];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
+                        acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
+                        acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
+                    }
+            }
+        } else {
+            // AT (both operands row = k): rows beyond kn were never staged -> loop to kn only
+#pragma unroll 4
+            for (int k = 0; k < kn; ++k) {
+                float a[TM], b[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) a[i] = As[k * a_ld + ty + i * TY];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[j] = BT ? Bs[k * b_ld + tx + j * TX] : Bs[(tx + j * TX) * b_ld + k];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    if (bias_on) bsum[i] += a[i];
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
             }
         }
-        if (kt + 1 < nk) stash(buf ^ 1);
-        __syncthreads();
     }
 
     // ---- epilogue ----
     float* __restrict__ C = resolve(sp.as, T.C, seed);
     const int ldc = T.ldc;
     const int epi = T.epi;
-    if (epi == EPI_ADAM) {
+    if (is_adam) {
         float* __restrict__ m1 = sp.as.base[AR_ADAM_M] + (long long)seed * sp.as.stride[AR_ADAM_M];
         float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
         float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
         const AdamScalars s = s_adam;
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-            int m = m0 + ty * TM + i;
+            const int m = m0 + ty + i * TY;
             if (m >= M) continue;
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                int n = n0 + tx * TN + j;
+                const int n = n0 + tx + j * TX;
                 if (n >= N) continue;
-                long long e = (long long)m * ldc + n;
+                const long long e = (long long)m * ldc + n;
                 float* tgt = T.target_off >= 0 ? pbase + T.target_off + e : nullptr;
                 adam_update(acc[i][j], C + e, m1 + T.adam_off + e, m2 + T.adam_off + e, tgt, s);
             }
-            if (bias_on != 0.f && tx == 0 && T.train_bias) {
+            if (bias_on && tx == 0) {
                 float* pb = resolve(sp.as, T.bias, seed) + m;
                 float* tgt = T.target_bias_off >= 0 ? pbase + T.target_bias_off + m : nullptr;
-                adam_update(bsum[i], pb, m1 + T.adam_bias_off + m, m2 + T.adam_bias_off + m, tgt, s);
-            } else if (bias_on != 0.f && tx == 0 && !T.train_bias && T.target_bias_off >= 0 && s.do_polyak) {
-                // frozen bias still takes part in soft_update_from_to (it is a parameter)
-                float* pb = resolve(sp.as, T.bias, seed) + m;
-                float* tgt = pbase + T.target_bias_off + m;
-                *tgt = __fadd_rn(__fmul_rn(*tgt, s.one_m_tau), __fmul_rn(*pb, s.tau));
+                if (T.train_bias) {
+                    adam_update(bsum[i], pb, m1 + T.adam_bias_off + m, m2 + T.adam_bias_off + m, tgt, s);
+                } else if (tgt != nullptr && s.do_polyak) {
+                    // a frozen bias still takes part in soft_update_from_to (it is a parameter)
+                    *tgt = __fadd_rn(__fmul_rn(*tgt, s.one_m_tau), __fmul_rn(*pb, s.tau));
+                }
             }
         }
         return;
@@ -248,11 +271,11 @@ gemm_stage_kernel(StageParams sp) {
     const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        int m = m0 + ty * TM + i;
+        const int m = m0 + ty + i * TY;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            int n = n0 + tx * TN + j;
+            const int n = n0 + tx + j * TX;
             if (n >= N) continue;
             float v = acc[i][j];
             if (epi == EPI_BIAS) v += bias[n];

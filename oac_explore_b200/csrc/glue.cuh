@@ -13,8 +13,7 @@ namespace oac {
 // policy heads: mean / log_std GEMV + TanhNormal.rsample + log_prob  (trainer/policies.py:260-316)
 // =====================================================================================
 struct PolicyHeadTask {
-    Ref h2;             // [rows, H] last hidden activation
-    Ref w, b;           // heads [2A, H] (mean rows then log_std rows), [2A]
+    Ref head;           // [rows, 2A] head outputs (mean | raw log_std), computed by a GEMM stage
     int rows;           // B or 2B
     int out_row0;       // first row in the io outputs (log_pi [.], mean/log_std [., A])
     int dst_block[2];   // X row block (units of B rows) receiving tanh actions, per B-row block
@@ -43,68 +42,50 @@ struct PolicyHeadParams {
     int n_opt_counters;      // counters CNT_OPT0 .. CNT_OPT0+n-1 are bumped once per step here
 };
 
+// one warp per row: lane j handles action dim j (+32 per pass)
 __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
     const PolicyHeadTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * GLUE_WARPS + warp;
-    const int A = p.A, H = p.H, B = p.B;
+    const int A = p.A, B = p.B;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
     int32_t* cnt = p.as.counters + seed * p.as.n_counters;
     const int step = cnt[CNT_TRAIN_STEPS];
 
     if (row < T.rows) {
-        const float* __restrict__ h = resolve(p.as, T.h2, seed) + (long long)row * H;
-        const float* __restrict__ w = resolve(p.as, T.w, seed);
-        const float* __restrict__ bias = resolve(p.as, T.b, seed);
+        const float* __restrict__ head = resolve(p.as, T.head, seed) + (long long)row * 2 * A;
         float* save = resolve(p.as, T.save, seed) + (long long)row * 4 * A;
         const int blk = row / B, b = row % B;
         float lp_acc = 0.f;
-        for (int j0 = 0; j0 < A; j0 += 32) {
-            // each pass handles up to 32 action dims; lane j keeps dim j0+j
-            float my_mean = 0.f, my_raw = 0.f;
-            const int jn = min(32, A - j0);
-            for (int j = 0; j < jn; ++j) {
-                const float* wm = w + (long long)(j0 + j) * H;
-                const float* ws = w + (long long)(A + j0 + j) * H;
-                float sm = 0.f, ss = 0.f;
-                for (int k = lane; k < H; k += 32) {
-                    float hv = h[k];
-                    sm = fmaf(hv, wm[k], sm);
-                    ss = fmaf(hv, ws[k], ss);
-                }
-                sm = warp_sum(sm); ss = warp_sum(ss);
-                if (lane == j) { my_mean = sm + bias[j0 + j]; my_raw = ss + bias[A + j0 + j]; }
+        for (int j = lane; j < A; j += 32) {
+            const float my_mean = head[j], my_raw = head[A + j];
+            float log_std = fminf(fmaxf(my_raw, LOG_SIG_MIN_F), LOG_SIG_MAX_F);
+            float std = expf(log_std);
+            float action, eps = 0.f, lp = 0.f;
+            if (p.deterministic) {
+                action = tanhf(my_mean);
+            } else {
+                if (p.use_external_eps)
+                    eps = io[p.off_eps + ((long long)T.eps_slot[blk] * B + b) * A + j];
+                else
+                    eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)seed,
+                                        (uint32_t)T.eps_slot[blk], (uint32_t)step, (uint32_t)b, (uint32_t)j);
+                float z = fmaf(std, eps, my_mean);
+                action = tanhf(z);
+                // Normal(mean,std).log_prob(z) - log(1 - a^2 + eps)   (policies.py:147-160)
+                float d = z - my_mean;
+                float var = std * std;
+                lp = -(d * d) / (2.f * var) - logf(std) - 0.91893853320467274178f
+                     - logf(1.f - action * action + TANH_EPS_F);
             }
-            if (lane < jn) {
-                const int j = j0 + lane;
-                float log_std = fminf(fmaxf(my_raw, LOG_SIG_MIN_F), LOG_SIG_MAX_F);
-                float std = expf(log_std);
-                float action, eps = 0.f, lp = 0.f;
-                if (p.deterministic) {
-                    action = tanhf(my_mean);
-                } else {
-                    if (p.use_external_eps)
-                        eps = io[p.off_eps + ((long long)T.eps_slot[blk] * B + b) * A + j];
-                    else
-                        eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)seed,
-                                            (uint32_t)T.eps_slot[blk], (uint32_t)step, (uint32_t)b, (uint32_t)j);
-                    float z = fmaf(std, eps, my_mean);
-                    action = tanhf(z);
-                    // Normal(mean,std).log_prob(z) - log(1 - a^2 + eps)   (policies.py:147-160)
-                    float d = z - my_mean;
-                    float var = std * std;
-                    lp = -(d * d) / (2.f * var) - logf(std) - 0.91893853320467274178f
-                         - logf(1.f - action * action + TANH_EPS_F);
-                }
-                lp_acc += lp;
-                const int orow = T.out_row0 + row;
-                io[p.off_mean + (long long)orow * A + j] = my_mean;
-                io[p.off_log_std + (long long)orow * A + j] = log_std;
-                io[p.off_x + ((long long)T.dst_block[blk] * B + b) * p.x_ld + p.O + j] = action;
-                save[0 * A + j] = action; save[1 * A + j] = std;
-                save[2 * A + j] = my_raw; save[3 * A + j] = eps;
-            }
+            lp_acc += lp;
+            const int orow = T.out_row0 + row;
+            io[p.off_mean + (long long)orow * A + j] = my_mean;
+            io[p.off_log_std + (long long)orow * A + j] = log_std;
+            io[p.off_x + ((long long)T.dst_block[blk] * B + b) * p.x_ld + p.O + j] = action;
+            save[0 * A + j] = action; save[1 * A + j] = std;
+            save[2 * A + j] = my_raw; save[3 * A + j] = eps;
         }
         lp_acc = warp_sum(lp_acc);
         if (lane == 0) io[p.off_log_pi + T.out_row0 + row] = lp_acc;
@@ -166,9 +147,8 @@ constexpr int MAX_HEAD_SRC = 40;
 constexpr int MAX_VALS = 40;
 
 struct HeadSrc {
-    Ref h2;          // [*, H] hidden activations; sample b uses row row0 + b
+    Ref q;           // [*, n_heads] critic head outputs (GEMM stage); sample b uses row row0 + b
     int row0;
-    Ref w3, b3;      // [n_heads, H], [n_heads]
     int n_heads;
     Ref dq;          // [B, n_heads] gradient w.r.t. the (pre-exp) head outputs, written here
 };
@@ -194,33 +174,25 @@ struct CriticHeadParams {
     float discount, reward_scale, standard_bound, std_init;
 };
 
-__global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+constexpr int CRITIC_THREADS = 128;
+
+// one thread per sample
+__global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
     const CriticHeadParams& p = *pp;
-    __shared__ float s_vals[GLUE_WARPS][MAX_VALS];
     const int seed = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * GLUE_WARPS + warp;
-    const int B = p.B, H = p.H;
+    const int b = blockIdx.x * CRITIC_THREADS + threadIdx.x;
+    const int B = p.B;
     if (b >= B) return;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
-    float* vals = s_vals[warp];
-
-    // ---- all head outputs of this sample: vals[g], g enumerates (src, head) ----
-    int g = 0;
-    for (int s = 0; s < p.n_src; ++s) {
-        const HeadSrc& S = p.src[s];
-        const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
-        const float* __restrict__ w = resolve(p.as, S.w3, seed);
-        const float* __restrict__ bias = resolve(p.as, S.b3, seed);
-        for (int hd = 0; hd < S.n_heads; ++hd, ++g) {
-            float acc = 0.f;
-            for (int k = lane; k < H; k += 32) acc = fmaf(h[k], w[(long long)hd * H + k], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) vals[g] = acc + bias[hd];
+    float vals[MAX_VALS];
+    {
+        int g = 0;
+        for (int s = 0; s < p.n_src; ++s) {
+            const HeadSrc& S = p.src[s];
+            const float* __restrict__ q = resolve(p.as, S.q, seed) + (long long)(S.row0 + b) * S.n_heads;
+            for (int hd = 0; hd < S.n_heads; ++hd, ++g) vals[g] = q[hd];
         }
     }
-    __syncwarp();
-    if (lane != 0) return;
 
     const float invB = 1.0f / (float)B;
     const float r = io[p.off_rewards + b];
@@ -335,14 +307,8 @@ __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticH
 // =====================================================================================
 // policy-loss gradient w.r.t. the policy head outputs
 // =====================================================================================
-struct PolicyGradSrc {
-    Ref dh1;          // [B, H] gradient at the critic's first hidden layer (rows of this policy)
-    Ref w1;           // critic fc0.weight [H, in_ld]; action columns start at O
-    int ld;
-};
-
 struct PolicyGradTask {
-    PolicyGradSrc src[20];
+    Ref da[20];       // per critic: [B, A] = dh1 W1[:, O:O+A]   (d loss / d action through that critic)
     int n_src;
     Ref save;         // [., 4, A] from policy_head (rows of this policy start at save_row0)
     int save_row0;
@@ -357,66 +323,38 @@ struct PolicyGradParams {
     int O, A, H, B;
 };
 
-// dyn smem: w1 action columns of one source, [H][A]
+// one thread per (sample, action dim)
 __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
-    extern __shared__ float s_wa[];
     const PolicyGradTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * GLUE_WARPS + warp;
-    const int A = p.A, H = p.H, B = p.B, O = p.O;
+    const int A = p.A, B = p.B;
+    const int idx = blockIdx.x * GLUE_THREADS + threadIdx.x;
+    if (idx >= B * A) return;
+    const int b = idx / A, j = idx - b * A;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
-
-    // g_a[j] = sum_src sum_n dh1[b,n] * W1[n, O+j]; lane j (+32 i) keeps action dim j
-    float ga[4] = {0.f, 0.f, 0.f, 0.f};      // A <= 128
-    for (int s = 0; s < T.n_src; ++s) {
-        const float* __restrict__ w1 = resolve(p.as, T.src[s].w1, seed);
-        const int ld = T.src[s].ld;
-        __syncthreads();
-        for (int i = threadIdx.x; i < H * A; i += GLUE_THREADS) {
-            int n = i / A, j = i % A;
-            s_wa[i] = w1[(long long)n * ld + O + j];
-        }
-        __syncthreads();
-        if (b < B) {
-            const float* __restrict__ dh = resolve(p.as, T.src[s].dh1, seed) + (long long)b * H;
-            for (int n = 0; n < H; ++n) {
-                float dv = dh[n];         // broadcast load
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int j = lane + 32 * i;
-                    if (j < A) ga[i] = fmaf(dv, s_wa[n * A + j], ga[i]);
-                }
-            }
-        }
-    }
-    if (b >= B) return;
+    float ga = 0.f;
+    for (int s = 0; s < T.n_src; ++s) ga += resolve(p.as, T.da[s], seed)[idx];
     const float alpha = io[p.off_scalars + SC_ALPHA];
     const float invB = 1.0f / (float)B;
     const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
     float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * 2 * A;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int j = lane + 32 * i;
-        if (j >= A) continue;
-        float a = save[0 * A + j];
-        float one_m_a2 = 1.f - a * a;
-        float dmean, draw;
-        if (T.entropy) {
-            float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
-            float u = one_m_a2 + TANH_EPS_F;
-            // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
-            dmean = alpha * invB * (2.f * a * one_m_a2 / u) + ga[i] * one_m_a2;
-            float dstd = dmean * eps - alpha * invB / std;
-            bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
-            draw = inside ? dstd * std : 0.f;
-        } else {
-            dmean = ga[i] * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
-            draw = 0.f;
-        }
-        dhead[j] = dmean;
-        dhead[A + j] = draw;
+    const float a = save[0 * A + j];
+    const float one_m_a2 = 1.f - a * a;
+    float dmean, draw;
+    if (T.entropy) {
+        const float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
+        const float u = one_m_a2 + TANH_EPS_F;
+        // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
+        dmean = alpha * invB * (2.f * a * one_m_a2 / u) + ga * one_m_a2;
+        const float dstd = dmean * eps - alpha * invB / std;
+        const bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
+        draw = inside ? dstd * std : 0.f;
+    } else {
+        dmean = ga * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
+        draw = 0.f;
     }
+    dhead[j] = dmean;
+    dhead[A + j] = draw;
 }
 
 }  // namespace oac

@@ -125,6 +125,9 @@ struct Stage {
     // launch
     void* dev = nullptr;        // task table / params on the device
     int small_tiles = 0;
+    int a_trans = 0, b_trans = 0;   // all tasks of a GEMM stage share the operand layouts
+    int kc = 0;
+    size_t smem = 0;
     int max_tiles = 0;
     int max_rows = 0;
     const char* name = "";
@@ -213,20 +216,37 @@ struct Builder {
     }
 
     // ---- policy forward (trunk) for rows of X blocks [blk0, blk0+nblk) ----
-    struct PolAct { Ref h1, h2, save; int rows; };
+    struct PolAct { Ref h1, h2, head, save; int rows; };
     PolAct alloc_pol(int nblk) {
         PolAct a; a.rows = nblk * B;
         a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
+        a.head = work((long long)a.rows * 2 * A);
         a.save = work((long long)a.rows * 4 * A);
         return a;
     }
-    struct CritAct { Ref h1, h2, dq, dh2, dh1; int rows; };
+    struct CritAct { Ref h1, h2, q, dq, dh2, dh1, da; int rows; };
     CritAct alloc_crit(int nblk, int heads) {
         CritAct a; a.rows = nblk * B;
         a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
+        a.q = work((long long)a.rows * heads);
         a.dq = work((long long)a.rows * heads);
         a.dh2 = work((long long)a.rows * H); a.dh1 = work((long long)a.rows * H);
+        a.da = work((long long)a.rows * A);
         return a;
+    }
+    void pol_l3(Stage& s, int ni, const PolAct& a) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, a.h2, H, a.rows, H, P(n.off_w2), H, P(n.off_b2), 2 * A, a.head, 2 * A, false);
+    }
+    void crit_l3(Stage& s, int ni, const CritAct& a) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, a.h2, H, a.rows, H, P(n.off_w2), H, P(n.off_b2), n.n_out, a.q, n.n_out, false);
+    }
+    // da[B,A] = dh1[B,H] W0[:, O:O+A] for rows [row0,row0+B)
+    void crit_da(Stage& s, int ni, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        dx(s, Ref{a.dh1.arena, a.dh1.off + (long long)row0 * H}, H, B, H, P(n.off_w0 + O), n.in_ld, A,
+           Ref{a.da.arena, a.da.off + (long long)row0 * A}, A, Ref{0, 0}, 0, false);
     }
     void pol_l1(Stage& s, int ni, int blk0, const PolAct& a) {
         const OacNetLayout& n = net(ni);
@@ -246,7 +266,7 @@ struct Builder {
     }
     HeadSrc head_src(int ni, const CritAct& a, int row0) {
         const OacNetLayout& n = net(ni);
-        HeadSrc h; h.h2 = a.h2; h.row0 = row0; h.w3 = P(n.off_w2); h.b3 = P(n.off_b2); h.n_heads = n.n_out;
+        HeadSrc h; h.q = a.q; h.row0 = row0; h.n_heads = n.n_out;
         h.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * n.n_out};
         return h;
     }
@@ -302,7 +322,8 @@ struct Builder {
         const OacNetLayout& n = net(ni);
         PolicyHeadTask p;
         memset(&p, 0, sizeof(p));
-        p.h2 = a.h2; p.w = P(n.off_w2); p.b = P(n.off_b2); p.rows = a.rows; p.out_row0 = out_row0;
+        (void)n;
+        p.head = a.head; p.rows = a.rows; p.out_row0 = out_row0;
         p.dst_block[0] = dst0; p.dst_block[1] = dst1; p.eps_slot[0] = eps0; p.eps_slot[1] = eps1;
         p.save = a.save;
         return p;
@@ -353,12 +374,15 @@ void Builder::build_sac() {
     PolGrad pg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
       crit_l1(s, q1, 1, ca1); crit_l1(s, q2, 1, ca2); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
+    { Stage& s = add_stage(ST_GEMM, "critic_l3");
+      crit_l3(s, q1, ca1); crit_l3(s, q2, ca2); crit_l3(s, t1, ta1); crit_l3(s, t2, ta2); }
     { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_sac");
       memset(&s.chp, 0, sizeof(s.chp));
       s.chp.src[0] = head_src(q1, ca1, 0); s.chp.src[1] = head_src(q2, ca2, 0);
@@ -375,10 +399,10 @@ void Builder::build_sac() {
     // NB mode B reads fc0.weight's action columns in policy_grad AFTER the Adam stage; to keep
     // B exact the policy_grad stage is placed before the critic Adam in that mode.
     auto policy_grad_stage = [&]() {
+        { Stage& sd = add_stage(ST_GEMM, "pi_da"); crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
         Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
         PolicyGradTask g; memset(&g, 0, sizeof(g));
-        g.src[0].dh1 = ca1.dh1; g.src[0].w1 = P(net(q1).off_w0); g.src[0].ld = net(q1).in_ld;
-        g.src[1].dh1 = ca2.dh1; g.src[1].w1 = P(net(q2).off_w0); g.src[1].ld = net(q2).in_ld;
+        g.da[0] = ca1.da; g.da[1] = ca2.da;
         g.n_src = 2; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = !c.deterministic;
         s.pg.push_back(g); fill_pgp(s);
     };
@@ -407,6 +431,7 @@ void Builder::build_poac() {
     PolGrad pg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     // eps slots are named by meaning (0: obs draw, 1: next_obs draw); the reference draws the
     // next_obs noise FIRST here (:193 then :271) -- the host wrapper maps call order to slots
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+alpha");
@@ -415,6 +440,8 @@ void Builder::build_poac() {
       for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
+    { Stage& s = add_stage(ST_GEMM, "critic_l3");
+      for (int i = 0; i < n; ++i) { crit_l3(s, t.ids.qf[i], qa[i]); crit_l3(s, t.ids.tf[i], ta[i]); } }
     { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_poac_q");
       memset(&s.chp, 0, sizeof(s.chp));
       for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0);
@@ -427,17 +454,17 @@ void Builder::build_poac() {
     // policy phase through the UPDATED critics
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 1, pa_q[i]); }
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pa_q[i]); }
+    { Stage& s = add_stage(ST_GEMM, "pi_critic_l3"); for (int i = 0; i < n; ++i) crit_l3(s, t.ids.qf[i], pa_q[i]); }
     { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_poac_pi");
       memset(&s.chp, 0, sizeof(s.chp));
       for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], pa_q[i], 0);
       s.chp.n_src = n; fill_chp(s, CM_POAC_PI, n); }
     { Stage& s = add_stage(ST_GEMM, "pi_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], pa_q[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "pi_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], pa_q[i], 0); }
+    { Stage& s = add_stage(ST_GEMM, "pi_da"); for (int i = 0; i < n; ++i) crit_da(s, t.ids.qf[i], pa_q[i], 0); }
     { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
       PolicyGradTask g; memset(&g, 0, sizeof(g));
-      for (int i = 0; i < n; ++i) {
-          g.src[i].dh1 = pa_q[i].dh1; g.src[i].w1 = P(net(t.ids.qf[i]).off_w0); g.src[i].ld = net(t.ids.qf[i]).in_ld;
-      }
+      for (int i = 0; i < n; ++i) g.da[i] = pa_q[i].da;
       g.n_src = n; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = !c.deterministic;
       s.pg.push_back(g); fill_pgp(s); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
@@ -458,6 +485,7 @@ void Builder::build_goac() {
     PolGrad pg = alloc_polgrad(), tpg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); pol_l1(s, tpol, 2, tpa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); pol_l2(s, tpol, tpa); }
+    { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); pol_l3(s, tpol, tpa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1));
       s.ph.push_back(ph_task(tpol, tpa, 2 * B, 0, 0, 0, 0));
@@ -466,6 +494,8 @@ void Builder::build_goac() {
       for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
+    { Stage& s = add_stage(ST_GEMM, "critic_l3");
+      for (int i = 0; i < n; ++i) { crit_l3(s, t.ids.qf[i], qa[i]); crit_l3(s, t.ids.tf[i], ta[i]); } }
     { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_goac_q");
       memset(&s.chp, 0, sizeof(s.chp));
       for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0);
@@ -479,6 +509,7 @@ void Builder::build_goac() {
     // policy (rows [B,2B) = block 1) and target policy (rows [0,B) = block 0) through the updated critic
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 0, pq[i]); }
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pq[i]); }
+    { Stage& s = add_stage(ST_GEMM, "pi_critic_l3"); for (int i = 0; i < n; ++i) crit_l3(s, t.ids.qf[i], pq[i]); }
     { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_goac_pi");
       memset(&s.chp, 0, sizeof(s.chp));
       for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], pq[i], B);        // a_pi rows
@@ -488,13 +519,14 @@ void Builder::build_goac() {
       for (int i = 0; i < n; ++i) { crit_dh2(s, t.ids.qf[i], pq[i], 0); crit_dh2(s, t.ids.qf[i], pq[i], B); } }
     { Stage& s = add_stage(ST_GEMM, "pi_dh1");
       for (int i = 0; i < n; ++i) { crit_dh1(s, t.ids.qf[i], pq[i], 0); crit_dh1(s, t.ids.qf[i], pq[i], B); } }
+    { Stage& s = add_stage(ST_GEMM, "pi_da");
+      for (int i = 0; i < n; ++i) { crit_da(s, t.ids.qf[i], pq[i], 0); crit_da(s, t.ids.qf[i], pq[i], B); } }
     { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
       PolicyGradTask g; memset(&g, 0, sizeof(g));
       PolicyGradTask gt; memset(&gt, 0, sizeof(gt));
       for (int i = 0; i < n; ++i) {
-          const OacNetLayout& qn = net(t.ids.qf[i]);
-          g.src[i].dh1 = Ref{pq[i].dh1.arena, pq[i].dh1.off + (long long)B * H}; g.src[i].w1 = P(qn.off_w0); g.src[i].ld = qn.in_ld;
-          gt.src[i].dh1 = pq[i].dh1; gt.src[i].w1 = P(qn.off_w0); gt.src[i].ld = qn.in_ld;
+          g.da[i] = Ref{pq[i].da.arena, pq[i].da.off + (long long)B * A};
+          gt.da[i] = pq[i].da;
       }
       g.n_src = n; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = 0;
       gt.n_src = n; gt.save = tpa.save; gt.save_row0 = 0; gt.dhead = tpg.dhead; gt.entropy = 0;
@@ -521,9 +553,26 @@ static int finalize(OacTrainer& t) {
     for (Stage& s : t.stages) {
         if (s.kind == ST_GEMM) {
             long long tiles64 = 0;
-            for (auto& g : s.gemm) tiles64 += (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
-            s.small_tiles = (tiles64 * seeds < 200);
+            int kmax = 0;
+            s.a_trans = s.gemm[0].a_trans; s.b_trans = s.gemm[0].b_trans;
+            for (auto& g : s.gemm) {
+                tiles64 += (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
+                kmax = std::max(kmax, g.K);
+                if (g.a_trans != s.a_trans || g.b_trans != s.b_trans || (g.a_trans && !g.b_trans))
+                    return set_error(OAC_E_INVALID, "internal: mixed operand layouts in one GEMM stage");
+            }
+            s.small_tiles = (tiles64 * seeds < 2 * 148);
             const int bm = s.small_tiles ? 32 : 64;
+            // largest K chunk (multiple of 4) whose A+B tiles fit the shared-memory budget
+            auto bytes_of = [&](int kc) {
+                size_t a = s.a_trans ? (size_t)kc * bm : (size_t)bm * kpad_of(kc);
+                size_t b = s.b_trans ? (size_t)kc * bm : (size_t)bm * kpad_of(kc);
+                return (a + b) * sizeof(float);
+            };
+            int kc = (kmax + 3) & ~3;
+            const size_t budget = s.small_tiles ? 100 * 1024 : 208 * 1024;   // small tiles: keep 2 CTAs / SM
+            while (kc > 16 && bytes_of(kc) > budget) kc = ((kc / 2) + 3) & ~3;
+            s.kc = kc; s.smem = bytes_of(kc);
             s.max_tiles = 0;
             for (auto& g : s.gemm) {
                 g.tiles_m = (g.M + bm - 1) / bm; g.tiles_n = (g.N + bm - 1) / bm;
@@ -552,21 +601,27 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
     const int seeds = t.cfg.n_seeds;
     for (Stage& s : t.stages) {
         if (s.kind == ST_GEMM) {
-            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper;
+            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
-            if (s.small_tiles) gemm_stage_kernel<32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(sp);
-            else gemm_stage_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(sp);
+            const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
+            switch (sel) {
+                case 0: gemm_stage_kernel<32, 32, 2, 2, false, false><<<grid, 256, s.smem, st>>>(sp); break;
+                case 1: gemm_stage_kernel<32, 32, 2, 2, false, true><<<grid, 256, s.smem, st>>>(sp); break;
+                case 2: gemm_stage_kernel<32, 32, 2, 2, true, true><<<grid, 256, s.smem, st>>>(sp); break;
+                case 3: gemm_stage_kernel<64, 64, 4, 4, false, false><<<grid, 256, s.smem, st>>>(sp); break;
+                case 4: gemm_stage_kernel<64, 64, 4, 4, false, true><<<grid, 256, s.smem, st>>>(sp); break;
+                default: gemm_stage_kernel<64, 64, 4, 4, true, true><<<grid, 256, s.smem, st>>>(sp); break;
+            }
         } else if (s.kind == ST_POLICY_HEAD) {
             PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps;
             dim3 grid((s.max_rows + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.ph.size(), seeds);
             policy_head_kernel<<<grid, GLUE_THREADS, 0, st>>>(p);
         } else if (s.kind == ST_CRITIC_HEAD) {
-            dim3 grid((t.cfg.batch + GLUE_WARPS - 1) / GLUE_WARPS, seeds, 1);
-            critic_head_kernel<<<grid, GLUE_THREADS, 0, st>>>((const CriticHeadParams*)s.dev);
+            dim3 grid((t.cfg.batch + CRITIC_THREADS - 1) / CRITIC_THREADS, seeds, 1);
+            critic_head_kernel<<<grid, CRITIC_THREADS, 0, st>>>((const CriticHeadParams*)s.dev);
         } else {
-            dim3 grid((t.cfg.batch + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.pg.size(), seeds);
-            size_t smem = sizeof(float) * (size_t)t.cfg.hidden * t.cfg.act_dim;
-            policy_grad_kernel<<<grid, GLUE_THREADS, smem, st>>>(s.pgp);
+            dim3 grid((t.cfg.batch * t.cfg.act_dim + GLUE_THREADS - 1) / GLUE_THREADS, (unsigned)s.pg.size(), seeds);
+            policy_grad_kernel<<<grid, GLUE_THREADS, 0, st>>>(s.pgp);
         }
         OAC_CUDA(cudaGetLastError());
     }
@@ -608,7 +663,6 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     else b.build_goac();
     t->lay.work_floats = t->work_cursor;
     const OacLayout& L = t->lay;
-    if (cfg->hidden * cfg->act_dim * sizeof(float) > 200 * 1024) { delete t; return set_error(OAC_E_UNSUPPORTED, "hidden*act_dim too large"); }
     t->as.base[AR_PARAM] = buf->params;  t->as.stride[AR_PARAM] = L.param_floats;
     t->as.base[AR_ADAM_M] = buf->adam_m; t->as.stride[AR_ADAM_M] = L.adam_floats;
     t->as.base[AR_ADAM_V] = buf->adam_v; t->as.stride[AR_ADAM_V] = L.adam_floats;
@@ -623,9 +677,16 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         double tau = rint((double)cfg->soft_target_tau * 1e9) * 1e-9;
         t->hyper.one_minus_tau = (float)(1.0 - tau);
     }
-    size_t pg_smem = sizeof(float) * (size_t)cfg->hidden * cfg->act_dim;
-    if (pg_smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(policy_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pg_smem);
+    {
+        const int big = 212 * 1024;
+        cudaError_t e = cudaSuccess;
+        auto opt_in = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, big); };
+        opt_in((const void*)gemm_stage_kernel<32, 32, 2, 2, false, false>);
+        opt_in((const void*)gemm_stage_kernel<32, 32, 2, 2, false, true>);
+        opt_in((const void*)gemm_stage_kernel<32, 32, 2, 2, true, true>);
+        opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>);
+        opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>);
+        opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>);
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
@@ -669,5 +730,49 @@ extern "C" int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* s
         if (e != cudaSuccess) return set_cuda_error(e, "cudaGraphInstantiate");
     }
     OAC_CUDA(cudaGraphLaunch(t->graph[gi], st));
+    return 0;
+}
+
+extern "C" int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_stages, float* ms, int32_t* is_gemm,
+                                   double* flops, const char** names, int32_t* n_stages, void* stream) {
+    if (!t || !ms || !n_stages || iters < 1) return set_error(OAC_E_INVALID, "oac_trainer_profile: bad argument");
+    const int n = (int)t->stages.size();
+    if (n > max_stages) return set_error(OAC_E_INVALID, "oac_trainer_profile: max_stages too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) OAC_CUDA(cudaEventCreate(&e));
+    std::vector<double> acc(n, 0.0);
+    std::vector<Stage> all;
+    all.swap(t->stages);
+    int rc = 0;
+    // each stage is launched `iters` times back to back between two events, so the figure is the
+    // warm, launch-gap-free kernel duration (the state drifts: call this on a scratch trainer)
+    for (int i = 0; i < n && !rc; ++i) {
+        t->stages.clear();
+        t->stages.push_back(all[i]);
+        rc = launch_stages(*t, 0, st);          // warm-up
+        cudaEventRecord(ev[0], st);
+        for (int it = 0; it < iters && !rc; ++it) rc = launch_stages(*t, 0, st);
+        cudaEventRecord(ev[1], st);
+        cudaStreamSynchronize(st);
+        float f = 0.f;
+        cudaEventElapsedTime(&f, ev[0], ev[1]);
+        acc[i] = f;
+    }
+    t->stages.swap(all);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        ms[i] = (float)(acc[i] / iters);
+        const Stage& s = t->stages[i];
+        if (is_gemm) is_gemm[i] = s.kind == ST_GEMM;
+        if (names) names[i] = s.name;
+        if (flops) {
+            double f = 0.0;
+            if (s.kind == ST_GEMM) for (auto& g : s.gemm) f += 2.0 * g.M * (double)g.N * g.K;
+            flops[i] = f;
+        }
+    }
+    *n_stages = n;
     return 0;
 }

@@ -135,3 +135,15 @@ class Engine(object):
     def step(self, external_eps=False):
         _lib.check(self.lib.oac_trainer_step(self.handle, 1 if external_eps else 0, _lib.current_stream()),
                    "oac_trainer_step")
+
+    def profile(self, iters=20):
+        """Per-stage mean milliseconds (stage-by-stage launches, CUDA events): [(name, ms, is_gemm, flops)]."""
+        n_max = 64
+        ms = (C.c_float * n_max)()
+        isg = (C.c_int32 * n_max)()
+        fl = (C.c_double * n_max)()
+        names = (C.c_char_p * n_max)()
+        n = C.c_int32(0)
+        _lib.check(self.lib.oac_trainer_profile(self.handle, iters, n_max, ms, isg, fl, names, C.byref(n),
+                                                _lib.current_stream()), "oac_trainer_profile")
+        return [(names[i].decode(), float(ms[i]), bool(isg[i]), float(fl[i])) for i in range(n.value)]

@@ -119,6 +119,17 @@ class Mlp(object):
             views['last_fc.weight'], views['last_fc.bias'] = w2, b2
         self._bind(views, self._own, lay)
 
+    def _rel(self):
+        """(device pointer of this net's first float, layout with offsets relative to it): lets a
+        kernel take several same-shaped nets as plain base pointers + ONE layout."""
+        self._ensure_bound()
+        l, r = self._lay, OacNetLayout()
+        for f, _ in OacNetLayout._fields_:
+            setattr(r, f, getattr(l, f))
+        for f in ("off_w0", "off_b0", "off_w1", "off_b1", "off_w2", "off_b2"):
+            setattr(r, f, getattr(l, f) - l.off_w0)
+        return self._arena.data_ptr() + 4 * l.off_w0, r
+
     # ---- nn.Module-like surface (what main.py / rl_algorithm.py / snapshots touch) --------
     def state_dict(self):
         src = self._views if self._views is not None else self._init

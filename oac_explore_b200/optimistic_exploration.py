@@ -48,13 +48,13 @@ def explore_batch(obs, policy, qfs, hyper_params, trainer=None, deterministic=Fa
     A = policy.action_dim
     st = _buffers(O, A, n)
     a = OacExploreArgs()
-    a.policy, a.policy_lay = policy._arena.data_ptr(), policy._lay
+    a.policy, a.policy_lay = policy._rel()
     nq = len(qfs)
     if nq > 16:
         raise NotImplementedError("more than 16 critics")
     for i, q in enumerate(qfs):
-        a.q[i] = q._arena.data_ptr()
-    a.q_lay, a.n_q = qfs[0]._lay, nq
+        a.q[i], lay = q._rel()
+    a.q_lay, a.n_q = lay, nq
     a.exp_mask = qfs[0]._exp_mask()
     if trainer is not None and hasattr(trainer, 'delta_index'):
         a.mode, a.quantile_index = _lib.EXPLORE_QUANTILE, trainer.delta_index      # ParticleTrainer.predict

@@ -62,6 +62,8 @@ class ReplayBuffer(object):
         self._idx_host = None
         self._idx_dev = None
         self._trainer = None
+        self._desc_cache = {}
+        self._view_cache = None
 
     # ---- insert path (replay_buffer.py:50-104) -------------------------------------
     def add_path(self, path):
@@ -129,35 +131,44 @@ class ReplayBuffer(object):
         if self._idx_host is None or self._idx_host.shape[0] < n:
             self._idx_host = torch.zeros(n, dtype=torch.int64).pin_memory()
             self._idx_dev = torch.zeros(n, dtype=torch.int64, device=self._device)
-        self._idx_host.numpy()[:n] = indices
-        self._idx_dev[:n].copy_(self._idx_host[:n], non_blocking=True)
+            self._idx_np = self._idx_host.numpy()
+        if n == self._idx_host.shape[0]:
+            self._idx_np[:] = indices
+            self._idx_dev.copy_(self._idx_host, non_blocking=True)
+        else:
+            self._idx_np[:n] = indices
+            self._idx_dev[:n].copy_(self._idx_host[:n], non_blocking=True)
         return self._idx_dev
 
-    def gather_into(self, engine, indices_dev, batch_size, seed=0, n_seeds=1):
-        L = engine.lay
-        dst = OacBatchDst()
-        dst.x = engine.io[seed, L.off_x:].data_ptr()
-        dst.x_ld = L.x_ld
-        goac = engine.cfg.algo == _lib.ALGO_GOAC
-        dst.obs_blocks[0], dst.obs_blocks[1], dst.obs_blocks[2] = 1, 2, (0 if goac else -1)
-        dst.act_block, dst.next_block = 2, 3
-        dst.rewards = engine.io[seed, L.off_rewards:].data_ptr()
-        dst.terminals = engine.io[seed, L.off_terminals:].data_ptr()
-        dst.counts = engine.io[seed, L.off_counts:].data_ptr() if self._counts_dev is not None else None
-        dst.n_seeds, dst.seed_stride = n_seeds, L.io_floats
-        st = self._store()
-        _lib.check(self._lib.oac_replay_gather(C.byref(st), _lib.ptr(indices_dev), batch_size, C.byref(dst),
-                                               _lib.current_stream()), "oac_replay_gather")
+    def _gather_desc(self, engine, seed, n_seeds):
+        key = (id(engine), seed, n_seeds)
+        d = self._desc_cache.get(key)
+        if d is None:
+            L = engine.lay
+            dst = OacBatchDst()
+            dst.x = engine.io[seed, L.off_x:].data_ptr()
+            dst.x_ld = L.x_ld
+            goac = engine.cfg.algo == _lib.ALGO_GOAC
+            dst.obs_blocks[0], dst.obs_blocks[1], dst.obs_blocks[2] = 1, 2, (0 if goac else -1)
+            dst.act_block, dst.next_block = 2, 3
+            dst.rewards = engine.io[seed, L.off_rewards:].data_ptr()
+            dst.terminals = engine.io[seed, L.off_terminals:].data_ptr()
+            dst.counts = engine.io[seed, L.off_counts:].data_ptr() if self._counts_dev is not None else None
+            dst.n_seeds, dst.seed_stride = n_seeds, L.io_floats
+            d = (self._store(), dst, engine)          # keeps the engine alive while cached
+            self._desc_cache = {key: d}
+        return d
 
-    def random_batch(self, batch_size):
-        self._flush()
-        indices = self._draw_indices(batch_size)
-        idx_dev = self._upload_indices(indices)
-        tr = self._trainer
-        if tr is not None:
-            tr._ensure_engine(batch_size)
-            e = tr._engine
-            self.gather_into(e, idx_dev, batch_size)
+    def gather_into(self, engine, indices_dev, batch_size, seed=0, n_seeds=1):
+        st, dst, _ = self._gather_desc(engine, seed, n_seeds)
+        rc = self._lib.oac_replay_gather(C.byref(st), C.c_void_p(indices_dev.data_ptr()), batch_size, C.byref(dst),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            _lib.check(rc, "oac_replay_gather")
+
+    def _resident_views(self, e, batch_size):
+        key = (id(e), batch_size)
+        if self._view_cache is None or self._view_cache[0] != key:
             O, A = self._ob_dim, self._ac_dim
             xb2, L = e.x_block(2), e.lay
             batch = dict(observations=xb2[:, :O], actions=xb2[:, O:O + A],
@@ -166,7 +177,20 @@ class ReplayBuffer(object):
                          next_observations=e.x_block(3)[:, :O], _oac_resident=e)
             if self._counts_dev is not None:
                 batch['counts'] = e.io_view(L.off_counts, (batch_size, 1))
-            return batch
+            self._view_cache = (key, batch)
+        return dict(self._view_cache[1])
+
+    def random_batch(self, batch_size):
+        if self._n_staged:
+            self._flush()
+        indices = self._draw_indices(batch_size)
+        idx_dev = self._upload_indices(indices)
+        tr = self._trainer
+        if tr is not None:
+            tr._ensure_engine(batch_size)
+            e = tr._engine
+            self.gather_into(e, idx_dev, batch_size)
+            return self._resident_views(e, batch_size)
         return self._numpy_batch(self.gather_dense(idx_dev, batch_size))
 
     def gather_dense(self, idx_dev, batch_size):
@@ -240,6 +264,7 @@ class ReplayBufferCount(ReplayBuffer):
 
     @property
     def _counts(self):
+        self._flush()
         return self._counts_dev.to('cpu').numpy().astype(np.float64)
 
     def _draw_indices(self, batch_size):

@@ -174,9 +174,9 @@ def test_adam_first_step_kat():
     after = net_cpu(tr.qf1)['fc1.weight']
     m = tr._engine.net_views(1, arena=tr._engine.adam_m)['fc1.weight'].cpu()
     moved = (after - before).abs()
-    nz = m.abs() > 1e-9
+    nz = m.abs() > 1e-6     # |g| > 1e-5 >> adam eps: update = lr * g / (|g| + 1e-8)
     assert torch.allclose(moved[nz], torch.full_like(moved[nz], 3e-4), rtol=2e-2)
-    assert torch.all(moved[~nz] == 0)
+    assert torch.all(moved[m == 0] == 0)
 
 
 def test_device_noise_statistics():
