@@ -153,6 +153,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+GEMM_PATHS = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+GEMM_PATH = 2
+
+
 def build_trainer(algo, seed):
     from oac_explore_b200.networks import get_policy_producer, get_q_producer
     torch.manual_seed(seed)
@@ -160,15 +164,65 @@ def build_trainer(algo, seed):
         from oac_explore_b200.trainer import SACTrainer
         pp, qp = get_policy_producer(O, A, [H, H]), get_q_producer(O, A, [H, H])
         return SACTrainer(pp, qp, action_space=Box(A), use_automatic_entropy_tuning=True, rng_seed=seed,
-                          target_update_period=1, **HP)
+                          target_update_period=1, gemm_path=GEMM_PATH, **HP)
     if algo == "poac":
         from oac_explore_b200.particle_trainer_oac import ParticleTrainer
         pp, qp = get_policy_producer(O, A, [H, H]), get_q_producer(O, A, [H, H], output_size=10)
         return ParticleTrainer(pp, qp, n_estimators=10, action_space=Box(A), share_layers=True, deterministic=False,
-                               delta=0.95, q_min=0.0, q_max=500.0, rng_seed=seed, **HP)
+                               delta=0.95, q_min=0.0, q_max=500.0, rng_seed=seed, gemm_path=GEMM_PATH, **HP)
     from oac_explore_b200.gaussian_trainer import GaussianTrainer
     pp, qp = get_policy_producer(O, A, [H, H]), get_q_producer(O, A, [H, H], output_size=2)
-    return GaussianTrainer(pp, qp, action_space=Box(A), share_layers=True, delta=0.95, q_min=0.0, q_max=500.0, **HP)
+    return GaussianTrainer(pp, qp, action_space=Box(A), share_layers=True, delta=0.95, q_min=0.0, q_max=500.0,
+                           gemm_path=GEMM_PATH, **HP)
+
+
+class _Single(object):
+    """Adapter: one reference-style trainer + buffer (the public API of BASELINE config 2)."""
+
+    def __init__(self, args, rank, rb):
+        self.tr = build_trainer(args.algo, seed=rank)
+        self.rb = rb
+        rb.attach(self.tr)
+        self.engine = self.tr._engine
+        self.S = 1
+
+    def device_step(self, idx_dev):              # idx_dev [1, B] on the device
+        self.rb.gather_into(self.engine, idx_dev, B)
+        self.engine.step()
+
+    def api_step(self):
+        batch = self.rb.random_batch(B)          # host np.random indices -> pinned -> H2D -> gather kernel
+        batch['buffer'] = self.rb
+        self.tr.train(batch)                     # fused step (CUDA graph)
+
+    def scalars(self):
+        return self.engine.scalars()
+
+    api = "ReplayBuffer.random_batch(256) + SACTrainer.train(batch) + D2H scalars, sync per step"
+
+
+class _Group(object):
+    """Adapter: S independent seeds batched in one engine (BASELINE config 5)."""
+
+    def __init__(self, args, rank, world, rb):
+        from oac_explore_b200.seed_group import SACSeedGroup
+        S = args.seeds_per_gpu
+        ids = [rank + world * i for i in range(S)]               # seed % n_gpus == rank (main.py:575-576)
+        self.grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=GEMM_PATH, rng_seed=rank, **HP)
+        self.rb, self.engine, self.S = rb, self.grp.engine, S
+
+    def device_step(self, idx_dev):              # idx_dev [S, B]
+        self.grp.gather(self.rb, idx_dev)
+        self.grp.step()
+
+    def api_step(self):
+        self.grp.gather(self.rb, np.random.randint(0, N_REPLAY, (self.S, B)))
+        self.grp.step()
+
+    def scalars(self):
+        return self.engine.io[:, self.engine.lay.off_scalars:self.engine.lay.off_scalars + 16]
+
+    api = "SACSeedGroup.gather(replay, host indices [S,256]) + .step() + D2H per-seed scalars, sync per step"
 
 
 def run_ours(args):
@@ -183,16 +237,17 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     # 1M-transition synthetic store, generated on the device (obs/next N(0,1), actions U(-1,1),
-    # rewards N(0,1), terminals Bernoulli(0.01)); the store is setup, not step input.
+    # rewards N(0,1), terminals Bernoulli(0.01)); the store is setup, not step input.  The seeds of a
+    # GPU read one shared store with independent index streams (seeds only read it).
     rb = ReplayBuffer(N_REPLAY, Box(O), Box(A))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     rb._observations.normal_(generator=g); rb._next_obs.normal_(generator=g)
     rb._actions.uniform_(-1, 1, generator=g); rb._rewards.normal_(generator=g)
     rb._terminals.copy_((torch.rand(N_REPLAY, 1, device=dev, generator=g) < 0.01).float())
     rb._size, rb._top = N_REPLAY, 0
-    tr = build_trainer(args.algo, seed=rank)
-    rb.attach(tr)
-    e = tr._engine
+    S = args.seeds_per_gpu
+    w = _Single(args, rank, rb) if S == 1 else _Group(args, rank, world, rb)
+    e = w.engine
     K, W = args.steps, args.warmup
     np.random.seed(rank)
 
@@ -202,38 +257,33 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
-    idx_all = torch.from_numpy(np.random.randint(0, N_REPLAY, (W + K, B))).to(dev)
+    idx_all = torch.from_numpy(np.random.randint(0, N_REPLAY, (W + K, S, B))).to(dev)
     stream = torch.cuda.current_stream()
     for i in range(W):
-        rb.gather_into(e, idx_all[i], B)
-        e.step()
+        w.device_step(idx_all[i])
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for i in range(W, W + K):
-        rb.gather_into(e, idx_all[i], B)
-        e.step()
+        w.device_step(idx_all[i])
     ev1.record(stream)
     barrier()
     ms_dev = ev0.elapsed_time(ev1)
     clk = clocks.stop()
 
     # ---------------- end to end through the public API ----------------
-    sc_host = torch.zeros(16).pin_memory()
+    sc_host = torch.zeros((S, 16)).pin_memory()
     for _ in range(W):
-        batch = rb.random_batch(B); batch['buffer'] = rb
-        tr.train(batch)
-        sc_host.copy_(e.scalars(), non_blocking=True); stream.synchronize()
+        w.api_step()
+        sc_host.copy_(w.scalars().view(S, 16), non_blocking=True); stream.synchronize()
     barrier()
     ev0.record(stream)
     t0 = time.perf_counter()
     for _ in range(K):
-        batch = rb.random_batch(B)          # host np.random indices -> pinned -> H2D -> gather kernel
-        batch['buffer'] = rb
-        tr.train(batch)                     # fused step (CUDA graph)
-        sc_host.copy_(e.scalars(), non_blocking=True)   # D2H: alpha, alpha loss, mean log_pi
+        w.api_step()
+        sc_host.copy_(w.scalars().view(S, 16), non_blocking=True)   # D2H: alpha, alpha loss, mean log_pi per seed
         stream.synchronize()
     ev1.record(stream)
     barrier()
@@ -244,9 +294,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # the only collective of the design: per-seed statistics gathered after the timed region
-        stats = e.scalars().clone()
-        out = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(out, stats)
+        from oac_explore_b200.seed_group import allgather_stats
+        ids = [rank + world * i for i in range(S)]
+        allgather_stats(w.scalars().view(S, 16).clone(), ids, S * world)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
     if rank == 0:
@@ -254,33 +304,42 @@ def run_ours(args):
         pk = peaks()
         roof, cpu = None, None
         if world == 1:
-            scratch = build_trainer(args.algo, seed=99)
-            scratch._ensure_engine(B)
-            rb.gather_into(scratch._engine, idx_all[0], B)
-            prof = scratch._engine.profile(iters=50)
+            if S == 1:
+                scratch = build_trainer(args.algo, seed=99)
+                scratch._ensure_engine(B)
+                se = scratch._engine
+            else:
+                from oac_explore_b200.seed_group import SACSeedGroup
+                scratch = SACSeedGroup(list(range(S)), O, A, hidden=H, batch=B, gemm_path=GEMM_PATH, **HP)
+                se = scratch.engine
+            rb.gather_into(se, idx_all[0], B, n_seeds=S)
+            prof = se.profile(iters=50 if S == 1 else 10)
             gemm_ms = sum(p[1] for p in prof if p[2])
-            gemm_flops = sum(p[3] for p in prof if p[2])
+            gemm_flops = sum(p[3] for p in prof if p[2]) * S
             all_ms = sum(p[1] for p in prof)
             tf32_peak = pk["bf16"] / 2.0          # kind::tf32 runs at half the bf16 rate
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_stage_kernel (fp32 SIMT FFMA path, all GEMM stages of one step)",
+            kname = {0: "gemm_stage_kernel (fp32 SIMT FFMA)", 1: "gemm_tc_kernel (tcgen05 kind::tf32, TMEM accumulators)",
+                     2: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32 split, TMEM accumulators)"}[GEMM_PATH]
+            roof = {"bound": "tensor", "kernel": kname + ", all GEMM stages of one step",
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                     "peak_source": "%s bf16 %.1f TFLOP/s / 2 (tf32 rate)" % (pk["source"], pk["bf16"]),
                     "traffic": None, "share_of_step_kernel_time": gemm_ms / all_ms,
-                    "algorithmic_flops_per_step": FLOP_PER_UPDATE[args.algo], "executed_flops_per_step": gemm_flops,
+                    "algorithmic_flops_per_step": FLOP_PER_UPDATE[args.algo] * S, "executed_flops_per_step": gemm_flops,
                     "stages_ms": {p[0] + "#%d" % i: round(p[1], 5) for i, p in enumerate(prof)}}
             # replay gather: HBM roofline, timed alone over many launches
             for _ in range(5):
-                rb.gather_into(e, idx_all[0], B)
+                rb.gather_into(e, idx_all[0], B, n_seeds=S)
             ev0.record(stream)
             R = 200
             for i in range(R):
-                rb.gather_into(e, idx_all[i % (W + K)], B)
+                rb.gather_into(e, idx_all[i % (W + K)], B, n_seeds=S)
             ev1.record(stream); torch.cuda.synchronize()
             g_ms = ev0.elapsed_time(ev1) / R
-            roof["replay_gather"] = {"bound": "hbm", "achieved": GATHER_BYTES / (g_ms * 1e-3) / 1e9, "peak": pk["hbm"],
-                                     "unit": "GB/s", "frac": GATHER_BYTES / (g_ms * 1e-3) / 1e9 / pk["hbm"],
-                                     "us_per_batch": g_ms * 1e3, "algorithmic_bytes": GATHER_BYTES}
+            roof["replay_gather"] = {"bound": "hbm", "achieved": S * GATHER_BYTES / (g_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                                     "unit": "GB/s", "frac": S * GATHER_BYTES / (g_ms * 1e-3) / 1e9 / pk["hbm"],
+                                     "us_per_launch": g_ms * 1e3, "algorithmic_bytes": S * GATHER_BYTES,
+                                     "note": "launch time includes the Python/ctypes call overhead at S=1"}
             threads = os.cpu_count() or 1
             n_cpu = 150
             rate_all, _ = cpu_reference_rate(n_cpu, 5, threads)
@@ -289,20 +348,22 @@ def run_ours(args):
                    "sample": "%d updates of the oracle port of the reference's PyTorch CPU path (mode A), "
                              "50k-row store sample" % n_cpu,
                    "single_thread_value": rate_1}
-        n_seeds = world
-        line = {"metric": "OAC grad-updates/sec (Humanoid shapes, B=256)", "value": n_seeds * K / (ms_dev * 1e-3),
+        n_seeds = world * S
+        workload = ("OAC Humanoid-v2 shapes (obs 376, act 17) synthetic 1M replay, batch 256, twin-Q 2x256, "
+                    "%d seed%s per B200" % (S, "" if S == 1 else "s batched as grouped GEMMs"))
+        line = {"metric": "OAC grad-updates/sec (Humanoid shapes, B=256)" if S == 1 else
+                          "OAC seed-updates/sec (Humanoid shapes, B=256, %d seeds per GPU)" % S,
+                "value": n_seeds * K / (ms_dev * 1e-3),
                 "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "OAC Humanoid-v2 shapes (obs 376, act 17) synthetic 1M replay, batch 256, "
-                                       "twin-Q 2x256, 1 seed per B200" if args.algo == "sac" else args.algo,
-                           "algo": args.algo, "seeds_per_gpu": 1, "gemm_path": "fp32-simt", "stale_graph_mode": "A",
+                "config": {"workload": workload if args.algo == "sac" else args.algo,
+                           "algo": args.algo, "seeds_per_gpu": S, "gemm_path": args.gemm_path, "stale_graph_mode": "A",
                            "l2": "inputs are random rows of a 3.1 GB replay store (>> 126 MB L2); the 3.4 MB of "
-                                 "weights stay cache-resident as in the real training loop; no explicit flush",
+                                 "weights per seed stay cache-resident as in the real training loop; no explicit flush",
                            "cuda_graph": True},
                 "clocks": clk,
-                "e2e": {"value": n_seeds * K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 8,
-                        "d2h_bytes_per_step": 64, "ms_per_step": ms_e2e / K,
-                        "api": "ReplayBuffer.random_batch(256) + SACTrainer.train(batch) + D2H scalars, sync per step"},
+                "e2e": {"value": n_seeds * K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": S * B * 8,
+                        "d2h_bytes_per_step": S * 64, "ms_per_step": ms_e2e / K, "api": w.api},
                 "gpu_launches": (e.launches_per_step + 1) * K * 2,
                 "launches_per_step": e.launches_per_step + 1}
         if roof is not None:
@@ -321,7 +382,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="sac", choices=["sac", "poac", "goac"])
+    ap.add_argument("--seeds-per-gpu", type=int, default=1,
+                    help="independent OAC seeds batched per GPU (BASELINE config 5: 64 total)")
+    ap.add_argument("--gemm-path", default="tf32x3", choices=list(GEMM_PATHS),
+                    help="fp32: SIMT FFMA; tf32: tcgen05 kind::tf32; tf32x3: tcgen05 3xTF32 (fp32-grade accuracy)")
     args = ap.parse_args()
+    global GEMM_PATH
+    GEMM_PATH = GEMM_PATHS[args.gemm_path]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         if args.steps > 400:

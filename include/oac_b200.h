@@ -30,7 +30,7 @@
  *   - calls are asynchronous on the caller-supplied stream (a cudaStream_t passed
  *     as void*); a handle must not be used from two streams at once.
  *   - all arithmetic is fp32 (the reference casts every batch with .float(),
- *     utils/pytorch_util.py:76-77); GEMM_TF32 selects the tcgen05 kind::tf32 path.
+ *     utils/pytorch_util.py:76-77); OacConfig.gemm_path selects SIMT fp32 or the tcgen05 kind::tf32 paths.
  */
 #ifndef OAC_B200_H
 #define OAC_B200_H
@@ -47,7 +47,9 @@ extern "C" {
 enum { OAC_E_INVALID = -1, OAC_E_UNSUPPORTED = -2, OAC_E_NOMEM = -3 };
 
 enum OacAlgo { OAC_ALGO_SAC = 0, OAC_ALGO_POAC = 1, OAC_ALGO_GOAC = 2 };
-enum OacGemmPath { OAC_GEMM_FP32 = 0, OAC_GEMM_TF32 = 1 };
+/* FP32: SIMT FFMA.  TF32: tcgen05 kind::tf32, one MMA per product (rel ~1e-3).  TF32X3: tcgen05 with the
+ * 3xTF32 operand split (a_hi b_hi + a_hi b_lo + a_lo b_hi), fp32-grade accuracy on the tensor pipe. */
+enum OacGemmPath { OAC_GEMM_FP32 = 0, OAC_GEMM_TF32 = 1, OAC_GEMM_TF32X3 = 2 };
 enum OacNetKind { OAC_NET_POLICY = 0, OAC_NET_Q = 1, OAC_NET_SCALAR = 2 };
 
 /* ---- trainer configuration (mirrors the reference constructors' kwargs) ---- */
@@ -189,6 +191,13 @@ int oac_trainer_launches_per_step(const OacTrainer* t);
  * names: n_stages pointers to static strings.  Synchronises the stream. */
 int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_stages, float* ms, int32_t* is_gemm,
                         double* flops, const char** names, int32_t* n_stages, void* stream);
+
+/* Test / measurement aid: one GEMM C[M,N] = act(sum_k A(m,k) B(n,k) + bias[n]) through the fp32 SIMT stage
+ * kernel (gemm_path 0) or the tcgen05 kind::tf32 one (1).  a_trans: A(m,k) = A[k*lda+m] else A[m*lda+k];
+ * b_trans: B(n,k) = B[k*ldb+n] else B[n*ldb+k].  Synchronises the stream. */
+int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_trans, int32_t M, int32_t N, int32_t K,
+                   const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                   const float* bias, int32_t relu, void* stream);
 
 /* ---- inference ---- */
 /* TanhGaussianPolicy.forward on n rows: obs [n, obs_ld]; eps [n,A] or NULL (deterministic).

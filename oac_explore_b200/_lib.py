@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liboac_b200.so")
 
 OAC_MAX_NETS = 48
 ALGO_SAC, ALGO_POAC, ALGO_GOAC = 0, 1, 2
-GEMM_FP32, GEMM_TF32 = 0, 1
+GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
 NET_POLICY, NET_Q, NET_SCALAR = 0, 1, 2
 EXPLORE_TWIN, EXPLORE_ENSEMBLE, EXPLORE_QUANTILE = 0, 1, 2
 # counters (oac_internal.h)
@@ -94,7 +94,7 @@ EXPORTS = [
     "oac_last_error_string", "oac_abi_version",
     "oac_replay_gather", "oac_replay_gather_dense", "oac_replay_add",
     "oac_trainer_layout", "oac_trainer_create", "oac_trainer_destroy", "oac_trainer_step",
-    "oac_trainer_launches_per_step", "oac_trainer_profile",
+    "oac_trainer_launches_per_step", "oac_trainer_profile", "oac_gemm_debug",
     "oac_policy_forward", "oac_q_forward", "oac_explore",
 ]
 
@@ -126,6 +126,7 @@ def lib():
     L.oac_trainer_step.argtypes = [vp, i32, vp]
     L.oac_trainer_launches_per_step.argtypes = [vp]
     L.oac_trainer_profile.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.oac_gemm_debug.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
     L.oac_policy_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.oac_q_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, u32, vp, vp]
     L.oac_explore.argtypes = [C.POINTER(OacExploreArgs), vp]

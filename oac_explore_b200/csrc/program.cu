@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "glue.cuh"
+#include "gemm_tc.cuh"
 #include "oac_error.h"
 
 namespace oac {
@@ -128,6 +129,7 @@ struct Stage {
     int a_trans = 0, b_trans = 0;   // all tasks of a GEMM stage share the operand layouts
     int kc = 0;
     size_t smem = 0;
+    int use_tc = 0, bn = 0, tmem_cols = 0, n_main = 1;     // tcgen05 path
     int max_tiles = 0;
     int max_rows = 0;
     const char* name = "";
@@ -149,6 +151,7 @@ struct OacTrainer {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     bool use_graph = true;
     int n_opt = 0;
+    long long* tc_dbg = nullptr;
 };
 
 namespace oac {
@@ -561,6 +564,48 @@ static int finalize(OacTrainer& t) {
                 if (g.a_trans != s.a_trans || g.b_trans != s.b_trans || (g.a_trans && !g.b_trans))
                     return set_error(OAC_E_INVALID, "internal: mixed operand layouts in one GEMM stage");
             }
+            if (t.cfg.gemm_path == OAC_GEMM_TF32 || t.cfg.gemm_path == OAC_GEMM_TF32X3) {
+                const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
+                // tcgen05 path: 128 x BN tiles.  Pick the largest BN that still fills the chip.
+                s.use_tc = 1;
+                const int bn_min = s.b_trans ? 32 : 16;
+                int nmax = 0;
+                for (auto& g : s.gemm) nmax = std::max(nmax, g.N + ((g.epi == EPI_ADAM && g.has_bias) ? 1 : 0));
+                auto ctas = [&](int bn) {
+                    long long n = 0;
+                    for (auto& g : s.gemm) {
+                        int ncols = g.N + ((g.epi == EPI_ADAM && g.has_bias) ? 1 : 0);
+                        n += (long long)((g.M + 127) / 128) * ((ncols + bn - 1) / bn);
+                    }
+                    return n * seeds;
+                };
+                // ring: 2 x (128 + BN) x kc x 4 B must fit 227 KB -> BN <= 64.  One CTA per SM: take the narrowest
+                // tile whose grid still fits ONE wave of 148 CTAs (a second, partial wave doubles the stage time).
+                int bn = 64;
+                while (bn > bn_min) {
+                    if (nmax <= bn / 2) { bn >>= 1; continue; }        // narrower tile is free
+                    if (ctas(bn / 2) <= 148) { bn >>= 1; continue; }   // more CTAs, still one wave
+                    break;
+                }
+                s.bn = bn;
+                s.kc = x3 ? 64 : 128;
+                if (x3) {
+                    const int nchunks = (kmax + s.kc - 1) / s.kc;
+                    s.n_main = std::max(1, std::min(nchunks, 512 / bn - 1));
+                }
+                int cols = (x3 ? (s.n_main + 1) : 1) * bn;
+                s.tmem_cols = 32;
+                while (s.tmem_cols < cols) s.tmem_cols <<= 1;
+                s.smem = 2 * (size_t)(128 + bn) * s.kc * sizeof(float) * (x3 ? 2 : 1) + 1024;
+                s.max_tiles = 0;
+                for (auto& g : s.gemm) {
+                    int ncols = g.N + ((g.epi == EPI_ADAM && g.has_bias) ? 1 : 0);
+                    g.tiles_m = (g.M + 127) / 128; g.tiles_n = (ncols + bn - 1) / bn;
+                    s.max_tiles = std::max(s.max_tiles, g.tiles_m * g.tiles_n);
+                }
+                if (int e = upload(t, s.gemm.data(), s.gemm.size(), &s.dev)) return e;
+                continue;
+            }
             s.small_tiles = (tiles64 * seeds < 2 * 148);
             const int bm = s.small_tiles ? 32 : 64;
             // largest K chunk (multiple of 4) whose A+B tiles fit the shared-memory budget
@@ -603,6 +648,22 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
         if (s.kind == ST_GEMM) {
             StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
+            if (s.use_tc) {
+                TcStageParams tp; tp.sp = sp; tp.bn = s.bn; tp.kc = s.kc; tp.tmem_cols = s.tmem_cols; tp.n_main = s.n_main; tp.dbg = t.tc_dbg;
+                const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
+                if (!s.a_trans && !s.b_trans) {
+                    if (x3) gemm_tc_kernel<false, false, true><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                    else gemm_tc_kernel<false, false, false><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                } else if (!s.a_trans) {
+                    if (x3) gemm_tc_kernel<false, true, true><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                    else gemm_tc_kernel<false, true, false><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                } else {
+                    if (x3) gemm_tc_kernel<true, true, true><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                    else gemm_tc_kernel<true, true, false><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                }
+                OAC_CUDA(cudaGetLastError());
+                continue;
+            }
             const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
             switch (sel) {
                 case 0: gemm_stage_kernel<32, 32, 2, 2, false, false><<<grid, 256, s.smem, st>>>(sp); break;
@@ -653,7 +714,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     if (!cfg || !buf || !out) return set_error(OAC_E_INVALID, "null argument");
     if (!buf->params || !buf->adam_m || !buf->adam_v || !buf->work || !buf->io || !buf->counters)
         return set_error(OAC_E_INVALID, "null buffer");
-    if (cfg->gemm_path != OAC_GEMM_FP32) return set_error(OAC_E_UNSUPPORTED, "gemm_path: only OAC_GEMM_FP32 is built");
+    if (cfg->gemm_path < OAC_GEMM_FP32 || cfg->gemm_path > OAC_GEMM_TF32X3) return set_error(OAC_E_INVALID, "gemm_path");
     OacTrainer* t = new OacTrainer();
     t->cfg = *cfg;
     if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
@@ -687,6 +748,12 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>);
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>);
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>);
+        opt_in((const void*)gemm_tc_kernel<false, false, false>);
+        opt_in((const void*)gemm_tc_kernel<false, true, false>);
+        opt_in((const void*)gemm_tc_kernel<true, true, false>);
+        opt_in((const void*)gemm_tc_kernel<false, false, true>);
+        opt_in((const void*)gemm_tc_kernel<false, true, true>);
+        opt_in((const void*)gemm_tc_kernel<true, true, true>);
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
@@ -775,4 +842,62 @@ extern "C" int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_sta
     }
     *n_stages = n;
     return 0;
+}
+
+// Test / measurement aid: one GEMM  C[M,N] = epi(sum_k A(m,k) B(n,k))  through either stage kernel.
+extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_trans, int32_t M, int32_t N, int32_t K,
+                              const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                              const float* bias, int32_t relu_, void* stream) {
+    if (!A || !B || !C || M < 1 || N < 1 || K < 1) return set_error(OAC_E_INVALID, "oac_gemm_debug: bad argument");
+    if (a_trans && !b_trans) return set_error(OAC_E_UNSUPPORTED, "oac_gemm_debug: (a_trans, !b_trans) is unused");
+    OacTrainer t;
+    memset(&t.cfg, 0, sizeof(t.cfg));
+    t.cfg.n_seeds = 1; t.cfg.gemm_path = gemm_path;
+    memset(&t.as, 0, sizeof(t.as));          // null arena bases: offsets are absolute addresses / 4
+    memset(&t.hyper, 0, sizeof(t.hyper));
+    auto ref = [](const float* p) { return Ref{AR_WORK, (long long)(reinterpret_cast<uintptr_t>(p) / 4)}; };
+    t.stages.emplace_back();
+    Stage& s = t.stages.back();
+    s.kind = ST_GEMM; s.name = "debug";
+    GemmTask g; memset(&g, 0, sizeof(g));
+    g.A = ref(A); g.B = ref(B); g.C = ref(C); g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.a_trans = a_trans; g.b_trans = b_trans; g.M = M; g.N = N; g.K = K;
+    g.epi = bias ? (relu_ ? EPI_BIAS_RELU : EPI_BIAS) : EPI_STORE;
+    if (bias) g.bias = ref(bias);
+    g.target_off = g.target_bias_off = -1;
+    s.gemm.push_back(g);
+    {
+        const int big = 212 * 1024;
+        cudaFuncSetAttribute((const void*)gemm_stage_kernel<32, 32, 2, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_stage_kernel<32, 32, 2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_stage_kernel<32, 32, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    }
+    int rc = finalize(t);
+    const char* dbg_env = getenv("OAC_TC_DEBUG");
+    const int dbg_n = 64;
+    if (dbg_env && dbg_env[0] == '1') { cudaMalloc(&t.tc_dbg, sizeof(long long) * 8 * dbg_n * 8); cudaMemset(t.tc_dbg, 0, sizeof(long long) * 8 * dbg_n * 8); }
+    if (!rc) rc = launch_stages(t, 0, (cudaStream_t)stream);
+    if (!rc && t.tc_dbg) rc = launch_stages(t, 0, (cudaStream_t)stream);      // second (warm) run is the one reported
+    cudaStreamSynchronize((cudaStream_t)stream);
+    if (t.tc_dbg) {
+        std::vector<long long> h(8 * dbg_n);
+        cudaMemcpy(h.data(), t.tc_dbg, sizeof(long long) * 8 * dbg_n, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 3; ++i) {
+            fprintf(stderr, "[tc dbg] cta %d:", i);
+            for (int j = 1; j < 8; ++j) fprintf(stderr, " %lld", h[8 * i + j] - h[8 * i]);
+            fprintf(stderr, "  (alloc | chunk0 landed | pass done | mma issued | mma done | epilogue | dealloc)\n");
+        }
+        cudaFree(t.tc_dbg);
+    }
+    for (void* p : t.dev_allocs) cudaFree(p);
+    return rc;
 }

@@ -31,7 +31,8 @@ class GaussianTrainer(_EngineTrainer):
                  q_max=100, pac=False, ensemble=False, n_policies=1, share_layers=False, r_mellow_max=1.,
                  b_mellow_max=None, mellow_max=False, counts=False, mean_update=False, global_opt=False,
                  std_soft_update=False, std_soft_update_prob=0., train_bias=True, use_target_policy=False,
-                 rescale_targets_around_mean=False, rng_seed=None):
+                 rescale_targets_around_mean=False, rng_seed=None, gemm_path=_lib.GEMM_FP32):
+        self.gemm_path = gemm_path
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("the fused step implements torch.optim.Adam")
         if ensemble or global_opt or std_soft_update or mean_update or use_target_policy or not deterministic:
@@ -92,7 +93,7 @@ class GaussianTrainer(_EngineTrainer):
                     discount=self.discount, reward_scale=self.reward_scale,
                     soft_target_tau=self.soft_target_tau, policy_lr=self.policy_lr, qf_lr=self.qf_lr,
                     std_lr=self.std_lr, standard_bound=self.standard_bound, std_init=float(self.std_init),
-                    rng_seed=self._rng_seed)
+                    rng_seed=self._rng_seed, gemm_path=self.gemm_path)
 
     def _net_objects(self):
         # layout order: policy, target_policy, q, [std], log_alpha | q_target, [std_target]

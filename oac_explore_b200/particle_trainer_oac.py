@@ -24,7 +24,8 @@ class ParticleTrainer(_EngineTrainer):
                  target_entropy=None, deterministic=True, q_min=0, q_max=100, ensemble=False, n_policies=1,
                  share_layers=False, r_mellow_max=1., b_mellow_max=None, mellow_max=False, counts=False,
                  mean_update=False, global_opt=False, std_soft_update=False, std_soft_update_prob=0.,
-                 train_bias=True, lb=0.1, rng_seed=None):
+                 train_bias=True, lb=0.1, rng_seed=None, gemm_path=_lib.GEMM_FP32):
+        self.gemm_path = gemm_path
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("the fused step implements torch.optim.Adam")
         if ensemble or global_opt or std_soft_update or mean_update or mellow_max:
@@ -81,7 +82,7 @@ class ParticleTrainer(_EngineTrainer):
                     target_update_period=self.target_update_period, discount=self.discount,
                     reward_scale=self.reward_scale, soft_target_tau=self.soft_target_tau,
                     policy_lr=self.policy_lr, qf_lr=self.qf_lr, target_entropy=self.target_entropy,
-                    rng_seed=self._rng_seed)
+                    rng_seed=self._rng_seed, gemm_path=self.gemm_path)
 
     def _net_objects(self):
         # layout order: policy, qf[0..n), log_alpha | tf[0..n)

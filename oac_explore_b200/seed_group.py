@@ -1,0 +1,128 @@
+"""Independent OAC seeds batched in one handle (BASELINE.json config 5) and sharded over GPUs.
+
+The reference's only parallelism is one OS process per seed, pinned to GPU ``seed % n_gpus``
+(main.py:575-576, reproduce_*.sh).  Here the seeds of one GPU share ONE engine: every stage of the
+fused step is launched once with ``grid.z = n_seeds`` (grouped GEMMs over seeds x networks), each
+seed keeping its own weights, Adam state, entropy temperature, step counters and noise stream.
+Seeds never exchange data on the step path; ``allgather_stats`` (NCCL over NVLink in production,
+gloo in the CPU tests) only collects the per-seed statistics vector for reporting.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine, make_config
+from .networks import get_policy_producer, get_q_producer
+
+N_STATS = 8
+STAT_NAMES = ("alpha", "alpha_loss", "log_pi_mean", "qf1_loss", "qf2_loss", "q_target_mean", "q1_pred_mean",
+              "policy_loss")
+
+
+def partition_seeds(n_seeds_total, rank, world_size):
+    """Seed ids owned by ``rank``: the reference's ``seed % n_gpus`` placement (main.py:575-576)."""
+    return [s for s in range(n_seeds_total) if s % world_size == rank]
+
+
+class SACSeedGroup(object):
+    """S independent SACTrainer instances (trainer/trainer.py:14-97) in one engine."""
+
+    def __init__(self, seed_ids, obs_dim, act_dim, hidden=256, batch=256, gemm_path=_lib.GEMM_TF32,
+                 discount=0.99, reward_scale=1.0, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3,
+                 target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None,
+                 stale_graph_mode="A", rng_seed=0):
+        self.seed_ids = list(seed_ids)
+        S = len(self.seed_ids)
+        if S < 1:
+            raise ValueError("empty seed group")
+        cfg = make_config(_lib.ALGO_SAC, obs_dim, act_dim, hidden, batch, n_seeds=S,
+                          auto_alpha=use_automatic_entropy_tuning, stale_graph_mode=stale_graph_mode,
+                          target_update_period=target_update_period, gemm_path=gemm_path, discount=discount,
+                          reward_scale=reward_scale, soft_target_tau=soft_target_tau, policy_lr=policy_lr,
+                          qf_lr=qf_lr, target_entropy=target_entropy, rng_seed=rng_seed)
+        self.engine = Engine(cfg)
+        self.O, self.A, self.B = obs_dim, act_dim, batch
+        pp = get_policy_producer(obs_dim, act_dim, [hidden, hidden])
+        qp = get_q_producer(obs_dim, act_dim, [hidden, hidden])
+        self.nets = []          # per seed: OrderedDict(policy, qf1, qf2, target_qf1, target_qf2)
+        order = (("policy", 0), ("qf1", 1), ("qf2", 2), ("target_qf1", 4), ("target_qf2", 5))
+        for s, sid in enumerate(self.seed_ids):
+            torch.manual_seed(sid)                      # main.py:115: torch.manual_seed(seed) before construction
+            objs = OrderedDict()
+            for name, idx in order:                     # construction order of trainer/trainer.py:58-71
+                net = pp() if name == "policy" else qp()
+                net._bind(self.engine.net_views(idx, seed=s), self.engine.params[s], self.engine.net_layout(idx))
+                objs[name] = net
+            self.nets.append(objs)
+        self._n_train_steps_total = 0
+        self._idx_host = torch.zeros((S, batch), dtype=torch.int64).pin_memory()
+        self._idx_dev = torch.zeros((S, batch), dtype=torch.int64, device=self.engine.device)
+
+    @property
+    def n_seeds(self):
+        return len(self.seed_ids)
+
+    def gather(self, replay, indices):
+        """indices: [S, B] int64 (host numpy or device tensor) -> one gather launch for all seeds."""
+        if isinstance(indices, np.ndarray):
+            self._idx_host.numpy()[...] = indices
+            self._idx_dev.copy_(self._idx_host, non_blocking=True)
+            indices = self._idx_dev
+        replay.gather_into(self.engine, indices, self.B, seed=0, n_seeds=self.n_seeds)
+
+    def load_batch(self, seed_slot, batch):
+        f = lambda t: t.to(self.engine.device, torch.float32)
+        self.engine.load_batch(f(batch['observations']), f(batch['actions']), f(batch['rewards']),
+                               f(batch['terminals']), f(batch['next_observations']), seed=seed_slot)
+
+    def inject_noise(self, seed_slot, eps_obs, eps_next):
+        self.engine.set_eps(eps_obs.to(self.engine.device), eps_next.to(self.engine.device), seed=seed_slot)
+
+    def step(self, external_eps=False):
+        self.engine.step(external_eps=external_eps)
+        self._n_train_steps_total += 1
+
+    def stats(self):
+        """[S, N_STATS] fp32 device tensor (STAT_NAMES) of the last step -- the all-gather payload."""
+        e, L, B, S = self.engine, self.engine.lay, self.B, self.n_seeds
+        io = e.io
+        sc = io[:, L.off_scalars:L.off_scalars + 3]
+        qp = io[:, L.off_q_pred:L.off_q_pred + 2 * B].view(S, B, 2)
+        qt = io[:, L.off_q_target:L.off_q_target + 2 * B].view(S, B, 2)[:, :, 0]
+        qn = io[:, L.off_q_new:L.off_q_new + 2 * B].view(S, B, 2)
+        lp = io[:, L.off_log_pi:L.off_log_pi + B]
+        out = torch.empty((S, N_STATS), dtype=torch.float32, device=e.device)
+        out[:, 0:3] = sc
+        out[:, 3] = ((qp[:, :, 0] - qt) ** 2).mean(dim=1)
+        out[:, 4] = ((qp[:, :, 1] - qt) ** 2).mean(dim=1)
+        out[:, 5] = qt.mean(dim=1)
+        out[:, 6] = qp[:, :, 0].mean(dim=1)
+        out[:, 7] = (lp - torch.minimum(qn[:, :, 0], qn[:, :, 1])).mean(dim=1)
+        return out
+
+
+def allgather_stats(local_stats, seed_ids, n_seeds_total, group=None):
+    """Collects every rank's [S_local, n] statistics into one [n_seeds_total, n] tensor ordered by seed id.
+    The only collective of the design; runs once per reporting interval, never inside a step."""
+    import torch.distributed as dist
+    n = local_stats.shape[1]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        out = torch.zeros((n_seeds_total, n), dtype=local_stats.dtype, device=local_stats.device)
+        out[torch.as_tensor(list(seed_ids), device=local_stats.device)] = local_stats
+        return out
+    world = dist.get_world_size(group)
+    per = (n_seeds_total + world - 1) // world
+    pad = torch.zeros((per, n + 1), dtype=local_stats.dtype, device=local_stats.device)
+    pad[:, n] = -1
+    pad[:len(seed_ids), :n] = local_stats
+    pad[:len(seed_ids), n] = torch.as_tensor(list(seed_ids), dtype=local_stats.dtype, device=local_stats.device)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = torch.zeros((n_seeds_total, n), dtype=local_stats.dtype, device=local_stats.device)
+    for b in bufs:
+        ids = b[:, n]
+        keep = ids >= 0
+        out[ids[keep].long()] = b[keep, :n]
+    return out

@@ -1,0 +1,64 @@
+"""The two GEMM stage kernels in isolation (fp32 SIMT and tcgen05 kind::tf32) against torch fp32/fp64:
+every operand-layout combination the step uses (forward X W^T, dX = dY W, dW = dY^T X), ragged edges."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(path, a_trans, b_trans, M, N, K, bias=False, relu=False, pad=0, seed=0):
+    from oac_explore_b200 import _lib
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    lda = (M if a_trans else K) + pad
+    ldb = (N if b_trans else K) + pad
+    ldc = N + pad
+    A = torch.randn((K if a_trans else M, lda), device='cuda', generator=g)
+    B = torch.randn((K if b_trans else N, ldb), device='cuda', generator=g)
+    Cm = torch.full((M, ldc), 7.0, device='cuda')
+    bvec = torch.randn(N, device='cuda', generator=g) if bias else None
+    _lib.check(_lib.lib().oac_gemm_debug(path, int(a_trans), int(b_trans), M, N, K, _lib.ptr(A), lda, _lib.ptr(B), ldb,
+                                         _lib.ptr(Cm), ldc, _lib.ptr(bvec), int(relu), _lib.current_stream()),
+               "oac_gemm_debug")
+    Am = (A[:, :M].t() if a_trans else A[:, :K]).double()
+    Bm = (B[:, :N].t() if b_trans else B[:, :K]).double()
+    ref = Am @ Bm.t()
+    if bias:
+        ref = ref + bvec.double()
+    if relu:
+        ref = torch.relu(ref)
+    assert torch.all(Cm[:, N:] == 7.0), "wrote outside the N columns"
+    return Cm[:, :N].double().cpu(), ref.cpu()
+
+
+SHAPES = [(256, 256, 256), (512, 256, 376), (256, 256, 393), (256, 34, 256), (256, 1, 256), (256, 17, 256),
+          (256, 393, 256), (34, 256, 256), (1, 256, 256), (100, 70, 50), (128, 16, 8), (130, 33, 133)]
+LAYOUTS = [(0, 0), (0, 1), (1, 1)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
+def test_simt_gemm(M, N, K, a_trans, b_trans):
+    for pad in (0, 3):
+        got, ref = run_gemm(0, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=(b_trans == 0 and a_trans == 0), pad=pad)
+        assert rel_err(got, ref) <= 2e-6, (pad, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
+def test_tcgen05_tf32_gemm(M, N, K, a_trans, b_trans):
+    for pad in (0, 3):
+        got, ref = run_gemm(1, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=False, pad=pad)
+        # TF32 operands (10-bit mantissa), fp32 accumulate: ~5e-4 relative on random data
+        assert rel_err(got, ref) <= 1.5e-3, (pad, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
+def test_tcgen05_3xtf32_gemm(M, N, K, a_trans, b_trans):
+    for pad in (0, 3):
+        got, ref = run_gemm(2, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=False, pad=pad)
+        assert rel_err(got, ref) <= 3e-6, (pad, rel_err(got, ref))
