@@ -93,18 +93,24 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ sm, int sld, cons
                                            int r0, int R, int rmax, int c0, int CW, int cmax, bool vec_ok) {
     const int tid = threadIdx.x;
     if (vec_ok) {
+        // lanes over a row's 16-byte chunks (coalesced); short rows share a warp (lpr lanes per row, a power of
+        // two, so the index math is shifts only)
         const int cpr = (CW + 3) >> 2;
-        const int total = R * cpr;
-        for (int c = tid; c < total; c += NT) {
-            const int r = c / cpr, q = (c - r * cpr) << 2;
-            const int gr = r0 + r, gc = c0 + q;
-            int bytes = 0;
-            const float* p = src;
-            if (gr < rmax && gc < cmax) {
-                bytes = min(16, (cmax - gc) * 4);
-                p = src + (long long)gr * ld + gc;
+        const int lpr_shift = cpr <= 8 ? 3 : (cpr <= 16 ? 4 : 5);
+        const int lpr = 1 << lpr_shift;
+        const int rows_per_pass = NT >> lpr_shift;
+        const int q0 = tid & (lpr - 1);
+        for (int r = tid >> lpr_shift; r < R; r += rows_per_pass) {
+            const int gr = r0 + r;
+            const float* prow = src + (long long)gr * ld + c0;
+            float* srow = sm + r * sld;
+            for (int q = q0; q < cpr; q += lpr) {
+                const int gc = c0 + (q << 2);
+                int bytes = 0;
+                const float* p = src;
+                if (gr < rmax && gc < cmax) { bytes = min(16, (cmax - gc) * 4); p = prow + (q << 2); }
+                cp_async16_zfill(srow + (q << 2), p, bytes);
             }
-            cp_async16_zfill(sm + r * sld + q, p, bytes);
         }
     } else {
         const int cw4 = (CW + 3) & ~3;

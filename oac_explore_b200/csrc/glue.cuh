@@ -12,8 +12,23 @@ namespace oac {
 // =====================================================================================
 // policy heads: mean / log_std GEMV + TanhNormal.rsample + log_prob  (trainer/policies.py:260-316)
 // =====================================================================================
+constexpr int GLUE_MAX_HR = 16;     // hidden <= 512: one hidden row = <= 16 registers per lane
+
+// contiguous global -> shared copy with every load in flight at once (cp.async); caller waits + syncs
+__device__ __forceinline__ void stage_contig(float* dst, const float* __restrict__ src, int n) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)__cvta_generic_to_shared(dst)) & 15) == 0;
+    if (vec) {
+        const int n4 = n >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) cp_async16_zfill(dst + 4 * i, src + 4 * i, 16);
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) cp_async4(dst + i, src + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async4(dst + i, src + i);
+    }
+}
+
 struct PolicyHeadTask {
-    Ref head;           // [rows, 2A] head outputs (mean | raw log_std), computed by a GEMM stage
+    Ref h2;             // [rows, H] last hidden activation
+    Ref w, b;           // heads [2A, H] (mean rows then log_std rows), [2A]
     int rows;           // B or 2B
     int out_row0;       // first row in the io outputs (log_pi [.], mean/log_std [., A])
     int dst_block[2];   // X row block (units of B rows) receiving tanh actions, per B-row block
@@ -42,50 +57,81 @@ struct PolicyHeadParams {
     int n_opt_counters;      // counters CNT_OPT0 .. CNT_OPT0+n-1 are bumped once per step here
 };
 
-// one warp per row: lane j handles action dim j (+32 per pass)
+// Fused head layer + sampling: the [2A, H] head weights are staged in shared memory once per CTA; GLUE_G warps
+// share one row (each keeps the hidden row in registers and reduces every GLUE_G-th pair of dot products with
+// shuffles), then one of them runs the per-action-dim sampling math.  dyn smem: (2A*H + 2A + SPC*2A) floats.
 __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
+    extern __shared__ __align__(16) float s_ph[];
     const PolicyHeadTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * GLUE_WARPS + warp;
-    const int A = p.A, B = p.B;
+    const int sl = warp / GLUE_G, g = warp % GLUE_G;
+    const int row = blockIdx.x * GLUE_SPC + sl;
+    const int A = p.A, B = p.B, H = p.H;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
     int32_t* cnt = p.as.counters + seed * p.as.n_counters;
     const int step = cnt[CNT_TRAIN_STEPS];
 
+    float* Ws = s_ph;
+    float* bs = s_ph + 2 * A * H;
+    float* outv = bs + 2 * A + sl * 2 * A;                  // this row's head outputs (mean | raw log_std)
+    stage_contig(Ws, resolve(p.as, T.w, seed), 2 * A * H);
+    stage_contig(bs, resolve(p.as, T.b, seed), 2 * A);
+    float hreg[GLUE_MAX_HR];
     if (row < T.rows) {
-        const float* __restrict__ head = resolve(p.as, T.head, seed) + (long long)row * 2 * A;
+        const float* __restrict__ h = resolve(p.as, T.h2, seed) + (long long)row * H;
+#pragma unroll
+        for (int c = 0; c < GLUE_MAX_HR; ++c) hreg[c] = (lane + 32 * c < H) ? __ldg(h + lane + 32 * c) : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (row < T.rows) {
+        for (int j = g; j < A; j += GLUE_G) {
+            const float* wm = Ws + j * H;
+            const float* ws = Ws + (A + j) * H;
+            float sm = 0.f, ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < GLUE_MAX_HR; ++c) {
+                const int k = lane + 32 * c;
+                if (k < H) { sm = fmaf(hreg[c], wm[k], sm); ss = fmaf(hreg[c], ws[k], ss); }
+            }
+            sm = warp_sum(sm); ss = warp_sum(ss);
+            if (lane == 0) { outv[j] = sm + bs[j]; outv[A + j] = ss + bs[A + j]; }
+        }
+    }
+    __syncthreads();
+    if (row < T.rows && g == 0) {
         float* save = resolve(p.as, T.save, seed) + (long long)row * 4 * A;
         const int blk = row / B, b = row % B;
         float lp_acc = 0.f;
         for (int j = lane; j < A; j += 32) {
-            const float my_mean = head[j], my_raw = head[A + j];
-            float log_std = fminf(fmaxf(my_raw, LOG_SIG_MIN_F), LOG_SIG_MAX_F);
+            const float mean_j = outv[j], raw_j = outv[A + j];
+            float log_std = fminf(fmaxf(raw_j, LOG_SIG_MIN_F), LOG_SIG_MAX_F);
             float std = expf(log_std);
             float action, eps = 0.f, lp = 0.f;
             if (p.deterministic) {
-                action = tanhf(my_mean);
+                action = tanhf(mean_j);
             } else {
                 if (p.use_external_eps)
                     eps = io[p.off_eps + ((long long)T.eps_slot[blk] * B + b) * A + j];
                 else
                     eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)seed,
                                         (uint32_t)T.eps_slot[blk], (uint32_t)step, (uint32_t)b, (uint32_t)j);
-                float z = fmaf(std, eps, my_mean);
+                float z = fmaf(std, eps, mean_j);
                 action = tanhf(z);
                 // Normal(mean,std).log_prob(z) - log(1 - a^2 + eps)   (policies.py:147-160)
-                float d = z - my_mean;
+                float d = z - mean_j;
                 float var = std * std;
                 lp = -(d * d) / (2.f * var) - logf(std) - 0.91893853320467274178f
                      - logf(1.f - action * action + TANH_EPS_F);
             }
             lp_acc += lp;
             const int orow = T.out_row0 + row;
-            io[p.off_mean + (long long)orow * A + j] = my_mean;
+            io[p.off_mean + (long long)orow * A + j] = mean_j;
             io[p.off_log_std + (long long)orow * A + j] = log_std;
             io[p.off_x + ((long long)T.dst_block[blk] * B + b) * p.x_ld + p.O + j] = action;
             save[0 * A + j] = action; save[1 * A + j] = std;
-            save[2 * A + j] = my_raw; save[3 * A + j] = eps;
+            save[2 * A + j] = raw_j; save[3 * A + j] = eps;
         }
         lp_acc = warp_sum(lp_acc);
         if (lane == 0) io[p.off_log_pi + T.out_row0 + row] = lp_acc;
@@ -147,10 +193,13 @@ constexpr int MAX_HEAD_SRC = 40;
 constexpr int MAX_VALS = 40;
 
 struct HeadSrc {
-    Ref q;           // [*, n_heads] critic head outputs (GEMM stage); sample b uses row row0 + b
+    Ref h2;          // [*, H] hidden activations; sample b uses row row0 + b
     int row0;
+    Ref w3, b3;      // [n_heads, H], [n_heads]
     int n_heads;
     Ref dq;          // [B, n_heads] gradient w.r.t. the (pre-exp) head outputs, written here
+    int write_dh2;   // also emit dh2[b,:] = (dq[b,:] W3) * (h2 > 0) with the CURRENT W3
+    Ref dh2;         // [B, H]
 };
 
 enum CriticMode {
@@ -174,35 +223,74 @@ struct CriticHeadParams {
     float discount, reward_scale, standard_bound, std_init;
 };
 
-constexpr int CRITIC_THREADS = 128;
-
-// one thread per sample
-__global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+// Fused critic head layer + targets / loss gradients + first backward step.  GLUE_G warps share one sample:
+// the (critic, head) dot products are dealt round-robin to them (hidden row in registers, shuffle reduction),
+// one lane then evaluates the algorithm's targets and dLoss/dq, and all GLUE_G warps emit
+// dh2 = (dq W3) * relu'(h2) for the critics whose backward starts here.
+__global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
     const CriticHeadParams& p = *pp;
+    __shared__ float s_vals[GLUE_SPC][MAX_VALS];
+    __shared__ float s_dq[GLUE_SPC][MAX_VALS];
+    __shared__ int s_goff[MAX_HEAD_SRC];
+    __shared__ short s_pair_src[MAX_VALS], s_pair_hd[MAX_VALS];
+    __shared__ int s_npairs;
     const int seed = blockIdx.y;
-    const int b = blockIdx.x * CRITIC_THREADS + threadIdx.x;
-    const int B = p.B;
-    if (b >= B) return;
-    float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
-    float vals[MAX_VALS];
-    {
-        int g = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = warp / GLUE_G, g = warp % GLUE_G;
+    const int b = blockIdx.x * GLUE_SPC + sl;
+    const int B = p.B, H = p.H;
+    if (threadIdx.x == 0) {
+        int n = 0;
         for (int s = 0; s < p.n_src; ++s) {
-            const HeadSrc& S = p.src[s];
-            const float* __restrict__ q = resolve(p.as, S.q, seed) + (long long)(S.row0 + b) * S.n_heads;
-            for (int hd = 0; hd < S.n_heads; ++hd, ++g) vals[g] = q[hd];
+            s_goff[s] = n;
+            for (int hd = 0; hd < p.src[s].n_heads; ++hd, ++n) { s_pair_src[n] = (short)s; s_pair_hd[n] = (short)hd; }
+        }
+        s_npairs = n;
+    }
+    __syncthreads();
+    const bool live = b < B;
+    float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
+    float* vals = s_vals[sl];
+    float* dqv = s_dq[sl];
+    // per-sample scalars: issue the loads now, they are consumed after the head reductions
+    float r_pre = 0.f, d_pre = 0.f, alpha_pre = 0.f, lpn_pre = 0.f, cnt_pre = 0.f;
+    if (live && g == 0 && lane == 0) {
+        r_pre = io[p.off_rewards + b]; d_pre = io[p.off_terminals + b];
+        alpha_pre = io[p.off_scalars + SC_ALPHA]; lpn_pre = io[p.off_log_pi + B + b];
+        cnt_pre = p.counts ? io[p.off_counts + b] : 0.f;
+    }
+    if (live) {
+        for (int pi = g; pi < s_npairs; pi += GLUE_G) {
+            const HeadSrc& S = p.src[s_pair_src[pi]];
+            const int hd = s_pair_hd[pi];
+            const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
+            const float* __restrict__ w = resolve(p.as, S.w3, seed) + (long long)hd * H;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < GLUE_MAX_HR; ++c) {
+                const int k = lane + 32 * c;
+                if (k < H) acc = fmaf(__ldg(h + k), __ldg(w + k), acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) vals[pi] = acc + __ldg(resolve(p.as, S.b3, seed) + hd);
         }
     }
-
+    __syncthreads();
+    // every dq goes to global (GEMM operand of the weight-gradient stage) and to the sample's shared copy
+    auto put = [&](int s, int i, float v) {
+        resolve(p.as, p.src[s].dq, seed)[(long long)b * p.src[s].n_heads + i] = v;
+        dqv[s_goff[s] + i] = v;
+    };
+    if (live && g == 0 && lane == 0) {
     const float invB = 1.0f / (float)B;
-    const float r = io[p.off_rewards + b];
-    const float d = io[p.off_terminals + b];
+    const float r = r_pre;
+    const float d = d_pre;
     const float nd = (1.f - d) * p.discount;       // (1 - terminals) * discount
 
     if (p.mode == CM_SAC) {
-        const float alpha = io[p.off_scalars + SC_ALPHA];
+        const float alpha = alpha_pre;
         const float q1n = vals[0], q2n = vals[1], q1 = vals[2], q2 = vals[3], t1 = vals[4], t2 = vals[5];
-        const float lp_next = io[p.off_log_pi + B + b];
+        const float lp_next = lpn_pre;
         // trainer.py:178-184
         float tq = fminf(t1, t2) - alpha * lp_next;
         float y = p.reward_scale * r + nd * tq;
@@ -210,12 +298,12 @@ __global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const Criti
         io[p.off_q_target + b * 2 + 0] = y; io[p.off_q_target + b * 2 + 1] = y;
         io[p.off_q_new + b * 2 + 0] = q1n; io[p.off_q_new + b * 2 + 1] = q2n;
         // MSELoss mean over B: d/dq = 2 (q - y) / B          (trainer.py:194-195)
-        resolve(p.as, p.src[2].dq, seed)[b] = 2.f * (q1 - y) * invB;
-        resolve(p.as, p.src[3].dq, seed)[b] = 2.f * (q2 - y) * invB;
+        put(2, 0, 2.f * (q1 - y) * invB);
+        put(3, 0, 2.f * (q2 - y) * invB);
         // policy loss -mean(min(q1,q2)): gradient to the smaller one (first arg on ties)
         const bool sel1 = q1n <= q2n;
-        resolve(p.as, p.src[0].dq, seed)[b] = sel1 ? -invB : 0.f;
-        resolve(p.as, p.src[1].dq, seed)[b] = sel1 ? 0.f : -invB;
+        put(0, 0, sel1 ? -invB : 0.f);
+        put(1, 0, sel1 ? 0.f : -invB);
     } else if (p.mode == CM_POAC_Q) {
         // vals[0..P) current particles, vals[P..2P) target particles (particle_trainer_oac.py:185-208)
         const int P = p.P;
@@ -239,7 +327,7 @@ __global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const Criti
         }
         if (p.counts) {      // :220-224
             mean_sq /= (float)P; mean_T /= (float)P;
-            const float f = io[p.off_counts + b] == 0.f ? 1.f : 0.f;
+            const float f = cnt_pre == 0.f ? 1.f : 0.f;
             for (int i = 0; i < P; ++i) T[i] = T[i] * f + (1.f - f) * (sq[i] - mean_sq + mean_T);
         }
         for (int i = 0; i < P; ++i) {
@@ -250,8 +338,8 @@ __global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const Criti
         // receives gradient where it sits at its own rank (:247-264)
         for (int i = 0; i < P; ++i) {
             float gq = 2.f * (q[i] - T[rank_q[i]]) * invB;
-            if (p.share_layers) resolve(p.as, p.src[0].dq, seed)[(long long)b * P + i] = gq;
-            else resolve(p.as, p.src[i].dq, seed)[b] = (rank_q[i] == i) ? gq : 0.f;
+            if (p.share_layers) put(0, i, gq);
+            else put(i, 0, (rank_q[i] == i) ? gq : 0.f);
         }
     } else if (p.mode == CM_POAC_PI) {
         // policy loss uses the lowest particle (:291-295)
@@ -261,15 +349,15 @@ __global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const Criti
         for (int i = 0; i < P; ++i) {
             io[p.off_q_new + (long long)b * p.nq + i] = vals[i];
             float gq = (i == best) ? -invB : 0.f;
-            if (p.share_layers) resolve(p.as, p.src[0].dq, seed)[(long long)b * P + i] = gq;
-            else resolve(p.as, p.src[i].dq, seed)[b] = gq;
+            if (p.share_layers) put(0, i, gq);
+            else put(i, 0, gq);
         }
     } else if (p.mode == CM_GOAC_Q) {
         // shared: vals = q0, raw1 | tq0, traw1 ; separate: q0 | raw1 | tq0 | traw1  (same order)
         const float q0 = vals[0], sig = expf(vals[1]), t0 = vals[2], tsig = expf(vals[3]);
         float std_t = nd * tsig;                                    // gaussian_trainer.py:217
         if (p.counts) {
-            const float f = io[p.off_counts + b] == 0.f ? 1.f : 0.f;
+            const float f = cnt_pre == 0.f ? 1.f : 0.f;
             std_t = std_t * f + (1.f - f) * sig;                    // :224-228
         }
         const float y = p.reward_scale * r + nd * t0;               // :231-232
@@ -278,28 +366,33 @@ __global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const Criti
         io[p.off_q_target + b * 2 + 0] = y; io[p.off_q_target + b * 2 + 1] = std_t;
         const float g0 = 2.f * (q0 - y) * invB;
         const float g1 = 2.f * (sig - std_t) * invB * sig;          // through exp
-        if (p.share_layers) {
-            float* dq = resolve(p.as, p.src[0].dq, seed);
-            dq[b * 2 + 0] = g0; dq[b * 2 + 1] = g1;
-        } else {
-            resolve(p.as, p.src[0].dq, seed)[b] = g0;
-            resolve(p.as, p.src[1].dq, seed)[b] = g1;
-        }
+        if (p.share_layers) { put(0, 0, g0); put(0, 1, g1); }
+        else { put(0, 0, g0); put(1, 0, g1); }
     } else {   // CM_GOAC_PI
         // policy: -(q + z*sigma).mean() (:344-356); target policy: -(q).mean() (:361-373)
         const float q0 = vals[0], sig = expf(vals[1]);
         io[p.off_q_new + b * 2 + 0] = q0; io[p.off_q_new + b * 2 + 1] = sig;
         const float g0 = -invB, g1 = -invB * p.standard_bound * sig;
-        if (p.share_layers) {
-            float* dq = resolve(p.as, p.src[0].dq, seed);
-            dq[b * 2 + 0] = g0; dq[b * 2 + 1] = g1;
-            float* dt = resolve(p.as, p.src[1].dq, seed);
-            dt[b * 2 + 0] = -invB; dt[b * 2 + 1] = 0.f;
-        } else {
-            resolve(p.as, p.src[0].dq, seed)[b] = g0;
-            resolve(p.as, p.src[1].dq, seed)[b] = g1;
-            resolve(p.as, p.src[2].dq, seed)[b] = -invB;
-            resolve(p.as, p.src[3].dq, seed)[b] = 0.f;
+        if (p.share_layers) { put(0, 0, g0); put(0, 1, g1); put(1, 0, -invB); put(1, 1, 0.f); }
+        else { put(0, 0, g0); put(1, 0, g1); put(2, 0, -invB); put(3, 0, 0.f); }
+    }
+    }   // lane 0
+    __syncthreads();
+    if (!live) return;
+    // ---- dh2 = (dq W3) * relu'(h2) for the critics whose backward starts with the current weights ----
+    for (int s = 0; s < p.n_src; ++s) {
+        const HeadSrc& S = p.src[s];
+        if (!S.write_dh2) continue;
+        const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
+        const float* __restrict__ w = resolve(p.as, S.w3, seed);
+        float* __restrict__ out = resolve(p.as, S.dh2, seed) + (long long)b * H;
+        const int g0 = s_goff[s];
+#pragma unroll 4
+        for (int k = g * 32 + lane; k < H; k += 32 * GLUE_G) {
+            const float hv = __ldg(h + k);
+            float acc = 0.f;
+            for (int hd = 0; hd < S.n_heads; ++hd) acc = fmaf(dqv[g0 + hd], __ldg(w + (long long)hd * H + k), acc);
+            out[k] = hv > 0.f ? acc : 0.f;
         }
     }
 }
@@ -308,12 +401,18 @@ __global__ void __launch_bounds__(CRITIC_THREADS) critic_head_kernel(const Criti
 // policy-loss gradient w.r.t. the policy head outputs
 // =====================================================================================
 struct PolicyGradTask {
-    Ref da[20];       // per critic: [B, A] = dh1 W1[:, O:O+A]   (d loss / d action through that critic)
+    Ref dh1[20];      // per critic: [B, H] gradient at its first hidden layer (rows of this policy's actions)
+    Ref w1[20];       // per critic: fc0.weight [H, ld]; the action columns start at O
+    int ld[20];
     int n_src;
     Ref save;         // [., 4, A] from policy_head (rows of this policy start at save_row0)
     int save_row0;
     Ref dhead;        // out: [B, 2A]  d loss / d(mean), d loss / d(raw log_std)
     int entropy;      // 1: alpha*log_pi term present (stochastic policy)
+    Ref wh;           // policy head weights [2A, H]
+    Ref h2;           // policy second hidden activation [*, H]; rows of this batch start at h2_row0
+    int h2_row0;
+    Ref dhp2;         // out: [B, H] = (dhead Wh) * relu'(h2)
 };
 
 struct PolicyGradParams {
@@ -323,38 +422,93 @@ struct PolicyGradParams {
     int O, A, H, B;
 };
 
-// one thread per (sample, action dim)
+// Fused: dLoss/d(action) through every critic's first layer (only the A action columns of fc0.weight are
+// needed, not the full 393-wide dX the reference's autograd computes), the TanhNormal / entropy chain rule
+// to the policy head outputs, and the policy's first backward step dh2 = (dhead Wh) * relu'(h2).
+// GLUE_G warps share one sample.  dyn smem: Wa [H*AS] | Wh [2A*H] | ga [SPC][A] | dhead [SPC][2A]  (AS = A | 1)
 __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
+    extern __shared__ __align__(16) float s_pg[];
     const PolicyGradTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
-    const int A = p.A, B = p.B;
-    const int idx = blockIdx.x * GLUE_THREADS + threadIdx.x;
-    if (idx >= B * A) return;
-    const int b = idx / A, j = idx - b * A;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = warp / GLUE_G, g = warp % GLUE_G;
+    const int b = blockIdx.x * GLUE_SPC + sl;
+    const int A = p.A, H = p.H, B = p.B, O = p.O;
+    const int AS = A | 1;                                   // odd stride: conflict-free column reads
+    const bool live = b < B;
+    float* Wa = s_pg;
+    float* Whs = Wa + H * AS;
+    float* sga = Whs + 2 * A * H + sl * A;
+    float* sdh = Whs + 2 * A * H + GLUE_SPC * A + sl * 2 * A;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
-    float ga = 0.f;
-    for (int s = 0; s < T.n_src; ++s) ga += resolve(p.as, T.da[s], seed)[idx];
-    const float alpha = io[p.off_scalars + SC_ALPHA];
-    const float invB = 1.0f / (float)B;
-    const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
-    float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * 2 * A;
-    const float a = save[0 * A + j];
-    const float one_m_a2 = 1.f - a * a;
-    float dmean, draw;
-    if (T.entropy) {
-        const float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
-        const float u = one_m_a2 + TANH_EPS_F;
-        // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
-        dmean = alpha * invB * (2.f * a * one_m_a2 / u) + ga * one_m_a2;
-        const float dstd = dmean * eps - alpha * invB / std;
-        const bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
-        draw = inside ? dstd * std : 0.f;
-    } else {
-        dmean = ga * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
-        draw = 0.f;
+    stage_contig(Whs, resolve(p.as, T.wh, seed), 2 * A * H);       // consumed in the last phase
+    for (int s = 0; s < T.n_src; ++s) {
+        const float* __restrict__ w1 = resolve(p.as, T.w1[s], seed);
+        const int ld = T.ld[s];
+        __syncthreads();
+        // action columns of fc0.weight: row n -> Wa[n*AS + j]; one warp per row, lanes over j (no division)
+        for (int n = warp; n < H; n += GLUE_WARPS)
+            for (int j = lane; j < A; j += 32) cp_async4(Wa + n * AS + j, w1 + (long long)n * ld + O + j);
+        float dreg[GLUE_MAX_HR];
+        if (live) {
+            const float* __restrict__ dh = resolve(p.as, T.dh1[s], seed) + (long long)b * H;
+#pragma unroll
+            for (int c = 0; c < GLUE_MAX_HR; ++c) dreg[c] = (lane + 32 * c < H) ? __ldg(dh + lane + 32 * c) : 0.f;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (live) {
+            for (int j = g; j < A; j += GLUE_G) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < GLUE_MAX_HR; ++c) {
+                    const int n = lane + 32 * c;
+                    if (n < H) acc = fmaf(dreg[c], Wa[n * AS + j], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) sga[j] = (s == 0 ? 0.f : sga[j]) + acc;      // column j belongs to warp g only
+            }
+        }
     }
-    dhead[j] = dmean;
-    dhead[A + j] = draw;
+    __syncthreads();
+    if (live && g == 0) {
+        const float alpha = io[p.off_scalars + SC_ALPHA];
+        const float invB = 1.0f / (float)B;
+        const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
+        float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * 2 * A;
+        for (int j = lane; j < A; j += 32) {
+            const float a = save[0 * A + j];
+            const float one_m_a2 = 1.f - a * a;
+            const float gaj = sga[j];
+            float dmean, draw;
+            if (T.entropy) {
+                const float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
+                const float u = one_m_a2 + TANH_EPS_F;
+                // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
+                dmean = alpha * invB * (2.f * a * one_m_a2 / u) + gaj * one_m_a2;
+                const float dstd = dmean * eps - alpha * invB / std;
+                const bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
+                draw = inside ? dstd * std : 0.f;
+            } else {
+                dmean = gaj * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
+                draw = 0.f;
+            }
+            dhead[j] = dmean; dhead[A + j] = draw;
+            sdh[j] = dmean; sdh[A + j] = draw;
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    // ---- policy backward, first step: dh2 = (dhead Wh) * relu'(h2) ----
+    const float* __restrict__ hp2 = resolve(p.as, T.h2, seed) + (long long)(T.h2_row0 + b) * H;
+    float* __restrict__ out = resolve(p.as, T.dhp2, seed) + (long long)b * H;
+#pragma unroll 2
+    for (int n = g * 32 + lane; n < H; n += 32 * GLUE_G) {
+        const float hv = __ldg(hp2 + n);
+        float acc = 0.f;
+        for (int j = 0; j < 2 * A; ++j) acc = fmaf(sdh[j], Whs[j * H + n], acc);
+        out[n] = hv > 0.f ? acc : 0.f;
+    }
 }
 
 }  // namespace oac

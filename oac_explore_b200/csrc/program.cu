@@ -58,6 +58,9 @@ static int validate(const OacConfig& c) {
     if (c.obs_dim < 1 || c.act_dim < 1 || c.hidden < 1 || c.batch < 1 || c.n_seeds < 1)
         return set_error(OAC_E_INVALID, "dims must be positive");
     if (c.act_dim > 128) return set_error(OAC_E_UNSUPPORTED, "act_dim > 128");
+    if (c.hidden > 512) return set_error(OAC_E_UNSUPPORTED, "hidden > 512 (glue kernels keep a hidden row in registers)");
+    if ((size_t)c.hidden * (c.act_dim | 1) + (size_t)2 * c.act_dim * c.hidden + 16 * c.act_dim > 50000)
+        return set_error(OAC_E_UNSUPPORTED, "hidden*act_dim too large for the fused glue kernels' shared memory");
     if (c.algo == OAC_ALGO_POAC && (c.n_particles < 2 || c.n_particles > 16))
         return set_error(OAC_E_UNSUPPORTED, "P-OAC needs 2 <= n_particles <= 16");
     if (c.algo < 0 || c.algo > OAC_ALGO_GOAC) return set_error(OAC_E_INVALID, "unknown algo");
@@ -269,7 +272,9 @@ struct Builder {
     }
     HeadSrc head_src(int ni, const CritAct& a, int row0) {
         const OacNetLayout& n = net(ni);
-        HeadSrc h; h.q = a.q; h.row0 = row0; h.n_heads = n.n_out;
+        HeadSrc h; memset(&h, 0, sizeof(h));
+        h.h2 = a.h2; h.row0 = row0; h.w3 = P(n.off_w2); h.b3 = P(n.off_b2); h.n_heads = n.n_out;
+        h.write_dh2 = 0; h.dh2 = Ref{a.dh2.arena, a.dh2.off + (long long)row0 * H};
         h.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * n.n_out};
         return h;
     }
@@ -321,12 +326,25 @@ struct Builder {
         dw(s, g.dh2, H, Ref{a.h1.arena, a.h1.off + ro}, H, B, H, H, n.off_w1, H, n.off_b1, -1, -1, lr, counter, 1);
         dw(s, g.dhead, 2 * A, Ref{a.h2.arena, a.h2.off + ro}, H, B, 2 * A, H, n.off_w2, H, n.off_b2, -1, -1, lr, counter, 1);
     }
+    // policy-loss gradient task: critics (dh1 rows, fc0 weights) -> dhead, and the policy's own dh2
+    PolicyGradTask pg_task(const std::vector<std::pair<int, Ref>>& crit_dh1, int pol, const PolAct& a, int row0,
+                           const PolGrad& g, bool entropy) {
+        PolicyGradTask t_; memset(&t_, 0, sizeof(t_));
+        int i = 0;
+        for (auto& c_ : crit_dh1) {
+            const OacNetLayout& qn = net(c_.first);
+            t_.dh1[i] = c_.second; t_.w1[i] = P(qn.off_w0); t_.ld[i] = qn.in_ld; ++i;
+        }
+        t_.n_src = i;
+        t_.save = a.save; t_.save_row0 = row0; t_.dhead = g.dhead; t_.entropy = entropy ? 1 : 0;
+        t_.wh = P(net(pol).off_w2); t_.h2 = a.h2; t_.h2_row0 = row0; t_.dhp2 = g.dh2;
+        return t_;
+    }
     PolicyHeadTask ph_task(int ni, const PolAct& a, int out_row0, int dst0, int dst1, int eps0, int eps1) {
         const OacNetLayout& n = net(ni);
         PolicyHeadTask p;
         memset(&p, 0, sizeof(p));
-        (void)n;
-        p.head = a.head; p.rows = a.rows; p.out_row0 = out_row0;
+        p.h2 = a.h2; p.w = P(n.off_w2); p.b = P(n.off_b2); p.rows = a.rows; p.out_row0 = out_row0;
         p.dst_block[0] = dst0; p.dst_block[1] = dst1; p.eps_slot[0] = eps0; p.eps_slot[1] = eps1;
         p.save = a.save;
         return p;
@@ -375,49 +393,41 @@ void Builder::build_sac() {
     CritAct ca1 = alloc_crit(2, 1), ca2 = alloc_crit(2, 1);   // rows [0,B) a_pi (block 1), [B,2B) data (block 2)
     CritAct ta1 = alloc_crit(1, 1), ta2 = alloc_crit(1, 1);   // block 3
     PolGrad pg = alloc_polgrad();
+    const bool mode_b = c.stale_graph_mode == 1;
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
-    { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
-    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+alpha");
+    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
       crit_l1(s, q1, 1, ca1); crit_l1(s, q2, 1, ca2); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
-    { Stage& s = add_stage(ST_GEMM, "critic_l3");
-      crit_l3(s, q1, ca1); crit_l3(s, q2, ca2); crit_l3(s, t1, ta1); crit_l3(s, t2, ta2); }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_sac");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2");
       memset(&s.chp, 0, sizeof(s.chp));
       s.chp.src[0] = head_src(q1, ca1, 0); s.chp.src[1] = head_src(q2, ca2, 0);
       s.chp.src[2] = head_src(q1, ca1, B); s.chp.src[3] = head_src(q2, ca2, B);
       s.chp.src[4] = head_src(t1, ta1, 0); s.chp.src[5] = head_src(t2, ta2, 0);
+      s.chp.src[2].write_dh2 = s.chp.src[3].write_dh2 = 1;              // Q-loss backward starts here
+      // mode B: the policy-loss dX uses the PRE-step critic weights, so its dh2 can be formed here as well;
+      // mode A (torch 1.4) multiplies by the POST-step W3 -> separate stage after the critic Adam
+      if (mode_b) s.chp.src[0].write_dh2 = s.chp.src[1].write_dh2 = 1;
       s.chp.n_src = 6; fill_chp(s, CM_SAC, 2); }
-    { Stage& s = add_stage(ST_GEMM, "qloss_dh2"); crit_dh2(s, q1, ca1, B); crit_dh2(s, q2, ca2, B); }
-    { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); crit_dh1(s, q1, ca1, B); crit_dh1(s, q2, ca2, B); }
-    if (c.stale_graph_mode == 1) {
-        // mode B: the policy-loss dX uses PRE-step critic weights -> run it before the critic Adam
-        { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
-        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
-    }
-    // NB mode B reads fc0.weight's action columns in policy_grad AFTER the Adam stage; to keep
-    // B exact the policy_grad stage is placed before the critic Adam in that mode.
+    { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); crit_dh1(s, q1, ca1, B); crit_dh1(s, q2, ca2, B);
+      if (mode_b) { crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); } }
     auto policy_grad_stage = [&]() {
-        { Stage& sd = add_stage(ST_GEMM, "pi_da"); crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
-        Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
-        PolicyGradTask g; memset(&g, 0, sizeof(g));
-        g.da[0] = ca1.da; g.da[1] = ca2.da;
-        g.n_src = 2; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = !c.deterministic;
-        s.pg.push_back(g); fill_pgp(s);
+        Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad+da+dh2");
+        s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic));
+        fill_pgp(s);
     };
-    if (c.stale_graph_mode == 1) policy_grad_stage();
+    // NB mode B reads fc0.weight's action columns too: its policy_grad stage runs before the critic Adam
+    if (mode_b) policy_grad_stage();
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
-    if (c.stale_graph_mode == 0) {
+    if (!mode_b) {
         { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
         { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
         policy_grad_stage();
     }
-    { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
 }
@@ -434,43 +444,34 @@ void Builder::build_poac() {
     PolGrad pg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
-    { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     // eps slots are named by meaning (0: obs draw, 1: next_obs draw); the reference draws the
     // next_obs noise FIRST here (:193 then :271) -- the host wrapper maps call order to slots
-    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+alpha");
+    { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 1); }
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
       for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
-    { Stage& s = add_stage(ST_GEMM, "critic_l3");
-      for (int i = 0; i < n; ++i) { crit_l3(s, t.ids.qf[i], qa[i]); crit_l3(s, t.ids.tf[i], ta[i]); } }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_poac_q");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+sort+targets+dh2");
       memset(&s.chp, 0, sizeof(s.chp));
-      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0);
+      for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0); s.chp.src[i].write_dh2 = 1; }
       for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.tf[i], ta[i], 0);
       s.chp.n_src = 2 * n; fill_chp(s, CM_POAC_Q, n); }
-    { Stage& s = add_stage(ST_GEMM, "qloss_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], qa[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], qa[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       for (int i = 0; i < n; ++i) crit_adam(s, t.ids.qf[i], t.ids.tf[i], qa[i], 0, 2, c.qf_lr, 2 + i); }
     // policy phase through the UPDATED critics
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 1, pa_q[i]); }
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pa_q[i]); }
-    { Stage& s = add_stage(ST_GEMM, "pi_critic_l3"); for (int i = 0; i < n; ++i) crit_l3(s, t.ids.qf[i], pa_q[i]); }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_poac_pi");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+min_particle+dh2");
       memset(&s.chp, 0, sizeof(s.chp));
-      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], pa_q[i], 0);
+      for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], pa_q[i], 0); s.chp.src[i].write_dh2 = 1; }
       s.chp.n_src = n; fill_chp(s, CM_POAC_PI, n); }
-    { Stage& s = add_stage(ST_GEMM, "pi_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], pa_q[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "pi_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], pa_q[i], 0); }
-    { Stage& s = add_stage(ST_GEMM, "pi_da"); for (int i = 0; i < n; ++i) crit_da(s, t.ids.qf[i], pa_q[i], 0); }
-    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
-      PolicyGradTask g; memset(&g, 0, sizeof(g));
-      for (int i = 0; i < n; ++i) g.da[i] = pa_q[i].da;
-      g.n_src = n; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = !c.deterministic;
-      s.pg.push_back(g); fill_pgp(s); }
-    { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
+    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad+da+dh2");
+      std::vector<std::pair<int, Ref>> cr;
+      for (int i = 0; i < n; ++i) cr.push_back({t.ids.qf[i], pa_q[i].dh1});
+      s.pg.push_back(pg_task(cr, pol, pa, 0, pg, !c.deterministic)); fill_pgp(s); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
 }
@@ -488,7 +489,6 @@ void Builder::build_goac() {
     PolGrad pg = alloc_polgrad(), tpg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); pol_l1(s, tpol, 2, tpa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); pol_l2(s, tpol, tpa); }
-    { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); pol_l3(s, tpol, tpa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1));
       s.ph.push_back(ph_task(tpol, tpa, 2 * B, 0, 0, 0, 0));
@@ -497,14 +497,11 @@ void Builder::build_goac() {
       for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
-    { Stage& s = add_stage(ST_GEMM, "critic_l3");
-      for (int i = 0; i < n; ++i) { crit_l3(s, t.ids.qf[i], qa[i]); crit_l3(s, t.ids.tf[i], ta[i]); } }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_goac_q");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2");
       memset(&s.chp, 0, sizeof(s.chp));
-      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0);
+      for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0); s.chp.src[i].write_dh2 = 1; }
       for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.tf[i], ta[i], 0);
       s.chp.n_src = 2 * n; fill_chp(s, CM_GOAC_Q, n); }
-    { Stage& s = add_stage(ST_GEMM, "qloss_dh2"); for (int i = 0; i < n; ++i) crit_dh2(s, t.ids.qf[i], qa[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], qa[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       for (int i = 0; i < n; ++i)
@@ -512,29 +509,22 @@ void Builder::build_goac() {
     // policy (rows [B,2B) = block 1) and target policy (rows [0,B) = block 0) through the updated critic
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 0, pq[i]); }
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pq[i]); }
-    { Stage& s = add_stage(ST_GEMM, "pi_critic_l3"); for (int i = 0; i < n; ++i) crit_l3(s, t.ids.qf[i], pq[i]); }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head_goac_pi");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+upper_bound+dh2");
       memset(&s.chp, 0, sizeof(s.chp));
-      for (int i = 0; i < n; ++i) s.chp.src[i] = head_src(t.ids.qf[i], pq[i], B);        // a_pi rows
-      for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.qf[i], pq[i], 0);    // a_tp rows
+      for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], pq[i], B); s.chp.src[i].write_dh2 = 1; }          // a_pi rows
+      for (int i = 0; i < n; ++i) { s.chp.src[n + i] = head_src(t.ids.qf[i], pq[i], 0); s.chp.src[n + i].write_dh2 = 1; }  // a_tp rows
       s.chp.n_src = 2 * n; fill_chp(s, CM_GOAC_PI, n); }
-    { Stage& s = add_stage(ST_GEMM, "pi_dh2");
-      for (int i = 0; i < n; ++i) { crit_dh2(s, t.ids.qf[i], pq[i], 0); crit_dh2(s, t.ids.qf[i], pq[i], B); } }
     { Stage& s = add_stage(ST_GEMM, "pi_dh1");
       for (int i = 0; i < n; ++i) { crit_dh1(s, t.ids.qf[i], pq[i], 0); crit_dh1(s, t.ids.qf[i], pq[i], B); } }
-    { Stage& s = add_stage(ST_GEMM, "pi_da");
-      for (int i = 0; i < n; ++i) { crit_da(s, t.ids.qf[i], pq[i], 0); crit_da(s, t.ids.qf[i], pq[i], B); } }
-    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad");
-      PolicyGradTask g; memset(&g, 0, sizeof(g));
-      PolicyGradTask gt; memset(&gt, 0, sizeof(gt));
+    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad+da+dh2");
+      std::vector<std::pair<int, Ref>> cr, crt;
       for (int i = 0; i < n; ++i) {
-          g.da[i] = Ref{pq[i].da.arena, pq[i].da.off + (long long)B * A};
-          gt.da[i] = pq[i].da;
+          cr.push_back({t.ids.qf[i], Ref{pq[i].dh1.arena, pq[i].dh1.off + (long long)B * H}});
+          crt.push_back({t.ids.qf[i], pq[i].dh1});
       }
-      g.n_src = n; g.save = pa.save; g.save_row0 = 0; g.dhead = pg.dhead; g.entropy = 0;
-      gt.n_src = n; gt.save = tpa.save; gt.save_row0 = 0; gt.dhead = tpg.dhead; gt.entropy = 0;
-      s.pg.push_back(g); s.pg.push_back(gt); fill_pgp(s); }
-    { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); pol_dh2(s, tpol, tpa, 0, tpg); }
+      s.pg.push_back(pg_task(cr, pol, pa, 0, pg, false));
+      s.pg.push_back(pg_task(crt, tpol, tpa, 0, tpg, false));
+      fill_pgp(s); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); pol_dh1(s, tpol, tpa, 0, tpg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam");
       pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); pol_adam(s, tpol, tpa, 0, 2, tpg, c.policy_lr, 1); }
@@ -675,14 +665,17 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
             }
         } else if (s.kind == ST_POLICY_HEAD) {
             PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps;
-            dim3 grid((s.max_rows + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.ph.size(), seeds);
-            policy_head_kernel<<<grid, GLUE_THREADS, 0, st>>>(p);
+            dim3 grid((s.max_rows + GLUE_SPC - 1) / GLUE_SPC, (unsigned)s.ph.size(), seeds);
+            const size_t smem = sizeof(float) * ((size_t)2 * t.cfg.act_dim * t.cfg.hidden + 2 * t.cfg.act_dim * (1 + GLUE_SPC));
+            policy_head_kernel<<<grid, GLUE_THREADS, smem, st>>>(p);
         } else if (s.kind == ST_CRITIC_HEAD) {
-            dim3 grid((t.cfg.batch + CRITIC_THREADS - 1) / CRITIC_THREADS, seeds, 1);
-            critic_head_kernel<<<grid, CRITIC_THREADS, 0, st>>>((const CriticHeadParams*)s.dev);
+            dim3 grid((t.cfg.batch + GLUE_SPC - 1) / GLUE_SPC, seeds, 1);
+            critic_head_kernel<<<grid, GLUE_THREADS, 0, st>>>((const CriticHeadParams*)s.dev);
         } else {
-            dim3 grid((t.cfg.batch * t.cfg.act_dim + GLUE_THREADS - 1) / GLUE_THREADS, (unsigned)s.pg.size(), seeds);
-            policy_grad_kernel<<<grid, GLUE_THREADS, 0, st>>>(s.pgp);
+            dim3 grid((t.cfg.batch + GLUE_SPC - 1) / GLUE_SPC, (unsigned)s.pg.size(), seeds);
+            const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
+            const size_t smem = sizeof(float) * ((size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_ + GLUE_SPC * 3 * A_);
+            policy_grad_kernel<<<grid, GLUE_THREADS, smem, st>>>(s.pgp);
         }
         OAC_CUDA(cudaGetLastError());
     }
@@ -754,6 +747,8 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_in((const void*)gemm_tc_kernel<false, false, true>);
         opt_in((const void*)gemm_tc_kernel<false, true, true>);
         opt_in((const void*)gemm_tc_kernel<true, true, true>);
+        opt_in((const void*)policy_head_kernel);
+        opt_in((const void*)policy_grad_kernel);
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
