@@ -4,7 +4,7 @@ PyTorch owns every byte (SURVEY.md section 8b "Ownership"): the parameter arena,
 Adam moment arenas, the activation workspace, the IO slice (batch rows, noise, per-sample
 outputs) and the int32 step counters are plain CUDA tensors; the library borrows their
 pointers.  ``net_views`` exposes the arena as ``state_dict``-shaped tensor views
-(``fc0.weight`` ... ``last_fc_log_std.bias``) so snapshots and the oracle see the
+(``fc0.weight`` ... ``last_fc_log_std.bias``) so snapshots and parity checkers see the
 reference's layout.
 """
 import ctypes as C

@@ -18,7 +18,8 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--algo", default="sac")
 ap.add_argument("--no-graph", action="store_true")
 ap.add_argument("--replay", type=int, default=200000)
-ap.add_argument("--gemm-path", default="tf32x3")
+ap.add_argument("--gemm-path", default="fp32")
+ap.add_argument("--seeds", type=int, default=1)
 args = ap.parse_args()
 if args.no_graph:
     os.environ["OAC_NO_GRAPH"] = "1"
@@ -34,13 +35,20 @@ g = torch.Generator(device=dev).manual_seed(0)
 rb._observations.normal_(generator=g); rb._next_obs.normal_(generator=g)
 rb._actions.uniform_(-1, 1, generator=g); rb._rewards.normal_(generator=g)
 rb._size = args.replay
-tr = bench.build_trainer(args.algo, 0)
-rb.attach(tr)
 np.random.seed(0)
-idx = torch.from_numpy(np.random.randint(0, args.replay, (args.steps, bench.B))).to(dev)
+S = args.seeds
+idx = torch.from_numpy(np.random.randint(0, args.replay, (args.steps, S, bench.B))).to(dev)
+if S == 1:
+    tr = bench.build_trainer(args.algo, 0)
+    rb.attach(tr)
+    engine = tr._engine
+else:
+    from oac_explore_b200.seed_group import SACSeedGroup
+    grp = SACSeedGroup(list(range(S)), bench.O, bench.A, hidden=bench.H, batch=bench.B, gemm_path=bench.GEMM_PATH, **bench.HP)
+    engine = grp.engine
 torch.cuda.synchronize()
 for i in range(args.steps):
-    rb.gather_into(tr._engine, idx[i], bench.B)
-    tr._engine.step()
+    rb.gather_into(engine, idx[i], bench.B, n_seeds=S)
+    engine.step()
 torch.cuda.synchronize()
-print("done", args.steps, "steps;", tr._engine.launches_per_step, "launches/step")
+print("done", args.steps, "steps;", engine.launches_per_step, "launches/step; seeds", S)

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Turns the ncu artefacts in gpurun_out/ into the small text summaries committed under profiles/."""
+import csv
+import os
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+os.makedirs(P, exist_ok=True)
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum"]
+
+
+def launch_list(name, per_step):
+    path = os.path.join(G, name)
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    ks = [(r["Kernel Name"], r["Grid Size"], float(r["Metric Value"].replace(",", "")) / 1000.0) for r in rows]
+    last = ks[-per_step:]
+    tot = sum(k[2] for k in last)
+    out = ["# %s: last step's launches (gpu__time_duration, us; cold-cache, serialised under ncu --clock-control none)" % name,
+           "# share = duration / sum of the step's launches (%.1f us)" % tot]
+    agg = OrderedDict()
+    for n, g, d in last:
+        out.append("%-100s grid %-14s %8.2f us  %5.1f %%" % (n[:100], g, d, 100 * d / tot))
+        key = n.split("(")[0][:70]
+        agg[key] = agg.get(key, 0.0) + d
+    out.append("# by kernel:")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+        out.append("#   %-72s %8.2f us  %5.1f %%" % (k, v, 100 * v / tot))
+    open(os.path.join(P, name.replace(".csv", ".txt")), "w").write("\n".join(out) + "\n")
+    print("\n".join(out[-8:]))
+
+
+def full_report(rep, out_name):
+    path = os.path.join(G, rep)
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr = rows[0]
+    out = ["# %s (ncu --set full --clock-control none), one line block per profiled launch" % rep]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        out.append("kernel: %s  grid %s block %s" % (d.get("Kernel Name"), d.get("Grid Size"), d.get("Block Size")))
+        for k in KEYS:
+            for h in hdr:
+                if h == k:
+                    out.append("    %-80s %s" % (k, d[h]))
+    open(os.path.join(P, out_name), "w").write("\n".join(out) + "\n")
+    print(out_name, "written,", len(rows) - 2, "launches")
+
+
+if __name__ == "__main__":
+    launch_list("r01_launches_sac_fp32.csv", 14)
+    launch_list("r01_launches_64seeds_tf32.csv", 14)
+    full_report("r01_gemm_simt.ncu-rep", "r01_gemm_simt_full.txt")
+    full_report("r01_gemm_tc_64seeds.ncu-rep", "r01_gemm_tc_64seeds_full.txt")
+    full_report("r01_gather.ncu-rep", "r01_replay_gather_full.txt")
