@@ -26,6 +26,13 @@ struct StageParams {
 
 __device__ __forceinline__ float relu(float x) { return x > 0.f ? x : 0.f; }
 
+// Programmatic dependent launch: let the next stage's grid be scheduled now, then wait until the previous
+// stage's results are visible.  Both are no-ops for a kernel launched without the PDL attribute.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
 // torch.optim.Adam (1.4 formula order, trainer/trainer.py:75-91) on one element; no FMA
 // contraction so the rounding sequence is the reference's: mul, add; mul, addcmul; sqrt,
 // div, add; div, mul, add.
@@ -131,6 +138,7 @@ gemm_stage_kernel(StageParams sp) {
     extern __shared__ __align__(16) float smem[];
     __shared__ AdamScalars s_adam;
 
+    pdl_prologue();
     const GemmTask& T = sp.tasks[blockIdx.y];
     const int tile = blockIdx.x;
     if (tile >= T.tiles_m * T.tiles_n) return;

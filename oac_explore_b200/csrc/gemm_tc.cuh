@@ -183,12 +183,13 @@ struct TcStageParams {
 // X3: 3xTF32 split (a = a_hi + a_lo with both parts exact in tf32; D += a_hi b_hi + a_hi b_lo + a_lo b_hi):
 // fp32-grade accuracy on the tensor pipe (dropped term a_lo b_lo ~ 2^-22) at three MMAs per k-step.
 template <bool A_MN, bool B_MN, bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcStageParams tp) {
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(TcStageParams tp) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
     __shared__ AdamScalars s_adam;
 
+    pdl_prologue();
     const StageParams& sp = tp.sp;
     const GemmTask& T = sp.tasks[blockIdx.y];
     const int tile = blockIdx.x;
@@ -349,61 +350,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcStageParams tp
     tc_fence_after();
     if (dbg) dbg[5] = clock64();
 
-    // ---- epilogue: TMEM -> registers -> shared (row-major tile) -> coalesced global ----
+    // ---- epilogue: TMEM -> registers -> shared (row-major slab) -> coalesced global ----
     // TMEM hands each thread one accumulator ROW (lane = row); writing rows straight to global would touch 32
-    // different rows per store.  The tile is therefore parked in shared memory (the operand ring is idle once the
-    // last MMA retired) and re-read with consecutive threads on consecutive columns, so the bias / mask / Adam
-    // traffic (param, two moments, Polyak target) is fully coalesced.
+    // different rows per store.  The tile is therefore parked in shared memory, SLAB columns at a time (the
+    // operand ring is idle once the last MMA retired), and re-read with consecutive threads on consecutive
+    // columns, so the bias / mask / Adam traffic (param, two moments, Polyak target) is fully coalesced.
     float* stile = reinterpret_cast<float*>(ring);
-    const int sld = BN + 1;                                 // odd row stride: conflict-free lane=row stores
-    {
-        const int q = warp & 3, half = warp >> 2;
-        const int cols_per_half = BN >> 1;                  // BN >= 16 -> >= 8
-        const int row = q * 32 + lane;
-        for (int cg = 0; cg < cols_per_half; cg += 8) {
-            const int nloc = half * cols_per_half + cg;
-            float v[8];
-            tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)nloc, v);
-            if (X3) {
-                const int n_acc = min(tp.n_main, nchunks);
-                for (int a = 1; a <= tp.n_main; ++a) {
-                    if (a < tp.n_main && a >= n_acc) continue;              // accumulator never written
-                    float w[8];
-                    tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + nloc), w);
+    const int SLAB = BN < 64 ? BN : 64;
+    const int sld = SLAB + 1;                               // odd row stride: conflict-free lane=row stores
+    float* __restrict__ C = resolve(sp.as, T.C, seed);
+    const int ldc = T.ldc, epi = T.epi;
+    const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
+    const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+    float* __restrict__ m1 = sp.as.base[AR_ADAM_M] + (long long)seed * sp.as.stride[AR_ADAM_M];
+    float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
+    float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
+    // task fields live in global memory next to buffers this loop stores to: copy them to registers once
+    const long long t_adam = T.adam_off, t_adam_b = T.adam_bias_off, t_tgt = T.target_off, t_tgt_b = T.target_bias_off;
+    const int t_has_bias = T.has_bias, t_train_bias = T.train_bias, t_ldmask = T.ldmask;
+    float* __restrict__ pb_base = is_adam ? resolve(sp.as, T.bias, seed) : nullptr;
+    const int sl_shift = 31 - __clz(SLAB);                  // SLAB is a power of two
+    const int rows = min(TC_BM, M - m0);
+    const int total = rows << sl_shift;
+    for (int c0 = 0; c0 < BN; c0 += SLAB) {
+        if (n0 + c0 >= N + (is_adam && t_has_bias ? 1 : 0)) break;          // nothing live further right (CTA-uniform)
+        {
+            const int q = warp & 3, half = warp >> 2;
+            const int cols_per_half = SLAB >> 1;            // SLAB >= 16 -> >= 8
+            const int row = q * 32 + lane;
+            for (int cg = 0; cg < cols_per_half; cg += 8) {
+                const int nloc = half * cols_per_half + cg;
+                float v[8];
+                tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + nloc), v);
+                if (X3) {
+                    const int n_acc = min(tp.n_main, nchunks);
+                    for (int a = 1; a <= tp.n_main; ++a) {
+                        if (a < tp.n_main && a >= n_acc) continue;          // accumulator never written
+                        float w[8];
+                        tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0 + nloc), w);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += w[j];
+                        for (int j = 0; j < 8; ++j) v[j] += w[j];
+                    }
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) stile[row * sld + nloc + j] = v[j];
+                for (int j = 0; j < 8; ++j) stile[row * sld + nloc + j] = v[j];
+            }
         }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {      // TMEM is drained: release it while the other warps run the global epilogue
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)tp.tmem_cols) : "memory");
-    }
-    if (dbg) dbg[6] = clock64();
-    {
-        float* __restrict__ C = resolve(sp.as, T.C, seed);
-        const int ldc = T.ldc, epi = T.epi;
-        const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
-        const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
-        float* __restrict__ m1 = sp.as.base[AR_ADAM_M] + (long long)seed * sp.as.stride[AR_ADAM_M];
-        float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
-        float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
-        const int bn_shift = 31 - __clz(BN);               // BN is a power of two
-        const int rows = min(TC_BM, M - m0);
-        const int total = rows << bn_shift;
-        // task fields live in global memory next to buffers this loop stores to: copy them to registers once
-        const long long t_adam = T.adam_off, t_adam_b = T.adam_bias_off, t_tgt = T.target_off, t_tgt_b = T.target_bias_off;
-        const int t_has_bias = T.has_bias, t_train_bias = T.train_bias, t_ldmask = T.ldmask;
-        float* __restrict__ pb_base = is_adam ? resolve(sp.as, T.bias, seed) : nullptr;
+        __syncthreads();
         if (is_adam) {
             const AdamScalars s = s_adam;
             for (int idx = tid; idx < total; idx += TC_THREADS) {
-                const int r = idx >> bn_shift, nl = idx & (BN - 1);
-                const int m = m0 + r, n = n0 + nl;
+                const int r = idx >> sl_shift, nl = idx & (SLAB - 1);
+                const int m = m0 + r, n = n0 + c0 + nl;
                 const float x = stile[r * sld + nl];
                 if (n < N) {
                     const long long e = (long long)m * ldc + n;
@@ -418,8 +416,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcStageParams tp
         } else {
 #pragma unroll 4
             for (int idx = tid; idx < total; idx += TC_THREADS) {
-                const int r = idx >> bn_shift, nl = idx & (BN - 1);
-                const int m = m0 + r, n = n0 + nl;
+                const int r = idx >> sl_shift, nl = idx & (SLAB - 1);
+                const int m = m0 + r, n = n0 + c0 + nl;
                 if (n >= N) continue;
                 float x = stile[r * sld + nl];
                 if (epi == EPI_BIAS) x += __ldg(bias + n);
@@ -428,6 +426,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcStageParams tp
                 C[(long long)m * ldc + n] = x;
             }
         }
+        __syncthreads();                                   // the slab buffer is reused
+    }
+    if (dbg) dbg[6] = clock64();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)tp.tmem_cols) : "memory");
     }
     if (dbg) dbg[7] = clock64();
 }

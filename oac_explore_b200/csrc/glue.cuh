@@ -62,6 +62,7 @@ struct PolicyHeadParams {
 // shuffles), then one of them runs the per-action-dim sampling math.  dyn smem: (2A*H + 2A + SPC*2A) floats.
 __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
     extern __shared__ __align__(16) float s_ph[];
+    pdl_prologue();
     const PolicyHeadTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -228,6 +229,7 @@ struct CriticHeadParams {
 // one lane then evaluates the algorithm's targets and dLoss/dq, and all GLUE_G warps emit
 // dh2 = (dq W3) * relu'(h2) for the critics whose backward starts here.
 __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+    pdl_prologue();
     const CriticHeadParams& p = *pp;
     __shared__ float s_vals[GLUE_SPC][MAX_VALS];
     __shared__ float s_dq[GLUE_SPC][MAX_VALS];
@@ -428,6 +430,7 @@ struct PolicyGradParams {
 // GLUE_G warps share one sample.  dyn smem: Wa [H*AS] | Wh [2A*H] | ga [SPC][A] | dhead [SPC][2A]  (AS = A | 1)
 __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
     extern __shared__ __align__(16) float s_pg[];
+    pdl_prologue();
     const PolicyGradTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -569,16 +569,26 @@ static int finalize(OacTrainer& t) {
                     }
                     return n * seeds;
                 };
-                // ring: 2 x (128 + BN) x kc x 4 B must fit 227 KB -> BN <= 64.  One CTA per SM: take the narrowest
-                // tile whose grid still fits ONE wave of 148 CTAs (a second, partial wave doubles the stage time).
+                // Two regimes.  Latency (the grid fits ~2 waves even with 64-wide tiles: single seed): one CTA per
+                // SM, the narrowest tile whose grid still fits ONE wave of 148 CTAs (a partial second wave doubles
+                // the stage time), 128-deep K chunks.  Throughput (many seeds): the widest tile the N extent allows
+                // (one A-tile staging feeds up to 256 output columns), 32-deep K chunks so the 2-slot ring is <= 96 KB
+                // and TWO CTAs share an SM (one stages / rounds while the other's MMAs and epilogue run).
                 int bn = 64;
-                while (bn > bn_min) {
-                    if (nmax <= bn / 2) { bn >>= 1; continue; }        // narrower tile is free
-                    if (ctas(bn / 2) <= 148) { bn >>= 1; continue; }   // more CTAs, still one wave
-                    break;
+                const bool throughput = !x3 && ctas(64) > 2 * 148;
+                if (throughput) {
+                    bn = bn_min;
+                    while (bn < 256 && bn < nmax) bn <<= 1;
+                    s.kc = 32;
+                } else {
+                    while (bn > bn_min) {
+                        if (nmax <= bn / 2) { bn >>= 1; continue; }        // narrower tile is free
+                        if (ctas(bn / 2) <= 148) { bn >>= 1; continue; }   // more CTAs, still one wave
+                        break;
+                    }
+                    s.kc = x3 ? 64 : 128;
                 }
                 s.bn = bn;
-                s.kc = x3 ? 64 : 128;
                 if (x3) {
                     const int nchunks = (kmax + s.kc - 1) / s.kc;
                     s.n_main = std::max(1, std::min(nchunks, 512 / bn - 1));
@@ -632,6 +642,24 @@ static int finalize(OacTrainer& t) {
     return 0;
 }
 
+// Launch with Programmatic Dependent Launch: the next stage's grid is scheduled as soon as every CTA of the
+// current one has started (each kernel executes griddepcontrol.launch_dependents first and
+// griddepcontrol.wait before touching global memory), which hides the launch + CTA-scheduling latency of
+// the dependent stages of a step.  Measured on B200 inside the CUDA graph it is a LOSS (209 vs 181 us per step),
+// so it is off unless OAC_PDL=1.
+static bool g_use_pdl = false;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
     const int seeds = t.cfg.n_seeds;
     for (Stage& s : t.stages) {
@@ -642,40 +670,40 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
                 TcStageParams tp; tp.sp = sp; tp.bn = s.bn; tp.kc = s.kc; tp.tmem_cols = s.tmem_cols; tp.n_main = s.n_main; tp.dbg = t.tc_dbg;
                 const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
                 if (!s.a_trans && !s.b_trans) {
-                    if (x3) gemm_tc_kernel<false, false, true><<<grid, TC_THREADS, s.smem, st>>>(tp);
-                    else gemm_tc_kernel<false, false, false><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                    if (x3) launch_pdl(gemm_tc_kernel<false, false, true>, grid, dim3(TC_THREADS), s.smem, st, tp);
+                    else launch_pdl(gemm_tc_kernel<false, false, false>, grid, dim3(TC_THREADS), s.smem, st, tp);
                 } else if (!s.a_trans) {
-                    if (x3) gemm_tc_kernel<false, true, true><<<grid, TC_THREADS, s.smem, st>>>(tp);
-                    else gemm_tc_kernel<false, true, false><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                    if (x3) launch_pdl(gemm_tc_kernel<false, true, true>, grid, dim3(TC_THREADS), s.smem, st, tp);
+                    else launch_pdl(gemm_tc_kernel<false, true, false>, grid, dim3(TC_THREADS), s.smem, st, tp);
                 } else {
-                    if (x3) gemm_tc_kernel<true, true, true><<<grid, TC_THREADS, s.smem, st>>>(tp);
-                    else gemm_tc_kernel<true, true, false><<<grid, TC_THREADS, s.smem, st>>>(tp);
+                    if (x3) launch_pdl(gemm_tc_kernel<true, true, true>, grid, dim3(TC_THREADS), s.smem, st, tp);
+                    else launch_pdl(gemm_tc_kernel<true, true, false>, grid, dim3(TC_THREADS), s.smem, st, tp);
                 }
                 OAC_CUDA(cudaGetLastError());
                 continue;
             }
             const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
             switch (sel) {
-                case 0: gemm_stage_kernel<32, 32, 2, 2, false, false><<<grid, 256, s.smem, st>>>(sp); break;
-                case 1: gemm_stage_kernel<32, 32, 2, 2, false, true><<<grid, 256, s.smem, st>>>(sp); break;
-                case 2: gemm_stage_kernel<32, 32, 2, 2, true, true><<<grid, 256, s.smem, st>>>(sp); break;
-                case 3: gemm_stage_kernel<64, 64, 4, 4, false, false><<<grid, 256, s.smem, st>>>(sp); break;
-                case 4: gemm_stage_kernel<64, 64, 4, 4, false, true><<<grid, 256, s.smem, st>>>(sp); break;
-                default: gemm_stage_kernel<64, 64, 4, 4, true, true><<<grid, 256, s.smem, st>>>(sp); break;
+                case 0: launch_pdl(gemm_stage_kernel<32, 32, 2, 2, false, false>, grid, dim3(256), s.smem, st, sp); break;
+                case 1: launch_pdl(gemm_stage_kernel<32, 32, 2, 2, false, true>, grid, dim3(256), s.smem, st, sp); break;
+                case 2: launch_pdl(gemm_stage_kernel<32, 32, 2, 2, true, true>, grid, dim3(256), s.smem, st, sp); break;
+                case 3: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, false>, grid, dim3(256), s.smem, st, sp); break;
+                case 4: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, true>, grid, dim3(256), s.smem, st, sp); break;
+                default: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, true, true>, grid, dim3(256), s.smem, st, sp); break;
             }
         } else if (s.kind == ST_POLICY_HEAD) {
             PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps;
             dim3 grid((s.max_rows + GLUE_SPC - 1) / GLUE_SPC, (unsigned)s.ph.size(), seeds);
             const size_t smem = sizeof(float) * ((size_t)2 * t.cfg.act_dim * t.cfg.hidden + 2 * t.cfg.act_dim * (1 + GLUE_SPC));
-            policy_head_kernel<<<grid, GLUE_THREADS, smem, st>>>(p);
+            launch_pdl(policy_head_kernel, grid, dim3(GLUE_THREADS), smem, st, p);
         } else if (s.kind == ST_CRITIC_HEAD) {
             dim3 grid((t.cfg.batch + GLUE_SPC - 1) / GLUE_SPC, seeds, 1);
-            critic_head_kernel<<<grid, GLUE_THREADS, 0, st>>>((const CriticHeadParams*)s.dev);
+            launch_pdl(critic_head_kernel, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
         } else {
             dim3 grid((t.cfg.batch + GLUE_SPC - 1) / GLUE_SPC, (unsigned)s.pg.size(), seeds);
             const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
             const size_t smem = sizeof(float) * ((size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_ + GLUE_SPC * 3 * A_);
-            policy_grad_kernel<<<grid, GLUE_THREADS, smem, st>>>(s.pgp);
+            launch_pdl(policy_grad_kernel, grid, dim3(GLUE_THREADS), smem, st, s.pgp);
         }
         OAC_CUDA(cudaGetLastError());
     }
@@ -752,6 +780,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
+    { const char* np_ = getenv("OAC_PDL"); g_use_pdl = (np_ && np_[0] == '1'); }
     const char* ng = getenv("OAC_NO_GRAPH");
     t->use_graph = !(ng && ng[0] == '1');
     *out = t;
