@@ -185,6 +185,9 @@ int oac_trainer_destroy(OacTrainer* t);
 int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* stream);
 /* Number of kernel launches one step issues (for bench.py's gpu_launches). */
 int oac_trainer_launches_per_step(const OacTrainer* t);
+/* Number of GEMM stages of the step that run on the warp-specialised TMA + tcgen05 kernel (tests assert the
+ * tensor-core path is the one measured). */
+int oac_trainer_ws_stages(const OacTrainer* t);
 /* Measurement aid: runs `iters` steps stage by stage (no graph) with a CUDA event between
  * stages and returns the mean duration of each stage in milliseconds (ms[n_stages]) and, per
  * stage, whether it is a GEMM stage (is_gemm) and its algorithmic FLOPs per seed (flops).
@@ -198,6 +201,8 @@ int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_stages, float*
 int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_trans, int32_t M, int32_t N, int32_t K,
                    const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
                    const float* bias, int32_t relu, void* stream);
+/* Which kernel the last oac_gemm_debug call ran: 0 SIMT, 1 per-tile tcgen05, 2 warp-specialised TMA + tcgen05. */
+int oac_gemm_debug_kernel(void);
 
 /* ---- inference ---- */
 /* TanhGaussianPolicy.forward on n rows: obs [n, obs_ld]; eps [n,A] or NULL (deterministic).

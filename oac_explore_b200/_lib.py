@@ -94,7 +94,7 @@ EXPORTS = [
     "oac_last_error_string", "oac_abi_version",
     "oac_replay_gather", "oac_replay_gather_dense", "oac_replay_add",
     "oac_trainer_layout", "oac_trainer_create", "oac_trainer_destroy", "oac_trainer_step",
-    "oac_trainer_launches_per_step", "oac_trainer_profile", "oac_gemm_debug",
+    "oac_trainer_launches_per_step", "oac_trainer_ws_stages", "oac_trainer_profile", "oac_gemm_debug", "oac_gemm_debug_kernel",
     "oac_policy_forward", "oac_q_forward", "oac_explore",
 ]
 
@@ -125,6 +125,7 @@ def lib():
     L.oac_trainer_destroy.argtypes = [vp]
     L.oac_trainer_step.argtypes = [vp, i32, vp]
     L.oac_trainer_launches_per_step.argtypes = [vp]
+    L.oac_trainer_ws_stages.argtypes = [vp]
     L.oac_trainer_profile.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.oac_gemm_debug.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
     L.oac_policy_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -1,0 +1,387 @@
+// Warp-specialised, persistent tcgen05 (kind::tf32) grouped-GEMM stage: the throughput path of the
+// batched-seed configuration (BASELINE config 5: 64 independent OAC seeds as grouped GEMMs).
+//
+// Same task table and fused epilogues as gemm_simt.cuh / gemm_tc.cuh, different machine mapping:
+//   * one persistent CTA per SM walks a static list of (seed, task, tile) work items;
+//   * warp 0 (one lane) is the TMA producer: every operand tile is fetched with
+//     cp.async.bulk.tensor.3d through a per-task tensor map ([seed][row][col] view of the arena), 32 k per
+//     pipeline slot, straight into the canonical UMMA layouts -- SWIZZLE_128B for K-contiguous operands,
+//     SWIZZLE_128B_ATOM_32B for the M/N-contiguous ones (dX and dW products), so transposed copies never
+//     exist.  The maps use the TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 to nearest while it
+//     copies (measured: tools/probes/tma_probe.cu), which removes the MMA's truncation bias without any
+//     rounding pass over shared memory or rounded copies of the weights.  Ragged M / N / K edges are
+//     zero-filled by the TMA bounds check.
+//   * warp 1 (one lane) issues tcgen05.mma into one of TWO TMEM accumulators (2 x 256 columns) and
+//     signals slot reuse / accumulator completion with tcgen05.commit -> mbarrier;
+//   * warps 2..9 are the epilogue: tcgen05.ld (lane = row) -> per-warp shared slab -> float4 accesses with
+//     consecutive lanes on consecutive columns, so bias/ReLU, the ReLU mask and the Adam (+Polyak) update
+//     of the weight block (param, two moments, target: 32 B per element) are fully coalesced and keep
+//     ~64 KB of loads in flight per SM.  The epilogue of tile i overlaps the TMA + MMA of tile i+1.
+//   * the bias gradient of a dW task (column sums of dY) is one extra N=32 MMA per k-step against a
+//     constant all-ones tile into spare TMEM columns.
+#pragma once
+#include <cuda.h>
+#include "gemm_tc.cuh"
+
+namespace oac {
+
+constexpr int WS_BM = 128;
+constexpr int WS_KC = 32;                        // k per pipeline slot = one 128-byte swizzle row
+constexpr int WS_EPI_WARPS = 8;
+constexpr int WS_THREADS = (2 + WS_EPI_WARPS) * 32;
+constexpr int WS_SLAB = 64;                      // columns per epilogue slab
+constexpr int WS_SLAB_LD = 68;                   // floats; 16-byte aligned rows, conflict-free v4 stores (lane = row)
+constexpr int WS_MAX_TASKS = 64;
+constexpr int WS_MAX_SLOTS = 8;
+constexpr int WS_BIAS_COL = 224;                 // TMEM column (inside an accumulator buffer) of the bias-gradient MMA
+constexpr int WS_BN_MAX_BIAS = 224;              // tile width limit for tasks that carry the bias MMA
+constexpr uint32_t WS_A_BYTES = WS_BM * WS_KC * 4;
+constexpr uint32_t WS_ONES_BYTES = 32 * WS_KC * 4;
+constexpr uint32_t WS_SLAB_BYTES = WS_EPI_WARPS * 32 * WS_SLAB_LD * 4;
+
+struct WsParams {
+    StageParams sp;
+    const CUtensorMap* tmaps;     // device, [2 * n_tasks]: A and B operand of every task
+    int n_tasks;
+    int tiles_per_seed;
+    int total_tiles;              // tiles_per_seed * n_seeds
+    int n_slots;                  // operand ring depth
+    int slot_bytes;               // WS_A_BYTES + max_bn * 128
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// beta^t for integer t by squaring (double): agrees with pow() to ~1e-15 relative, far below the fp32 rounding of
+// the two scalars derived from it, at a few dozen DP multiplies instead of a DP pow per tile.
+__device__ __forceinline__ double ipow(double b, int t) {
+    double r = 1.0;
+    while (t > 0) { if (t & 1) r *= b; b *= b; t >>= 1; }
+    return r;
+}
+__device__ __forceinline__ AdamScalars make_adam_scalars_fast(const AdamHyper& h, float lr, int t, int train_steps_done) {
+    AdamScalars s;
+    const double b1 = rint((double)h.beta1 * 1e6) * 1e-6, b2 = rint((double)h.beta2 * 1e6) * 1e-6;
+    s.step_size = (float)((double)lr / (1.0 - ipow(b1, t)));
+    s.bc2_sqrt = (float)sqrt(1.0 - ipow(b2, t));
+    s.beta1 = (float)b1; s.beta2 = (float)b2;
+    s.one_m_beta1 = (float)(1.0 - b1); s.one_m_beta2 = (float)(1.0 - b2);
+    s.eps = h.eps; s.tau = h.tau; s.one_m_tau = h.one_minus_tau;
+    s.do_polyak = ((train_steps_done - 1) % (h.target_period > 0 ? h.target_period : 1)) == 0;
+    return s;
+}
+// adam_update (gemm_simt.cuh) on register operands: same operation order / roundings
+__device__ __forceinline__ void adam_core(float g, float& p, float& m, float& v, float& tgt, bool has_tgt, const AdamScalars& s) {
+    m = __fadd_rn(__fmul_rn(m, s.beta1), __fmul_rn(s.one_m_beta1, g));
+    v = __fadd_rn(__fmul_rn(v, s.beta2), __fmul_rn(__fmul_rn(s.one_m_beta2, g), g));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
+    p = __fadd_rn(p, __fmul_rn(-s.step_size, __fdiv_rn(m, denom)));
+    if (has_tgt) tgt = __fadd_rn(__fmul_rn(tgt, s.one_m_tau), __fmul_rn(p, s.tau));
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
+    extern __shared__ __align__(1024) uint8_t ws_smem[];
+    __shared__ __align__(8) uint64_t s_full[WS_MAX_SLOTS], s_empty[WS_MAX_SLOTS], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_tile0[WS_MAX_TASKS + 1];
+
+    pdl_prologue();
+    const StageParams& sp = wp.sp;
+    const GemmTask* __restrict__ tasks = sp.tasks;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* ring = ws_smem + ((1024u - (smem_u32(ws_smem) & 1023u)) & 1023u);
+    uint8_t* ones = ring + (size_t)wp.n_slots * wp.slot_bytes;
+    float* slabs = reinterpret_cast<float*>(ones + WS_ONES_BYTES);
+
+    // ---- one-time setup ----
+    for (int i = tid; i <= wp.n_tasks; i += WS_THREADS) s_tile0[i] = (i < wp.n_tasks) ? tasks[i].tile0 : wp.tiles_per_seed;
+    for (int i = tid; i < (int)(WS_ONES_BYTES / 4); i += WS_THREADS) reinterpret_cast<float*>(ones)[i] = 1.0f;
+    fence_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < wp.n_slots; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        mbar_init(&s_tfull[0], 1); mbar_init(&s_tfull[1], 1);
+        mbar_init(&s_tempty[0], WS_EPI_WARPS); mbar_init(&s_tempty[1], WS_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    auto decode = [&](int g, int& seed, int& j, int& tm, int& tn) {
+        seed = g / wp.tiles_per_seed;
+        const int r = g - seed * wp.tiles_per_seed;
+        j = 0;
+        while (r >= s_tile0[j + 1]) ++j;
+        const int t = r - s_tile0[j];
+        const int tnc = tasks[j].tiles_n;
+        tm = t / tnc; tn = t - tm * tnc;
+    };
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x) {
+                int seed, j, tm, tn;
+                decode(g, seed, j, tm, tn);
+                const GemmTask& T = tasks[j];
+                const CUtensorMap* ta = wp.tmaps + 2 * j;
+                const CUtensorMap* tb = ta + 1;
+                const int bn = T.bn;
+                const int m0 = tm * WS_BM, n0 = tn * bn;
+                const int nch = (T.K + WS_KC - 1) / WS_KC;
+                const uint32_t bytes = WS_A_BYTES + (uint32_t)bn * (WS_KC * 4);
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(&s_empty[slot], ph ^ 1u);
+                    const uint32_t sa = smem_u32(ring + (size_t)slot * wp.slot_bytes), sb = sa + WS_A_BYTES;
+                    const uint32_t bar = smem_u32(&s_full[slot]);
+                    mbar_expect_tx(bar, bytes);
+                    if (!A_MN) tma_load_3d(sa, ta, c * WS_KC, m0, seed, bar);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < WS_BM / 32; ++i) tma_load_3d(sa + i * 4096, ta, m0 + 32 * i, c * WS_KC, seed, bar);
+                    }
+                    if (!B_MN) tma_load_3d(sb, tb, c * WS_KC, n0, seed, bar);
+                    else for (int i = 0; i < (bn >> 5); ++i) tma_load_3d(sb + i * 4096, tb, n0 + 32 * i, c * WS_KC, seed, bar);
+                    if (++slot == wp.n_slots) { slot = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            int tl = 0;
+            const uint64_t ones_desc = umma_desc(smem_u32(ones), 4096, 512, 1);
+            const uint32_t idesc_bias = umma_idesc_tf32(WS_BM, 32, true, true);
+            for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x, ++tl) {
+                int seed, j, tm, tn;
+                decode(g, seed, j, tm, tn);
+                const GemmTask& T = tasks[j];
+                const int bn = T.bn, K = T.K;
+                const int nch = (K + WS_KC - 1) / WS_KC;
+                const int buf = tl & 1;
+                mbar_wait(&s_tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_main = tmem + (uint32_t)(buf * 256), d_bias = d_main + WS_BIAS_COL;
+                const uint32_t idesc = umma_idesc_tf32(WS_BM, bn, A_MN, B_MN);
+                const bool bias_mma = A_MN && B_MN && T.epi == EPI_ADAM && T.has_bias && tn == 0;
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(&s_full[slot], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(ring + (size_t)slot * wp.slot_bytes), sb = sa + WS_A_BYTES;
+                    const int ksteps = (min(WS_KC, K - c * WS_KC) + 7) >> 3;
+                    // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), a k-step is 32 B inside the swizzle row.
+                    // MN-major (SWIZZLE_128B_ATOM_32B): slot holds [mn-atom (32)][k (32 rows)][128 B]: atoms 4096 B apart
+                    // (LBO), 4-row k-groups 512 B apart (SBO), a k-step is 8 rows = 1024 B.
+                    uint64_t ad = A_MN ? umma_desc(sa, 4096, 512, 1) : umma_desc(sa, 16, 1024, 2);
+                    uint64_t bd = B_MN ? umma_desc(sb, 4096, 512, 1) : umma_desc(sb, 16, 1024, 2);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+                        umma_tf32(d_main, ad, bd, idesc, acc);
+                        if (bias_mma) umma_tf32(d_bias, ad, ones_desc, idesc_bias, acc);
+                        ad += A_MN ? 64u : 2u;
+                        bd += B_MN ? 64u : 2u;
+                    }
+                    umma_commit(&s_empty[slot]);                 // slot reusable once these MMAs have read it
+                    if (++slot == wp.n_slots) { slot = 0; ph ^= 1u; }
+                }
+                umma_commit(&s_tfull[buf]);                      // accumulator complete
+            }
+        }
+    } else {
+        // =========================== epilogue warps ===========================
+        const int e = warp - 2;
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        const int hsel = e >> 2;                                 // two warps per quarter alternate over the slabs
+        float* slab = slabs + e * (32 * WS_SLAB_LD);
+        float* __restrict__ m1 = sp.as.base[AR_ADAM_M];
+        float* __restrict__ m2 = sp.as.base[AR_ADAM_V];
+        float* __restrict__ pb0 = sp.as.base[AR_PARAM];
+        const int rsub = lane >> 4, c4 = (lane & 15) << 2;
+        int tl = 0;
+        for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x, ++tl) {
+            int seed, j, tm, tn;
+            decode(g, seed, j, tm, tn);
+            const GemmTask& T = tasks[j];
+            const int bn = T.bn, M = T.M, N = T.N, epi = T.epi, ldc = T.ldc;
+            const int m0 = tm * WS_BM, n0 = tn * bn;
+            const int nlim = min(N, n0 + bn);
+            const int buf = tl & 1;
+            float* __restrict__ C = resolve(sp.as, T.C, seed);
+            const bool is_adam = epi == EPI_ADAM;
+            AdamScalars s;
+            float* __restrict__ am = nullptr; float* __restrict__ av = nullptr; float* __restrict__ tg = nullptr;
+            if (is_adam) {
+                const int32_t* cnt = sp.as.counters + seed * sp.as.n_counters;
+                s = make_adam_scalars_fast(sp.hyper, T.lr, cnt[T.counter], cnt[CNT_TRAIN_STEPS]);
+                am = m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off;
+                av = m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off;
+                if (T.target_off >= 0 && s.do_polyak) tg = pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off;
+            }
+            const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
+            const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+            const int ldmask = T.ldmask;
+
+            mbar_wait(&s_tfull[buf], ((uint32_t)tl >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+            const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
+            for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
+                const int c0 = sl * WS_SLAB;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {                 // 32 columns at a time: 32 live registers
+                    if (c0 + 32 * hf >= bn) break;
+                    float v[32];
+                    tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf), &v[0]);
+                    if (c0 + 32 * hf + 16 < bn) tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf + 16), &v[16]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(slab + lane * WS_SLAB_LD + 32 * hf + 4 * i) =
+                            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                __syncwarp();
+                const int n = n0 + c0 + c4;
+                if (n < nlim) {
+                    const bool vec = n + 3 < nlim;
+                    if (is_adam) {
+                        constexpr int RB = 4;                    // row pairs per batch: 4 x 4 float4 loads in flight per lane
+                        for (int rp0 = 0; rp0 < 16; rp0 += RB) {
+                            float4 x[RB], p4[RB], a4[RB], v4[RB], t4[RB];
+                            long long eo[RB];
+#pragma unroll
+                            for (int r = 0; r < RB; ++r) {
+                                const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
+                                eo[r] = (m < M) ? (long long)m * ldc + n : -1;
+                                x[r] = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
+                                if (eo[r] >= 0 && vec) {
+                                    p4[r] = *reinterpret_cast<const float4*>(C + eo[r]);
+                                    a4[r] = *reinterpret_cast<const float4*>(am + eo[r]);
+                                    v4[r] = *reinterpret_cast<const float4*>(av + eo[r]);
+                                    if (tg) t4[r] = *reinterpret_cast<const float4*>(tg + eo[r]);
+                                }
+                            }
+#pragma unroll
+                            for (int r = 0; r < RB; ++r) {
+                                if (eo[r] < 0) continue;
+                                if (vec) {
+                                    const bool ht = tg != nullptr;
+                                    adam_core(x[r].x, p4[r].x, a4[r].x, v4[r].x, t4[r].x, ht, s);
+                                    adam_core(x[r].y, p4[r].y, a4[r].y, v4[r].y, t4[r].y, ht, s);
+                                    adam_core(x[r].z, p4[r].z, a4[r].z, v4[r].z, t4[r].z, ht, s);
+                                    adam_core(x[r].w, p4[r].w, a4[r].w, v4[r].w, t4[r].w, ht, s);
+                                    *reinterpret_cast<float4*>(C + eo[r]) = p4[r];
+                                    *reinterpret_cast<float4*>(am + eo[r]) = a4[r];
+                                    *reinterpret_cast<float4*>(av + eo[r]) = v4[r];
+                                    if (ht) *reinterpret_cast<float4*>(tg + eo[r]) = t4[r];
+                                } else {
+#pragma unroll
+                                    for (int jj = 0; jj < 3; ++jj) {             // a partial float4 holds at most 3 live columns
+                                        if (n + jj >= nlim) continue;
+                                        const float xj = jj == 0 ? x[r].x : (jj == 1 ? x[r].y : x[r].z);
+                                        const long long ee = eo[r] + jj;
+                                        float pp = C[ee], mm = am[ee], vv = av[ee], tt = tg ? tg[ee] : 0.f;
+                                        adam_core(xj, pp, mm, vv, tt, tg != nullptr, s);
+                                        C[ee] = pp; am[ee] = mm; av[ee] = vv;
+                                        if (tg) tg[ee] = tt;
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias != nullptr) {
+                            if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                            else { b4.x = __ldg(bias + n); if (n + 1 < nlim) b4.y = __ldg(bias + n + 1); if (n + 2 < nlim) b4.z = __ldg(bias + n + 2); }
+                        }
+#pragma unroll 4
+                        for (int rp = 0; rp < 16; ++rp) {
+                            const int row = 2 * rp + rsub, m = m0 + q * 32 + row;
+                            if (m >= M) continue;
+                            float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
+                            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                            if (epi == EPI_BIAS_RELU) { x.x = relu(x.x); x.y = relu(x.y); x.z = relu(x.z); x.w = relu(x.w); }
+                            float* dst = C + (long long)m * ldc + n;
+                            if (vec) {
+                                if (mask != nullptr) {
+                                    const float4 k4 = __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n));
+                                    x.x = k4.x > 0.f ? x.x : 0.f; x.y = k4.y > 0.f ? x.y : 0.f;
+                                    x.z = k4.z > 0.f ? x.z : 0.f; x.w = k4.w > 0.f ? x.w : 0.f;
+                                }
+                                *reinterpret_cast<float4*>(dst) = x;
+                            } else {
+#pragma unroll
+                                for (int jj = 0; jj < 3; ++jj) {
+                                    if (n + jj >= nlim) continue;
+                                    float y = jj == 0 ? x.x : (jj == 1 ? x.y : x.z);
+                                    if (mask != nullptr) y = __ldg(mask + (long long)m * ldmask + n + jj) > 0.f ? y : 0.f;
+                                    dst[jj] = y;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                    // slab is rewritten by the next pass
+            }
+            // bias block of a dW task: column sums of dY sit in the spare TMEM columns (every column is the row sum)
+            if (is_adam && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
+                const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
+                const int m = m0 + q * 32 + lane;
+                if (m < M) {
+                    float* pb = resolve(sp.as, T.bias, seed) + m;
+                    float* tgb = T.target_bias_off >= 0 ? pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_bias_off + m : nullptr;
+                    if (T.train_bias) {
+                        adam_update(gsum, pb, m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_bias_off + m,
+                                    m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_bias_off + m, tgb, s);
+                    } else if (tgb != nullptr && s.do_polyak) {
+                        *tgb = __fadd_rn(__fmul_rn(*tgb, s.one_m_tau), __fmul_rn(*pb, s.tau));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace oac

@@ -198,7 +198,8 @@ struct HeadSrc {
     int row0;
     Ref w3, b3;      // [n_heads, H], [n_heads]
     int n_heads;
-    Ref dq;          // [B, n_heads] gradient w.r.t. the (pre-exp) head outputs, written here
+    Ref dq;          // [B, dq_ld] gradient w.r.t. the (pre-exp) head outputs, written here
+    int dq_ld;       // row stride of dq (n_heads rounded up to 4)
     int write_dh2;   // also emit dh2[b,:] = (dq[b,:] W3) * (h2 > 0) with the CURRENT W3
     Ref dh2;         // [B, H]
 };
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticH
     __syncthreads();
     // every dq goes to global (GEMM operand of the weight-gradient stage) and to the sample's shared copy
     auto put = [&](int s, int i, float v) {
-        resolve(p.as, p.src[s].dq, seed)[(long long)b * p.src[s].n_heads + i] = v;
+        resolve(p.as, p.src[s].dq, seed)[(long long)b * p.src[s].dq_ld + i] = v;
         dqv[s_goff[s] + i] = v;
     };
     if (live && g == 0 && lane == 0) {
@@ -409,7 +410,8 @@ struct PolicyGradTask {
     int n_src;
     Ref save;         // [., 4, A] from policy_head (rows of this policy start at save_row0)
     int save_row0;
-    Ref dhead;        // out: [B, 2A]  d loss / d(mean), d loss / d(raw log_std)
+    Ref dhead;        // out: [B, dhead_ld]  d loss / d(mean), d loss / d(raw log_std)
+    int dhead_ld;     // row stride (2A rounded up to 4)
     int entropy;      // 1: alpha*log_pi term present (stochastic policy)
     Ref wh;           // policy head weights [2A, H]
     Ref h2;           // policy second hidden activation [*, H]; rows of this batch start at h2_row0
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradPar
         const float alpha = io[p.off_scalars + SC_ALPHA];
         const float invB = 1.0f / (float)B;
         const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
-        float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * 2 * A;
+        float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * T.dhead_ld;
         for (int j = lane; j < A; j += 32) {
             const float a = save[0 * A + j];
             const float one_m_a2 = 1.f - a * a;

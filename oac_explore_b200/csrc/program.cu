@@ -19,6 +19,7 @@
 
 #include "glue.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_ws.cuh"
 #include "oac_error.h"
 
 namespace oac {
@@ -133,6 +134,9 @@ struct Stage {
     int kc = 0;
     size_t smem = 0;
     int use_tc = 0, bn = 0, tmem_cols = 0, n_main = 1;     // tcgen05 path
+    // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
+    int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
+    void* ws_tmaps = nullptr;
     int max_tiles = 0;
     int max_rows = 0;
     const char* name = "";
@@ -155,6 +159,7 @@ struct OacTrainer {
     bool use_graph = true;
     int n_opt = 0;
     long long* tc_dbg = nullptr;
+    bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
 };
 
 namespace oac {
@@ -235,7 +240,7 @@ struct Builder {
         CritAct a; a.rows = nblk * B;
         a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
         a.q = work((long long)a.rows * heads);
-        a.dq = work((long long)a.rows * heads);
+        a.dq = work((long long)a.rows * pad4(heads));         // leading dimension pad4(heads): TMA needs 16-byte row strides
         a.dh2 = work((long long)a.rows * H); a.dh1 = work((long long)a.rows * H);
         a.da = work((long long)a.rows * A);
         return a;
@@ -275,14 +280,14 @@ struct Builder {
         HeadSrc h; memset(&h, 0, sizeof(h));
         h.h2 = a.h2; h.row0 = row0; h.w3 = P(n.off_w2); h.b3 = P(n.off_b2); h.n_heads = n.n_out;
         h.write_dh2 = 0; h.dh2 = Ref{a.dh2.arena, a.dh2.off + (long long)row0 * H};
-        h.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * n.n_out};
+        h.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)}; h.dq_ld = pad4(n.n_out);
         return h;
     }
     // dh2 = (dq W3) * (h2>0) for rows [row0, row0+B) of a critic activation set
     void crit_dh2(Stage& s, int ni, const CritAct& a, int row0) {
         const OacNetLayout& n = net(ni);
         long long ro = (long long)row0 * H;
-        dx(s, Ref{a.dq.arena, a.dq.off + (long long)row0 * n.n_out}, n.n_out, B, n.n_out, P(n.off_w2), H, H,
+        dx(s, Ref{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)}, pad4(n.n_out), B, n.n_out, P(n.off_w2), H, H,
            Ref{a.dh2.arena, a.dh2.off + ro}, H, Ref{a.h2.arena, a.h2.off + ro}, H, true);
     }
     void crit_dh1(Stage& s, int ni, const CritAct& a, int row0) {
@@ -298,22 +303,22 @@ struct Builder {
         long long ro = (long long)row0 * H;
         Ref dh1{a.dh1.arena, a.dh1.off + ro}, dh2{a.dh2.arena, a.dh2.off + ro};
         Ref h1{a.h1.arena, a.h1.off + ro}, h2{a.h2.arena, a.h2.off + ro};
-        Ref dq{a.dq.arena, a.dq.off + (long long)row0 * n.n_out};
+        Ref dq{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)};
         dw(s, dh1, H, X(xblk), L.x_ld, B, H, O + A, n.off_w0, n.in_ld, n.off_b0,
            tn ? tn->off_w0 : -1, tn ? tn->off_b0 : -1, lr, counter, 1);
         dw(s, dh2, H, h1, H, B, H, H, n.off_w1, H, n.off_b1, tn ? tn->off_w1 : -1, tn ? tn->off_b1 : -1, lr, counter, 1);
-        dw(s, dq, n.n_out, h2, H, B, n.n_out, H, n.off_w2, H, n.off_b2, tn ? tn->off_w2 : -1, tn ? tn->off_b2 : -1,
+        dw(s, dq, pad4(n.n_out), h2, H, B, n.n_out, H, n.off_w2, H, n.off_b2, tn ? tn->off_w2 : -1, tn ? tn->off_b2 : -1,
            lr, counter, c.train_bias);
     }
     // policy backward from dhead [B,2A] at rows [row0,row0+B) of a policy activation set
     struct PolGrad { Ref dhead, dh2, dh1; };
     PolGrad alloc_polgrad() {
-        PolGrad g; g.dhead = work((long long)B * 2 * A); g.dh2 = work((long long)B * H); g.dh1 = work((long long)B * H);
+        PolGrad g; g.dhead = work((long long)B * pad4(2 * A)); g.dh2 = work((long long)B * H); g.dh1 = work((long long)B * H);
         return g;
     }
     void pol_dh2(Stage& s, int ni, const PolAct& a, int row0, const PolGrad& g) {
         const OacNetLayout& n = net(ni);
-        dx(s, g.dhead, 2 * A, B, 2 * A, P(n.off_w2), H, H, g.dh2, H, Ref{a.h2.arena, a.h2.off + (long long)row0 * H}, H, true);
+        dx(s, g.dhead, pad4(2 * A), B, 2 * A, P(n.off_w2), H, H, g.dh2, H, Ref{a.h2.arena, a.h2.off + (long long)row0 * H}, H, true);
     }
     void pol_dh1(Stage& s, int ni, const PolAct& a, int row0, const PolGrad& g) {
         const OacNetLayout& n = net(ni);
@@ -324,7 +329,7 @@ struct Builder {
         long long ro = (long long)row0 * H;
         dw(s, g.dh1, H, X(xblk), L.x_ld, B, H, O, n.off_w0, n.in_ld, n.off_b0, -1, -1, lr, counter, 1);
         dw(s, g.dh2, H, Ref{a.h1.arena, a.h1.off + ro}, H, B, H, H, n.off_w1, H, n.off_b1, -1, -1, lr, counter, 1);
-        dw(s, g.dhead, 2 * A, Ref{a.h2.arena, a.h2.off + ro}, H, B, 2 * A, H, n.off_w2, H, n.off_b2, -1, -1, lr, counter, 1);
+        dw(s, g.dhead, pad4(2 * A), Ref{a.h2.arena, a.h2.off + ro}, H, B, 2 * A, H, n.off_w2, H, n.off_b2, -1, -1, lr, counter, 1);
     }
     // policy-loss gradient task: critics (dh1 rows, fc0 weights) -> dhead, and the policy's own dh2
     PolicyGradTask pg_task(const std::vector<std::pair<int, Ref>>& crit_dh1, int pol, const PolAct& a, int row0,
@@ -336,7 +341,7 @@ struct Builder {
             t_.dh1[i] = c_.second; t_.w1[i] = P(qn.off_w0); t_.ld[i] = qn.in_ld; ++i;
         }
         t_.n_src = i;
-        t_.save = a.save; t_.save_row0 = row0; t_.dhead = g.dhead; t_.entropy = entropy ? 1 : 0;
+        t_.save = a.save; t_.save_row0 = row0; t_.dhead = g.dhead; t_.dhead_ld = pad4(2 * A); t_.entropy = entropy ? 1 : 0;
         t_.wh = P(net(pol).off_w2); t_.h2 = a.h2; t_.h2_row0 = row0; t_.dhp2 = g.dh2;
         return t_;
     }
@@ -541,6 +546,125 @@ static int upload(OacTrainer& t, const T* host, size_t count, void** dev) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// warp-specialised tcgen05 path: eligibility, tile plan, tensor maps
+// ------------------------------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TensorMapEncodeFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    }
+    return n;
+}
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Every operand must be expressible as a [seed][row][col] fp32 tensor with 16-byte aligned base and strides, and the
+// float4 epilogue needs the same of the outputs.
+static bool ws_eligible(const OacTrainer& t, const Stage& s) {
+    const ArenaSet& as = t.as;
+    const int seeds = t.cfg.n_seeds;
+    if ((int)s.gemm.size() > WS_MAX_TASKS) return false;
+    for (int a = 0; a < AR_COUNT; ++a)
+        if (seeds > 1 && (as.stride[a] & 3)) return false;
+    for (const GemmTask& g : s.gemm) {
+        if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
+        if (!al16(resolve(as, g.A, 0)) || !al16(resolve(as, g.B, 0)) || !al16(resolve(as, g.C, 0))) return false;
+        if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_RELU) && !al16(resolve(as, g.bias, 0))) return false;
+        if (g.epi == EPI_MASK && ((g.ldmask & 3) || !al16(resolve(as, g.mask, 0)))) return false;
+        if (g.epi == EPI_ADAM) {
+            if ((g.adam_off & 3) || (g.target_off >= 0 && (g.target_off & 3))) return false;
+            if (!al16(as.base[AR_ADAM_M]) || !al16(as.base[AR_ADAM_V]) || !al16(as.base[AR_PARAM])) return false;
+            if (!(g.a_trans && g.b_trans)) return false;       // the bias-gradient MMA assumes the dW operand layouts
+        }
+    }
+    return tensor_map_encoder() != nullptr;
+}
+
+static int ws_plan(OacTrainer& t, Stage& s) {
+    const int seeds = t.cfg.n_seeds;
+    const int gran = s.b_trans ? 32 : 16;                      // MN-major B tiles come in 32-column TMA boxes
+    auto width = [&](const GemmTask& g, int cap) {             // tile width for a column cap: even split, rounded up
+        const int lim = (g.epi == EPI_ADAM && g.has_bias) ? std::min(cap, (int)WS_BN_MAX_BIAS) : cap;
+        const int tn = (g.N + lim - 1) / lim;
+        int bn = (((g.N + tn - 1) / tn) + gran - 1) / gran * gran;
+        return std::max(bn, gran);
+    };
+    auto tiles = [&](int cap) {
+        long long n = 0;
+        for (auto& g : s.gemm) { const int bn = width(g, cap); n += (long long)((g.M + WS_BM - 1) / WS_BM) * ((g.N + bn - 1) / bn); }
+        return n;
+    };
+    // widest tiles that still give every SM work; the narrowest ones when even those cannot (single seed: latency)
+    int cap = 256;
+    while (cap > 32 && tiles(cap) * seeds < sm_count()) cap >>= 1;
+    int t0 = 0, bn_max = 0;
+    for (auto& g : s.gemm) {
+        g.bn = width(g, cap);
+        g.tiles_m = (g.M + WS_BM - 1) / WS_BM; g.tiles_n = (g.N + g.bn - 1) / g.bn;
+        g.tile0 = t0; t0 += g.tiles_m * g.tiles_n;
+        bn_max = std::max(bn_max, g.bn);
+    }
+    s.ws_tiles_per_seed = t0;
+    s.ws_slot_bytes = (int)WS_A_BYTES + bn_max * (WS_KC * 4);
+    const int budget = 224 * 1024 - 1024 - (int)WS_ONES_BYTES - (int)WS_SLAB_BYTES;
+    s.ws_slots = std::min((int)WS_MAX_SLOTS, budget / s.ws_slot_bytes);
+    if (s.ws_slots < 2) return set_error(OAC_E_INVALID, "internal: ws ring does not fit");
+    s.smem = (size_t)s.ws_slots * s.ws_slot_bytes + WS_ONES_BYTES + WS_SLAB_BYTES + 1024;
+    s.ws_grid = (int)std::min<long long>((long long)t0 * seeds, sm_count());
+    // tensor maps
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    std::vector<CUtensorMap> maps(2 * s.gemm.size());
+    for (size_t i = 0; i < s.gemm.size(); ++i) {
+        const GemmTask& g = s.gemm[i];
+        for (int op = 0; op < 2; ++op) {
+            const Ref r = op == 0 ? g.A : g.B;
+            const bool mn = op == 0 ? g.a_trans != 0 : g.b_trans != 0;
+            const int ld = op == 0 ? g.lda : g.ldb;
+            const int ext = op == 0 ? g.M : g.N;               // M / N extent of this operand
+            const long long sstride = std::max<long long>(t.as.stride[r.arena], 4);
+            cuuint64_t dims[3], strides[2];
+            cuuint32_t box[3], es[3] = {1, 1, 1};
+            if (!mn) { dims[0] = (cuuint64_t)g.K; dims[1] = (cuuint64_t)ext; box[0] = WS_KC; box[1] = op == 0 ? WS_BM : (cuuint32_t)g.bn; }
+            else     { dims[0] = (cuuint64_t)ext; dims[1] = (cuuint64_t)g.K; box[0] = 32; box[1] = WS_KC; }
+            dims[2] = (cuuint64_t)seeds; box[2] = 1;
+            strides[0] = (cuuint64_t)ld * 4; strides[1] = (cuuint64_t)sstride * 4;
+            // TFLOAT32: the TMA unit rounds fp32 -> tf32 (nearest) on the way into shared memory
+            CUresult rc = enc(&maps[2 * i + op], CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, (void*)resolve(t.as, r, 0), dims, strides,
+                              box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) {
+                char msg[160];
+                snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) for stage %s task %d operand %d", (int)rc, s.name, (int)i, op);
+                return set_error(OAC_E_INVALID, msg);
+            }
+        }
+    }
+    if (int e = upload(t, maps.data(), maps.size(), &s.ws_tmaps)) return e;
+    if (int e = upload(t, s.gemm.data(), s.gemm.size(), &s.dev)) return e;
+    s.use_ws = 1;
+    return 0;
+}
+
 static int finalize(OacTrainer& t) {
     const int seeds = t.cfg.n_seeds;
     for (Stage& s : t.stages) {
@@ -556,6 +680,10 @@ static int finalize(OacTrainer& t) {
             }
             if (t.cfg.gemm_path == OAC_GEMM_TF32 || t.cfg.gemm_path == OAC_GEMM_TF32X3) {
                 const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
+                if (!x3 && t.allow_ws && ws_eligible(t, s)) {
+                    if (int e = ws_plan(t, s)) return e;
+                    continue;
+                }
                 // tcgen05 path: 128 x BN tiles.  Pick the largest BN that still fills the chip.
                 s.use_tc = 1;
                 const int bn_min = s.b_trans ? 32 : 16;
@@ -666,6 +794,17 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
         if (s.kind == ST_GEMM) {
             StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
+            if (s.use_ws) {
+                WsParams wp; wp.sp = sp; wp.tmaps = (const CUtensorMap*)s.ws_tmaps; wp.n_tasks = (int)s.gemm.size();
+                wp.tiles_per_seed = s.ws_tiles_per_seed; wp.total_tiles = s.ws_tiles_per_seed * seeds;
+                wp.n_slots = s.ws_slots; wp.slot_bytes = s.ws_slot_bytes;
+                const dim3 wg(s.ws_grid), wb(WS_THREADS);
+                if (!s.a_trans && !s.b_trans) launch_pdl(gemm_ws_kernel<false, false>, wg, wb, s.smem, st, wp);
+                else if (!s.a_trans) launch_pdl(gemm_ws_kernel<false, true>, wg, wb, s.smem, st, wp);
+                else launch_pdl(gemm_ws_kernel<true, true>, wg, wb, s.smem, st, wp);
+                OAC_CUDA(cudaGetLastError());
+                continue;
+            }
             if (s.use_tc) {
                 TcStageParams tp; tp.sp = sp; tp.bn = s.bn; tp.kc = s.kc; tp.tmem_cols = s.tmem_cols; tp.n_main = s.n_main; tp.dbg = t.tc_dbg;
                 const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
@@ -775,10 +914,16 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_in((const void*)gemm_tc_kernel<false, false, true>);
         opt_in((const void*)gemm_tc_kernel<false, true, true>);
         opt_in((const void*)gemm_tc_kernel<true, true, true>);
+        const int ws_big = 224 * 1024;
+        auto opt_ws = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_big); };
+        opt_ws((const void*)gemm_ws_kernel<false, false>);
+        opt_ws((const void*)gemm_ws_kernel<false, true>);
+        opt_ws((const void*)gemm_ws_kernel<true, true>);
         opt_in((const void*)policy_head_kernel);
         opt_in((const void*)policy_grad_kernel);
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
+    { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
     { const char* np_ = getenv("OAC_PDL"); g_use_pdl = (np_ && np_[0] == '1'); }
     const char* ng = getenv("OAC_NO_GRAPH");
@@ -797,6 +942,12 @@ extern "C" int oac_trainer_destroy(OacTrainer* t) {
 
 extern "C" int oac_trainer_launches_per_step(const OacTrainer* t) {
     return t ? (int)t->stages.size() : 0;
+}
+
+extern "C" int oac_trainer_ws_stages(const OacTrainer* t) {
+    int n = 0;
+    if (t) for (const Stage& s : t->stages) n += s.use_ws;
+    return n;
 }
 
 extern "C" int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* stream) {
@@ -868,6 +1019,10 @@ extern "C" int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_sta
     return 0;
 }
 
+static int g_debug_kernel = -1;
+// Which kernel the last oac_gemm_debug call ran: 0 SIMT, 1 per-tile tcgen05, 2 warp-specialised TMA + tcgen05.
+extern "C" int oac_gemm_debug_kernel(void) { return g_debug_kernel; }
+
 // Test / measurement aid: one GEMM  C[M,N] = epi(sum_k A(m,k) B(n,k))  through either stage kernel.
 extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_trans, int32_t M, int32_t N, int32_t K,
                               const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
@@ -904,11 +1059,16 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
         cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     }
+    { const char* nw = getenv("OAC_NO_WS"); t.allow_ws = !(nw && nw[0] == '1'); }
     int rc = finalize(t);
     const char* dbg_env = getenv("OAC_TC_DEBUG");
     const int dbg_n = 64;
     if (dbg_env && dbg_env[0] == '1') { cudaMalloc(&t.tc_dbg, sizeof(long long) * 8 * dbg_n * 8); cudaMemset(t.tc_dbg, 0, sizeof(long long) * 8 * dbg_n * 8); }
+    g_debug_kernel = rc ? -1 : (s.use_ws ? 2 : (s.use_tc ? 1 : 0));
     if (!rc) rc = launch_stages(t, 0, (cudaStream_t)stream);
     if (!rc && t.tc_dbg) rc = launch_stages(t, 0, (cudaStream_t)stream);      // second (warm) run is the one reported
     cudaStreamSynchronize((cudaStream_t)stream);

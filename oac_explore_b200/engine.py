@@ -57,6 +57,7 @@ class Engine(object):
         self.handle = h
         self.B, self.O, self.A, self.H = cfg.batch, cfg.obs_dim, cfg.act_dim, cfg.hidden
         self.launches_per_step = self.lib.oac_trainer_launches_per_step(self.handle)
+        self.ws_stages = self.lib.oac_trainer_ws_stages(self.handle)
 
     def __del__(self):
         h = getattr(self, "handle", None)

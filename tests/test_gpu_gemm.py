@@ -10,12 +10,14 @@ from tests.util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def run_gemm(path, a_trans, b_trans, M, N, K, bias=False, relu=False, pad=0, seed=0):
+def run_gemm(path, a_trans, b_trans, M, N, K, bias=False, relu=False, pad=0, seed=0, align4=False, want_kernel=None):
     from oac_explore_b200 import _lib
     g = torch.Generator(device='cuda').manual_seed(seed)
     lda = (M if a_trans else K) + pad
     ldb = (N if b_trans else K) + pad
     ldc = N + pad
+    if align4:          # 16-byte row strides: what the TMA-fed kernel needs (the step's own buffers are laid out so)
+        lda, ldb, ldc = [(x + 3) // 4 * 4 for x in (lda, ldb, ldc)]
     A = torch.randn((K if a_trans else M, lda), device='cuda', generator=g)
     B = torch.randn((K if b_trans else N, ldb), device='cuda', generator=g)
     Cm = torch.full((M, ldc), 7.0, device='cuda')
@@ -23,6 +25,8 @@ def run_gemm(path, a_trans, b_trans, M, N, K, bias=False, relu=False, pad=0, see
     _lib.check(_lib.lib().oac_gemm_debug(path, int(a_trans), int(b_trans), M, N, K, _lib.ptr(A), lda, _lib.ptr(B), ldb,
                                          _lib.ptr(Cm), ldc, _lib.ptr(bvec), int(relu), _lib.current_stream()),
                "oac_gemm_debug")
+    if want_kernel is not None:
+        assert _lib.lib().oac_gemm_debug_kernel() == want_kernel
     Am = (A[:, :M].t() if a_trans else A[:, :K]).double()
     Bm = (B[:, :N].t() if b_trans else B[:, :K]).double()
     ref = Am @ Bm.t()
@@ -62,3 +66,17 @@ def test_tcgen05_3xtf32_gemm(M, N, K, a_trans, b_trans):
     for pad in (0, 3):
         got, ref = run_gemm(2, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=False, pad=pad)
         assert rel_err(got, ref) <= 3e-6, (pad, rel_err(got, ref))
+
+
+WS_SHAPES = SHAPES + [(1024, 256, 393), (384, 512, 264), (256, 393, 1000), (640, 224, 96)]
+
+
+@pytest.mark.parametrize("M,N,K", WS_SHAPES)
+@pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
+def test_ws_tcgen05_tf32_gemm(M, N, K, a_trans, b_trans):
+    """Warp-specialised TMA + tcgen05 kernel (operands rounded to tf32 by the TMA unit), all operand layouts, ragged
+    M / N / K edges, multi-tile M and N, more K chunks than ring slots."""
+    for relu in (False, True):
+        got, ref = run_gemm(1, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=relu and a_trans == 0, align4=True,
+                            want_kernel=2)
+        assert rel_err(got, ref) <= 1.5e-3, rel_err(got, ref)
