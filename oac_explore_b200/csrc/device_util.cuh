@@ -7,8 +7,6 @@ namespace oac {
 
 constexpr int GLUE_WARPS = 8;
 constexpr int GLUE_THREADS = GLUE_WARPS * 32;
-constexpr int GLUE_G = 4;                           // warps cooperating on one sample
-constexpr int GLUE_SPC = GLUE_WARPS / GLUE_G;       // samples per CTA
 constexpr float LOG_SIG_MAX_F = 2.0f;     // trainer/policies.py:10
 constexpr float LOG_SIG_MIN_F = -20.0f;   // trainer/policies.py:11
 constexpr float TANH_EPS_F = 1e-6f;       // trainer/policies.py:127

@@ -26,6 +26,14 @@ __device__ __forceinline__ void stage_contig(float* dst, const float* __restrict
     }
 }
 
+// Row groups: G warps cooperate on one row and synchronise through shared memory.  G = 4 spreads a single seed's
+// 256..512 rows over enough CTAs (latency); G = 1 makes every warp self-contained (no block barriers inside the
+// row loop), which is what the many-seed launches want.
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    if (G == 1) __syncwarp(); else __syncthreads();
+}
+
 struct PolicyHeadTask {
     Ref h2;             // [rows, H] last hidden activation
     Ref w, b;           // heads [2A, H] (mean rows then log_std rows), [2A]
@@ -34,6 +42,8 @@ struct PolicyHeadTask {
     int dst_block[2];   // X row block (units of B rows) receiving tanh actions, per B-row block
     int eps_slot[2];    // io eps slot per block
     Ref save;           // [rows, 4, A]: action, std, raw log_std, eps  (for the backward glue)
+    Ref head_in;        // PolicyHeadParams::head_from_gemm: [rows, head_ld] head outputs (mean | raw log_std) of a GEMM stage
+    int head_ld;
 };
 
 struct AlphaUpdate {
@@ -55,39 +65,55 @@ struct PolicyHeadParams {
     int deterministic, use_external_eps;
     unsigned long long rng_seed;
     int n_opt_counters;      // counters CNT_OPT0 .. CNT_OPT0+n-1 are bumped once per step here
+    int iters;               // row groups (of GLUE_SPC rows) per CTA
+    int head_from_gemm;      // 1: the head layer ran as a tensor-core GEMM stage; this kernel only samples
 };
 
 // Fused head layer + sampling: the [2A, H] head weights are staged in shared memory once per CTA; GLUE_G warps
 // share one row (each keeps the hidden row in registers and reduces every GLUE_G-th pair of dot products with
 // shuffles), then one of them runs the per-action-dim sampling math.  dyn smem: (2A*H + 2A + SPC*2A) floats.
+template <int G>
 __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
+    constexpr int SPC = GLUE_WARPS / G;                    // rows per group (G warps share a row)
     extern __shared__ __align__(16) float s_ph[];
     pdl_prologue();
     const PolicyHeadTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = warp / GLUE_G, g = warp % GLUE_G;
-    const int row = blockIdx.x * GLUE_SPC + sl;
+    const int sl = warp / G, g = warp % G;
     const int A = p.A, B = p.B, H = p.H;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
     int32_t* cnt = p.as.counters + seed * p.as.n_counters;
     const int step = cnt[CNT_TRAIN_STEPS];
 
+    const bool from_gemm = p.head_from_gemm != 0;           // dyn smem is then only SPC * 2A floats
     float* Ws = s_ph;
-    float* bs = s_ph + 2 * A * H;
-    float* outv = bs + 2 * A + sl * 2 * A;                  // this row's head outputs (mean | raw log_std)
-    stage_contig(Ws, resolve(p.as, T.w, seed), 2 * A * H);
-    stage_contig(bs, resolve(p.as, T.b, seed), 2 * A);
-    float hreg[GLUE_MAX_HR];
-    if (row < T.rows) {
-        const float* __restrict__ h = resolve(p.as, T.h2, seed) + (long long)row * H;
-#pragma unroll
-        for (int c = 0; c < GLUE_MAX_HR; ++c) hreg[c] = (lane + 32 * c < H) ? __ldg(h + lane + 32 * c) : 0.f;
+    float* bs = s_ph + (from_gemm ? 0 : 2 * A * H);
+    float* outv = bs + (from_gemm ? 0 : 2 * A) + sl * 2 * A;  // this row's head outputs (mean | raw log_std)
+    if (!from_gemm) {
+        stage_contig(Ws, resolve(p.as, T.w, seed), 2 * A * H);
+        stage_contig(bs, resolve(p.as, T.b, seed), 2 * A);
     }
+    const float* __restrict__ h2 = resolve(p.as, T.h2, seed);
+    const float* __restrict__ head_in = from_gemm ? resolve(p.as, T.head_in, seed) : nullptr;
+    // the staged head weights serve p.iters row groups (many-seed launches: 16 -> 1/16 of the staging traffic)
+    float hreg[GLUE_MAX_HR];
+    auto load_row = [&](int row) {
+        if (row < T.rows && !from_gemm) {
+            const float* __restrict__ h = h2 + (long long)row * H;
+#pragma unroll
+            for (int c = 0; c < GLUE_MAX_HR; ++c) hreg[c] = (lane + 32 * c < H) ? __ldg(h + lane + 32 * c) : 0.f;
+        }
+    };
+    load_row(blockIdx.x * p.iters * SPC + sl);
     cp_async_wait_all();
     __syncthreads();
-    if (row < T.rows) {
-        for (int j = g; j < A; j += GLUE_G) {
+    for (int it = 0; it < p.iters; ++it) {
+    const int row = (blockIdx.x * p.iters + it) * SPC + sl;
+    if (row < T.rows && from_gemm) {
+        if (g == 0) for (int j = lane; j < 2 * A; j += 32) outv[j] = __ldg(head_in + (long long)row * T.head_ld + j);
+    } else if (row < T.rows) {
+        for (int j = g; j < A; j += G) {
             const float* wm = Ws + j * H;
             const float* ws = Ws + (A + j) * H;
             float sm = 0.f, ss = 0.f;
@@ -100,7 +126,8 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
             if (lane == 0) { outv[j] = sm + bs[j]; outv[A + j] = ss + bs[A + j]; }
         }
     }
-    __syncthreads();
+    if (it + 1 < p.iters) load_row(row + SPC);        // next group's hidden row flies during the sampling math
+    group_sync<G>();
     if (row < T.rows && g == 0) {
         float* save = resolve(p.as, T.save, seed) + (long long)row * 4 * A;
         const int blk = row / B, b = row % B;
@@ -136,6 +163,8 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
         }
         lp_acc = warp_sum(lp_acc);
         if (lane == 0) io[p.off_log_pi + T.out_row0 + row] = lp_acc;
+    }
+    if (it + 1 < p.iters) group_sync<G>();                 // outv is rewritten by the next group
     }
 
     // ---- last CTA of this seed: bump step counters, entropy-temperature Adam step ----
@@ -223,24 +252,64 @@ struct CriticHeadParams {
     int n_nets;           // P-OAC / G-OAC: critic nets per group (1 shared, P or 2 separate)
     int share_layers, counts;
     float discount, reward_scale, standard_bound, std_init;
+    int iters;            // sample groups (of GLUE_SPC samples) per CTA
 };
+
+// Head dot products of one sample: the loads of up to four (critic, head) pairs are issued before the first
+// reduction, so a warp keeps 4 x 2 x HR loads in flight (the kernel is bound by the latency of the h2 rows).
+template <int HR, int G>
+__device__ __forceinline__ void head_dots(const CriticHeadParams& p, int seed, int b, int g, int lane, int npairs,
+                                          const short* pair_src, const short* pair_hd, float* vals) {
+    constexpr int PB = 32 / HR;                       // 64 load registers either way
+    const int H = p.H;
+    for (int base = g; base < npairs; base += G * PB) {
+        float hv[PB][HR], wv[PB][HR];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int pi = base + u * G;
+            if (pi < npairs) {
+                const HeadSrc& S = p.src[pair_src[pi]];
+                const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
+                const float* __restrict__ w = resolve(p.as, S.w3, seed) + (long long)pair_hd[pi] * H;
+#pragma unroll
+                for (int c = 0; c < HR; ++c) {
+                    const int k = lane + 32 * c;
+                    hv[u][c] = k < H ? __ldg(h + k) : 0.f;
+                    wv[u][c] = k < H ? __ldg(w + k) : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int pi = base + u * G;
+            if (pi < npairs) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < HR; ++c) acc = fmaf(hv[u][c], wv[u][c], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) vals[pi] = acc + __ldg(resolve(p.as, p.src[pair_src[pi]].b3, seed) + pair_hd[pi]);
+            }
+        }
+    }
+}
 
 // Fused critic head layer + targets / loss gradients + first backward step.  GLUE_G warps share one sample:
 // the (critic, head) dot products are dealt round-robin to them (hidden row in registers, shuffle reduction),
 // one lane then evaluates the algorithm's targets and dLoss/dq, and all GLUE_G warps emit
 // dh2 = (dq W3) * relu'(h2) for the critics whose backward starts here.
-__global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+template <int G>
+__global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+    constexpr int SPC = GLUE_WARPS / G;
     pdl_prologue();
     const CriticHeadParams& p = *pp;
-    __shared__ float s_vals[GLUE_SPC][MAX_VALS];
-    __shared__ float s_dq[GLUE_SPC][MAX_VALS];
+    __shared__ float s_vals[SPC][MAX_VALS];
+    __shared__ float s_dq[SPC][MAX_VALS];
     __shared__ int s_goff[MAX_HEAD_SRC];
     __shared__ short s_pair_src[MAX_VALS], s_pair_hd[MAX_VALS];
     __shared__ int s_npairs;
     const int seed = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = warp / GLUE_G, g = warp % GLUE_G;
-    const int b = blockIdx.x * GLUE_SPC + sl;
+    const int sl = warp / G, g = warp % G;
     const int B = p.B, H = p.H;
     if (threadIdx.x == 0) {
         int n = 0;
@@ -251,6 +320,9 @@ __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticH
         s_npairs = n;
     }
     __syncthreads();
+    for (int it = 0; it < p.iters; ++it) {                 // p.iters sample groups per CTA (many-seed launches)
+    if (it > 0) group_sync<G>();                           // s_vals / s_dq are rewritten
+    const int b = (blockIdx.x * p.iters + it) * SPC + sl;
     const bool live = b < B;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
     float* vals = s_vals[sl];
@@ -263,22 +335,10 @@ __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticH
         cnt_pre = p.counts ? io[p.off_counts + b] : 0.f;
     }
     if (live) {
-        for (int pi = g; pi < s_npairs; pi += GLUE_G) {
-            const HeadSrc& S = p.src[s_pair_src[pi]];
-            const int hd = s_pair_hd[pi];
-            const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
-            const float* __restrict__ w = resolve(p.as, S.w3, seed) + (long long)hd * H;
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < GLUE_MAX_HR; ++c) {
-                const int k = lane + 32 * c;
-                if (k < H) acc = fmaf(__ldg(h + k), __ldg(w + k), acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) vals[pi] = acc + __ldg(resolve(p.as, S.b3, seed) + hd);
-        }
+        if (H <= 256) head_dots<8, G>(p, seed, b, g, lane, s_npairs, s_pair_src, s_pair_hd, vals);
+        else head_dots<GLUE_MAX_HR, G>(p, seed, b, g, lane, s_npairs, s_pair_src, s_pair_hd, vals);
     }
-    __syncthreads();
+    group_sync<G>();
     // every dq goes to global (GEMM operand of the weight-gradient stage) and to the sample's shared copy
     auto put = [&](int s, int i, float v) {
         resolve(p.as, p.src[s].dq, seed)[(long long)b * p.src[s].dq_ld + i] = v;
@@ -380,10 +440,9 @@ __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticH
         else { put(0, 0, g0); put(1, 0, g1); put(2, 0, -invB); put(3, 0, 0.f); }
     }
     }   // lane 0
-    __syncthreads();
-    if (!live) return;
+    group_sync<G>();
     // ---- dh2 = (dq W3) * relu'(h2) for the critics whose backward starts with the current weights ----
-    for (int s = 0; s < p.n_src; ++s) {
+    for (int s = 0; s < p.n_src && live; ++s) {
         const HeadSrc& S = p.src[s];
         if (!S.write_dh2) continue;
         const float* __restrict__ h = resolve(p.as, S.h2, seed) + (long long)(S.row0 + b) * H;
@@ -391,13 +450,14 @@ __global__ void __launch_bounds__(GLUE_THREADS) critic_head_kernel(const CriticH
         float* __restrict__ out = resolve(p.as, S.dh2, seed) + (long long)b * H;
         const int g0 = s_goff[s];
 #pragma unroll 4
-        for (int k = g * 32 + lane; k < H; k += 32 * GLUE_G) {
+        for (int k = g * 32 + lane; k < H; k += 32 * G) {
             const float hv = __ldg(h + k);
             float acc = 0.f;
             for (int hd = 0; hd < S.n_heads; ++hd) acc = fmaf(dqv[g0 + hd], __ldg(w + (long long)hd * H + k), acc);
             out[k] = hv > 0.f ? acc : 0.f;
         }
     }
+    }   // it
 }
 
 // =====================================================================================
@@ -417,6 +477,8 @@ struct PolicyGradTask {
     Ref h2;           // policy second hidden activation [*, H]; rows of this batch start at h2_row0
     int h2_row0;
     Ref dhp2;         // out: [B, H] = (dhead Wh) * relu'(h2)
+    Ref da[20];       // PolicyGradParams::da_from_gemm: per critic [B, da_ld] = dh1 W0[:, O:O+A] from a GEMM stage
+    int da_ld;
 };
 
 struct PolicyGradParams {
@@ -424,95 +486,131 @@ struct PolicyGradParams {
     ArenaSet as;
     long long off_scalars;
     int O, A, H, B;
+    int iters;        // sample groups (of GLUE_SPC samples) per CTA
+    int da_from_gemm; // 1: dQ/da and the policy's dh2 run as tensor-core GEMM stages; this kernel is the chain rule only
 };
 
 // Fused: dLoss/d(action) through every critic's first layer (only the A action columns of fc0.weight are
 // needed, not the full 393-wide dX the reference's autograd computes), the TanhNormal / entropy chain rule
 // to the policy head outputs, and the policy's first backward step dh2 = (dhead Wh) * relu'(h2).
 // GLUE_G warps share one sample.  dyn smem: Wa [H*AS] | Wh [2A*H] | ga [SPC][A] | dhead [SPC][2A]  (AS = A | 1)
+template <int G>
 __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
+    constexpr int SPC = GLUE_WARPS / G;
     extern __shared__ __align__(16) float s_pg[];
     pdl_prologue();
     const PolicyGradTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = warp / GLUE_G, g = warp % GLUE_G;
-    const int b = blockIdx.x * GLUE_SPC + sl;
+    const int sl = warp / G, g = warp % G;
     const int A = p.A, H = p.H, B = p.B, O = p.O;
     const int AS = A | 1;                                   // odd stride: conflict-free column reads
-    const bool live = b < B;
+    const int iters = p.iters;                              // sample groups per CTA: the staged weights serve all of them
+    const int b0 = blockIdx.x * iters * SPC + sl;      // this warp's sample in group it: b0 + it*SPC
+    const bool from_gemm = p.da_from_gemm != 0;             // dyn smem is then only the sga / sdh rows
     float* Wa = s_pg;
-    float* Whs = Wa + H * AS;
-    float* sga = Whs + 2 * A * H + sl * A;
-    float* sdh = Whs + 2 * A * H + GLUE_SPC * A + sl * 2 * A;
+    float* Whs = Wa + (from_gemm ? 0 : H * AS);
+    float* sga_all = Whs + (from_gemm ? 0 : 2 * A * H);     // [iters][SPC][A]
+    float* sdh_all = sga_all + iters * SPC * A;        // [iters][SPC][2A]
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
-    stage_contig(Whs, resolve(p.as, T.wh, seed), 2 * A * H);       // consumed in the last phase
-    for (int s = 0; s < T.n_src; ++s) {
+    if (from_gemm) {
+        for (int it = 0; it < iters; ++it) {
+            const int b = b0 + it * SPC;
+            if (b < B && g == 0) {
+                float* sga = sga_all + (it * SPC + sl) * A;
+                for (int j = lane; j < A; j += 32) {
+                    float acc = 0.f;
+                    for (int s = 0; s < T.n_src; ++s) acc += __ldg(resolve(p.as, T.da[s], seed) + (long long)b * T.da_ld + j);
+                    sga[j] = acc;
+                }
+            }
+        }
+    } else stage_contig(Whs, resolve(p.as, T.wh, seed), 2 * A * H);       // consumed in the last phase
+    for (int s = 0; s < T.n_src && !from_gemm; ++s) {
         const float* __restrict__ w1 = resolve(p.as, T.w1[s], seed);
         const int ld = T.ld[s];
         __syncthreads();
         // action columns of fc0.weight: row n -> Wa[n*AS + j]; one warp per row, lanes over j (no division)
         for (int n = warp; n < H; n += GLUE_WARPS)
             for (int j = lane; j < A; j += 32) cp_async4(Wa + n * AS + j, w1 + (long long)n * ld + O + j);
+        const float* __restrict__ dh_base = resolve(p.as, T.dh1[s], seed);
         float dreg[GLUE_MAX_HR];
-        if (live) {
-            const float* __restrict__ dh = resolve(p.as, T.dh1[s], seed) + (long long)b * H;
+        auto load_row = [&](int b) {
+            if (b < B) {
+                const float* __restrict__ dh = dh_base + (long long)b * H;
 #pragma unroll
-            for (int c = 0; c < GLUE_MAX_HR; ++c) dreg[c] = (lane + 32 * c < H) ? __ldg(dh + lane + 32 * c) : 0.f;
-        }
+                for (int c = 0; c < GLUE_MAX_HR; ++c) dreg[c] = (lane + 32 * c < H) ? __ldg(dh + lane + 32 * c) : 0.f;
+            }
+        };
+        load_row(b0);
         cp_async_wait_all();
         __syncthreads();
-        if (live) {
-            for (int j = g; j < A; j += GLUE_G) {
-                float acc = 0.f;
+        for (int it = 0; it < iters; ++it) {
+            const int b = b0 + it * SPC;
+            float* sga = sga_all + (it * SPC + sl) * A;
+            if (b < B) {
+                for (int j = g; j < A; j += G) {
+                    float acc = 0.f;
 #pragma unroll
-                for (int c = 0; c < GLUE_MAX_HR; ++c) {
-                    const int n = lane + 32 * c;
-                    if (n < H) acc = fmaf(dreg[c], Wa[n * AS + j], acc);
+                    for (int c = 0; c < GLUE_MAX_HR; ++c) {
+                        const int n = lane + 32 * c;
+                        if (n < H) acc = fmaf(dreg[c], Wa[n * AS + j], acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) sga[j] = (s == 0 ? 0.f : sga[j]) + acc;  // column j belongs to warp g only
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) sga[j] = (s == 0 ? 0.f : sga[j]) + acc;      // column j belongs to warp g only
             }
+            if (it + 1 < iters) load_row(b + SPC);
         }
     }
     __syncthreads();
-    if (live && g == 0) {
-        const float alpha = io[p.off_scalars + SC_ALPHA];
-        const float invB = 1.0f / (float)B;
-        const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
-        float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * T.dhead_ld;
-        for (int j = lane; j < A; j += 32) {
-            const float a = save[0 * A + j];
-            const float one_m_a2 = 1.f - a * a;
-            const float gaj = sga[j];
-            float dmean, draw;
-            if (T.entropy) {
-                const float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
-                const float u = one_m_a2 + TANH_EPS_F;
-                // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
-                dmean = alpha * invB * (2.f * a * one_m_a2 / u) + gaj * one_m_a2;
-                const float dstd = dmean * eps - alpha * invB / std;
-                const bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
-                draw = inside ? dstd * std : 0.f;
-            } else {
-                dmean = gaj * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
-                draw = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        const int b = b0 + it * SPC;
+        if (b < B && g == 0) {
+            const float* sga = sga_all + (it * SPC + sl) * A;
+            float* sdh = sdh_all + (it * SPC + sl) * 2 * A;
+            const float alpha = io[p.off_scalars + SC_ALPHA];
+            const float invB = 1.0f / (float)B;
+            const float* save = resolve(p.as, T.save, seed) + (long long)(T.save_row0 + b) * 4 * A;
+            float* dhead = resolve(p.as, T.dhead, seed) + (long long)b * T.dhead_ld;
+            for (int j = lane; j < A; j += 32) {
+                const float a = save[0 * A + j];
+                const float one_m_a2 = 1.f - a * a;
+                const float gaj = sga[j];
+                float dmean, draw;
+                if (T.entropy) {
+                    const float std = save[1 * A + j], raw = save[2 * A + j], eps = save[3 * A + j];
+                    const float u = one_m_a2 + TANH_EPS_F;
+                    // dL/dz: alpha/B * d(-log(1-a^2+eps))/dz  +  dL/da * (1-a^2)      
+                    dmean = alpha * invB * (2.f * a * one_m_a2 / u) + gaj * one_m_a2;
+                    const float dstd = dmean * eps - alpha * invB / std;
+                    const bool inside = (raw >= LOG_SIG_MIN_F) && (raw <= LOG_SIG_MAX_F);
+                    draw = inside ? dstd * std : 0.f;
+                } else {
+                    dmean = gaj * one_m_a2;    // a = tanh(mean); log_std head receives no gradient
+                    draw = 0.f;
+                }
+                dhead[j] = dmean; dhead[A + j] = draw;
+                sdh[j] = dmean; sdh[A + j] = draw;
             }
-            dhead[j] = dmean; dhead[A + j] = draw;
-            sdh[j] = dmean; sdh[A + j] = draw;
         }
     }
+    if (from_gemm) return;                                  // dh2 is a GEMM stage of its own
     __syncthreads();
-    if (!live) return;
     // ---- policy backward, first step: dh2 = (dhead Wh) * relu'(h2) ----
-    const float* __restrict__ hp2 = resolve(p.as, T.h2, seed) + (long long)(T.h2_row0 + b) * H;
-    float* __restrict__ out = resolve(p.as, T.dhp2, seed) + (long long)b * H;
+    for (int it = 0; it < iters; ++it) {
+        const int b = b0 + it * SPC;
+        if (b >= B) break;
+        const float* sdh = sdh_all + (it * SPC + sl) * 2 * A;
+        const float* __restrict__ hp2 = resolve(p.as, T.h2, seed) + (long long)(T.h2_row0 + b) * H;
+        float* __restrict__ out = resolve(p.as, T.dhp2, seed) + (long long)b * H;
 #pragma unroll 2
-    for (int n = g * 32 + lane; n < H; n += 32 * GLUE_G) {
-        const float hv = __ldg(hp2 + n);
-        float acc = 0.f;
-        for (int j = 0; j < 2 * A; ++j) acc = fmaf(sdh[j], Whs[j * H + n], acc);
-        out[n] = hv > 0.f ? acc : 0.f;
+        for (int n = g * 32 + lane; n < H; n += 32 * G) {
+            const float hv = __ldg(hp2 + n);
+            float acc = 0.f;
+            for (int j = 0; j < 2 * A; ++j) acc = fmaf(sdh[j], Whs[j * H + n], acc);
+            out[n] = hv > 0.f ? acc : 0.f;
+        }
     }
 }
 

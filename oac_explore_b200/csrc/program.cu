@@ -60,7 +60,7 @@ static int validate(const OacConfig& c) {
         return set_error(OAC_E_INVALID, "dims must be positive");
     if (c.act_dim > 128) return set_error(OAC_E_UNSUPPORTED, "act_dim > 128");
     if (c.hidden > 512) return set_error(OAC_E_UNSUPPORTED, "hidden > 512 (glue kernels keep a hidden row in registers)");
-    if ((size_t)c.hidden * (c.act_dim | 1) + (size_t)2 * c.act_dim * c.hidden + 16 * c.act_dim > 50000)
+    if ((size_t)c.hidden * (c.act_dim | 1) + (size_t)2 * c.act_dim * c.hidden + 16 * GLUE_WARPS * 3 * c.act_dim > 50000)
         return set_error(OAC_E_UNSUPPORTED, "hidden*act_dim too large for the fused glue kernels' shared memory");
     if (c.algo == OAC_ALGO_POAC && (c.n_particles < 2 || c.n_particles > 16))
         return set_error(OAC_E_UNSUPPORTED, "P-OAC needs 2 <= n_particles <= 16");
@@ -139,6 +139,8 @@ struct Stage {
     void* ws_tmaps = nullptr;
     int max_tiles = 0;
     int max_rows = 0;
+    int glue_iters = 1;         // glue kernels: sample groups per CTA (> 1 when many seeds share a launch)
+    int glue_g = 4;             // ... and warps cooperating on one sample
     const char* name = "";
 };
 
@@ -169,8 +171,13 @@ struct Builder {
     const OacConfig& c;
     const OacLayout& L;
     int O, A, H, B;
+    // Many seeds on the tensor-core path: the head layers, dQ/da and the policy's first backward step run as
+    // GEMM stages (the fused glue kernels are instruction-bound there: profiles/r01b_glue64); a single seed keeps
+    // them fused into the glue kernels (fewer launches: latency).
+    bool tensor_glue;
     explicit Builder(OacTrainer& tr) : t(tr), c(tr.cfg), L(tr.lay) {
         O = c.obs_dim; A = c.act_dim; H = c.hidden; B = c.batch;
+        tensor_glue = c.gemm_path == OAC_GEMM_TF32 && (long long)c.n_seeds * c.batch >= 2048;
     }
     Ref work(long long n) {
         Ref r{AR_WORK, t.work_cursor};
@@ -231,7 +238,7 @@ struct Builder {
     PolAct alloc_pol(int nblk) {
         PolAct a; a.rows = nblk * B;
         a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
-        a.head = work((long long)a.rows * 2 * A);
+        a.head = work((long long)a.rows * pad4(2 * A));
         a.save = work((long long)a.rows * 4 * A);
         return a;
     }
@@ -242,12 +249,12 @@ struct Builder {
         a.q = work((long long)a.rows * heads);
         a.dq = work((long long)a.rows * pad4(heads));         // leading dimension pad4(heads): TMA needs 16-byte row strides
         a.dh2 = work((long long)a.rows * H); a.dh1 = work((long long)a.rows * H);
-        a.da = work((long long)a.rows * A);
+        a.da = work((long long)a.rows * pad4(A));
         return a;
     }
     void pol_l3(Stage& s, int ni, const PolAct& a) {
         const OacNetLayout& n = net(ni);
-        fwd(s, a.h2, H, a.rows, H, P(n.off_w2), H, P(n.off_b2), 2 * A, a.head, 2 * A, false);
+        fwd(s, a.h2, H, a.rows, H, P(n.off_w2), H, P(n.off_b2), 2 * A, a.head, pad4(2 * A), false);
     }
     void crit_l3(Stage& s, int ni, const CritAct& a) {
         const OacNetLayout& n = net(ni);
@@ -257,7 +264,7 @@ struct Builder {
     void crit_da(Stage& s, int ni, const CritAct& a, int row0) {
         const OacNetLayout& n = net(ni);
         dx(s, Ref{a.dh1.arena, a.dh1.off + (long long)row0 * H}, H, B, H, P(n.off_w0 + O), n.in_ld, A,
-           Ref{a.da.arena, a.da.off + (long long)row0 * A}, A, Ref{0, 0}, 0, false);
+           Ref{a.da.arena, a.da.off + (long long)row0 * pad4(A)}, pad4(A), Ref{0, 0}, 0, false);
     }
     void pol_l1(Stage& s, int ni, int blk0, const PolAct& a) {
         const OacNetLayout& n = net(ni);
@@ -332,14 +339,18 @@ struct Builder {
         dw(s, g.dhead, pad4(2 * A), Ref{a.h2.arena, a.h2.off + ro}, H, B, 2 * A, H, n.off_w2, H, n.off_b2, -1, -1, lr, counter, 1);
     }
     // policy-loss gradient task: critics (dh1 rows, fc0 weights) -> dhead, and the policy's own dh2
+    // crit_da_refs (tensor_glue): per critic, where the pi_da GEMM stage left dh1 W0[:, O:O+A] for these rows
     PolicyGradTask pg_task(const std::vector<std::pair<int, Ref>>& crit_dh1, int pol, const PolAct& a, int row0,
-                           const PolGrad& g, bool entropy) {
+                           const PolGrad& g, bool entropy, const std::vector<Ref>& crit_da_refs = std::vector<Ref>()) {
         PolicyGradTask t_; memset(&t_, 0, sizeof(t_));
         int i = 0;
         for (auto& c_ : crit_dh1) {
             const OacNetLayout& qn = net(c_.first);
-            t_.dh1[i] = c_.second; t_.w1[i] = P(qn.off_w0); t_.ld[i] = qn.in_ld; ++i;
+            t_.dh1[i] = c_.second; t_.w1[i] = P(qn.off_w0); t_.ld[i] = qn.in_ld;
+            if (i < (int)crit_da_refs.size()) t_.da[i] = crit_da_refs[i];
+            ++i;
         }
+        t_.da_ld = pad4(A);
         t_.n_src = i;
         t_.save = a.save; t_.save_row0 = row0; t_.dhead = g.dhead; t_.dhead_ld = pad4(2 * A); t_.entropy = entropy ? 1 : 0;
         t_.wh = P(net(pol).off_w2); t_.h2 = a.h2; t_.h2_row0 = row0; t_.dhp2 = g.dh2;
@@ -352,6 +363,7 @@ struct Builder {
         p.h2 = a.h2; p.w = P(n.off_w2); p.b = P(n.off_b2); p.rows = a.rows; p.out_row0 = out_row0;
         p.dst_block[0] = dst0; p.dst_block[1] = dst1; p.eps_slot[0] = eps0; p.eps_slot[1] = eps1;
         p.save = a.save;
+        p.head_in = a.head; p.head_ld = pad4(2 * A);
         return p;
     }
     void fill_php(Stage& s, int alpha_task, int alpha_block, int alpha_counter) {
@@ -366,6 +378,7 @@ struct Builder {
         const OacNetLayout& la = net(t.ids.log_alpha);
         p.alpha.log_alpha = P(la.off_w0); p.alpha.adam_off = la.off_w0;
         p.alpha.lr = c.policy_lr; p.alpha.target_entropy = c.target_entropy; p.alpha.counter = alpha_counter;
+        p.head_from_gemm = tensor_glue ? 1 : 0;
     }
     void fill_chp(Stage& s, int mode, int n_nets) {
         CriticHeadParams& p = s.chp;
@@ -382,6 +395,7 @@ struct Builder {
         PolicyGradParams& p = s.pgp;
         memset(&p, 0, sizeof(p));
         p.off_scalars = L.off_scalars; p.O = O; p.A = A; p.H = H; p.B = B;
+        p.da_from_gemm = tensor_glue ? 1 : 0;
     }
 
     // X blocks: 0 [obs|a_tp] (G-OAC), 1 [obs|a_pi], 2 [obs|actions], 3 [next_obs|a_next]
@@ -401,6 +415,7 @@ void Builder::build_sac() {
     const bool mode_b = c.stale_graph_mode == 1;
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
@@ -420,9 +435,11 @@ void Builder::build_sac() {
     { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); crit_dh1(s, q1, ca1, B); crit_dh1(s, q2, ca2, B);
       if (mode_b) { crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); } }
     auto policy_grad_stage = [&]() {
-        Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad+da+dh2");
-        s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic));
+        if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
+        Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
+        s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic, {ca1.da, ca2.da}));
         fill_pgp(s);
+        if (tensor_glue) { Stage& s2 = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s2, pol, pa, 0, pg); }
     };
     // NB mode B reads fc0.weight's action columns too: its policy_grad stage runs before the critic Adam
     if (mode_b) policy_grad_stage();
@@ -449,6 +466,7 @@ void Builder::build_poac() {
     PolGrad pg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     // eps slots are named by meaning (0: obs draw, 1: next_obs draw); the reference draws the
     // next_obs noise FIRST here (:193 then :271) -- the host wrapper maps call order to slots
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
@@ -473,10 +491,13 @@ void Builder::build_poac() {
       for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], pa_q[i], 0); s.chp.src[i].write_dh2 = 1; }
       s.chp.n_src = n; fill_chp(s, CM_POAC_PI, n); }
     { Stage& s = add_stage(ST_GEMM, "pi_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], pa_q[i], 0); }
-    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad+da+dh2");
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "pi_da"); for (int i = 0; i < n; ++i) crit_da(s, t.ids.qf[i], pa_q[i], 0); }
+    { Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
       std::vector<std::pair<int, Ref>> cr;
-      for (int i = 0; i < n; ++i) cr.push_back({t.ids.qf[i], pa_q[i].dh1});
-      s.pg.push_back(pg_task(cr, pol, pa, 0, pg, !c.deterministic)); fill_pgp(s); }
+      std::vector<Ref> das;
+      for (int i = 0; i < n; ++i) { cr.push_back({t.ids.qf[i], pa_q[i].dh1}); das.push_back(pa_q[i].da); }
+      s.pg.push_back(pg_task(cr, pol, pa, 0, pg, !c.deterministic, das)); fill_pgp(s); }
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
 }
@@ -494,6 +515,7 @@ void Builder::build_goac() {
     PolGrad pg = alloc_polgrad(), tpg = alloc_polgrad();
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); pol_l1(s, tpol, 2, tpa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); pol_l2(s, tpol, tpa); }
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); pol_l3(s, tpol, tpa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1));
       s.ph.push_back(ph_task(tpol, tpa, 2 * B, 0, 0, 0, 0));
@@ -521,15 +543,21 @@ void Builder::build_goac() {
       s.chp.n_src = 2 * n; fill_chp(s, CM_GOAC_PI, n); }
     { Stage& s = add_stage(ST_GEMM, "pi_dh1");
       for (int i = 0; i < n; ++i) { crit_dh1(s, t.ids.qf[i], pq[i], 0); crit_dh1(s, t.ids.qf[i], pq[i], B); } }
-    { Stage& s = add_stage(ST_POLICY_GRAD, "policy_grad+da+dh2");
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "pi_da");
+      for (int i = 0; i < n; ++i) { crit_da(s, t.ids.qf[i], pq[i], 0); crit_da(s, t.ids.qf[i], pq[i], B); } }
+    { Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
       std::vector<std::pair<int, Ref>> cr, crt;
+      std::vector<Ref> das, dast;
       for (int i = 0; i < n; ++i) {
           cr.push_back({t.ids.qf[i], Ref{pq[i].dh1.arena, pq[i].dh1.off + (long long)B * H}});
           crt.push_back({t.ids.qf[i], pq[i].dh1});
+          das.push_back(Ref{pq[i].da.arena, pq[i].da.off + (long long)B * pad4(A)});
+          dast.push_back(pq[i].da);
       }
-      s.pg.push_back(pg_task(cr, pol, pa, 0, pg, false));
-      s.pg.push_back(pg_task(crt, tpol, tpa, 0, tpg, false));
+      s.pg.push_back(pg_task(cr, pol, pa, 0, pg, false, das));
+      s.pg.push_back(pg_task(crt, tpol, tpa, 0, tpg, false, dast));
       fill_pgp(s); }
+    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); pol_dh2(s, tpol, tpa, 0, tpg); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); pol_dh1(s, tpol, tpa, 0, tpg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam");
       pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); pol_adam(s, tpol, tpa, 0, 2, tpg, c.policy_lr, 1); }
@@ -665,6 +693,17 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     return 0;
 }
 
+// Glue kernels: G warps per row (4: a single seed's few hundred rows still fill the chip; 1: self-contained warps
+// for the many-seed launches) and, since every CTA stages head / action-column weights once, several row groups
+// per CTA when there are enough rows to keep ~4 CTAs on every SM anyway.
+static void glue_plan(Stage& s, long long rows_total, bool stages_weights) {
+    s.glue_g = rows_total >= 4096 ? 1 : 4;
+    const int spc = GLUE_WARPS / s.glue_g;
+    const long long groups = (rows_total + spc - 1) / spc;
+    const long long want = groups / (4ll * sm_count());
+    s.glue_iters = stages_weights ? (int)std::max<long long>(1, std::min<long long>(16, want)) : 1;
+}
+
 static int finalize(OacTrainer& t) {
     const int seeds = t.cfg.n_seeds;
     for (Stage& s : t.stages) {
@@ -755,13 +794,17 @@ static int finalize(OacTrainer& t) {
         } else if (s.kind == ST_POLICY_HEAD) {
             s.max_rows = 0;
             for (auto& p : s.ph) s.max_rows = std::max(s.max_rows, p.rows);
+            glue_plan(s, (long long)s.max_rows * s.ph.size() * seeds, !s.php.head_from_gemm);
             if (int e = upload(t, s.ph.data(), s.ph.size(), &s.dev)) return e;
             s.php.tasks = (const PolicyHeadTask*)s.dev;
             s.php.as = t.as; s.php.hyper = t.hyper;
         } else if (s.kind == ST_CRITIC_HEAD) {
+            glue_plan(s, (long long)t.cfg.batch * seeds, false);
+            s.chp.iters = s.glue_iters;
             s.chp.as = t.as;
             if (int e = upload(t, &s.chp, 1, &s.dev)) return e;
         } else if (s.kind == ST_POLICY_GRAD) {
+            glue_plan(s, (long long)t.cfg.batch * s.pg.size() * seeds, !s.pgp.da_from_gemm);
             if (int e = upload(t, s.pg.data(), s.pg.size(), &s.dev)) return e;
             s.pgp.tasks = (const PolicyGradTask*)s.dev;
             s.pgp.as = t.as;
@@ -831,18 +874,26 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
                 default: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, true, true>, grid, dim3(256), s.smem, st, sp); break;
             }
         } else if (s.kind == ST_POLICY_HEAD) {
-            PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps;
-            dim3 grid((s.max_rows + GLUE_SPC - 1) / GLUE_SPC, (unsigned)s.ph.size(), seeds);
-            const size_t smem = sizeof(float) * ((size_t)2 * t.cfg.act_dim * t.cfg.hidden + 2 * t.cfg.act_dim * (1 + GLUE_SPC));
-            launch_pdl(policy_head_kernel, grid, dim3(GLUE_THREADS), smem, st, p);
+            PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps; p.iters = s.glue_iters;
+            const int spc = GLUE_WARPS / s.glue_g, per_cta = spc * s.glue_iters;
+            dim3 grid((s.max_rows + per_cta - 1) / per_cta, (unsigned)s.ph.size(), seeds);
+            const size_t smem = sizeof(float) * (p.head_from_gemm ? (size_t)2 * t.cfg.act_dim * spc
+                                                : (size_t)2 * t.cfg.act_dim * t.cfg.hidden + 2 * t.cfg.act_dim * (1 + spc));
+            if (s.glue_g == 1) launch_pdl(policy_head_kernel<1>, grid, dim3(GLUE_THREADS), smem, st, p);
+            else launch_pdl(policy_head_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
         } else if (s.kind == ST_CRITIC_HEAD) {
-            dim3 grid((t.cfg.batch + GLUE_SPC - 1) / GLUE_SPC, seeds, 1);
-            launch_pdl(critic_head_kernel, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
+            const int per_cta = (GLUE_WARPS / s.glue_g) * s.glue_iters;       // iters is part of the uploaded CriticHeadParams
+            dim3 grid((t.cfg.batch + per_cta - 1) / per_cta, seeds, 1);
+            if (s.glue_g == 1) launch_pdl(critic_head_kernel<1>, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
+            else launch_pdl(critic_head_kernel<4>, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
         } else {
-            dim3 grid((t.cfg.batch + GLUE_SPC - 1) / GLUE_SPC, (unsigned)s.pg.size(), seeds);
+            PolicyGradParams p = s.pgp; p.iters = s.glue_iters;
+            const int per_cta = (GLUE_WARPS / s.glue_g) * s.glue_iters;
+            dim3 grid((t.cfg.batch + per_cta - 1) / per_cta, (unsigned)s.pg.size(), seeds);
             const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
-            const size_t smem = sizeof(float) * ((size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_ + GLUE_SPC * 3 * A_);
-            launch_pdl(policy_grad_kernel, grid, dim3(GLUE_THREADS), smem, st, s.pgp);
+            const size_t smem = sizeof(float) * ((p.da_from_gemm ? 0 : (size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_) + (size_t)per_cta * 3 * A_);
+            if (s.glue_g == 1) launch_pdl(policy_grad_kernel<1>, grid, dim3(GLUE_THREADS), smem, st, p);
+            else launch_pdl(policy_grad_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
         }
         OAC_CUDA(cudaGetLastError());
     }
@@ -919,8 +970,10 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_ws((const void*)gemm_ws_kernel<false, false>);
         opt_ws((const void*)gemm_ws_kernel<false, true>);
         opt_ws((const void*)gemm_ws_kernel<true, true>);
-        opt_in((const void*)policy_head_kernel);
-        opt_in((const void*)policy_grad_kernel);
+        opt_in((const void*)policy_head_kernel<1>);
+        opt_in((const void*)policy_head_kernel<4>);
+        opt_in((const void*)policy_grad_kernel<1>);
+        opt_in((const void*)policy_grad_kernel<4>);
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
