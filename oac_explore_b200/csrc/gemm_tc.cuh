@@ -45,6 +45,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
+// same, but a failed probe backs off: single-lane producer / MMA loops would otherwise burn issue slots that the
+// epilogue warps of the same SM sub-partition need (18 % of the instruction stream in profiles/r01b)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(32);
+    }
+    __trap();
+}
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }

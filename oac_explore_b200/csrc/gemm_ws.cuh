@@ -44,6 +44,7 @@ struct WsParams {
     const CUtensorMap* tmaps;     // device, [2 * n_tasks]: A and B operand of every task
     int n_tasks;
     int tiles_per_seed;
+    int n_seeds;
     int total_tiles;              // tiles_per_seed * n_seeds
     int n_slots;                  // operand ring depth
     int slot_bytes;               // WS_A_BYTES + max_bn * 128
@@ -59,6 +60,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {     // p 16-byte aligned, bytes % 16 == 0
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
     uint32_t r[16];
@@ -96,13 +100,20 @@ __device__ __forceinline__ AdamScalars make_adam_scalars_fast(const AdamHyper& h
     s.do_polyak = ((train_steps_done - 1) % (h.target_period > 0 ? h.target_period : 1)) == 0;
     return s;
 }
-// adam_update (gemm_simt.cuh) on register operands: same operation order / roundings
-__device__ __forceinline__ void adam_core(float g, float& p, float& m, float& v, float& tgt, bool has_tgt, const AdamScalars& s) {
-    m = __fadd_rn(__fmul_rn(m, s.beta1), __fmul_rn(s.one_m_beta1, g));
-    v = __fadd_rn(__fmul_rn(v, s.beta2), __fmul_rn(__fmul_rn(s.one_m_beta2, g), g));
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
-    p = __fadd_rn(p, __fmul_rn(-s.step_size, __fdiv_rn(m, denom)));
-    if (has_tgt) tgt = __fadd_rn(__fmul_rn(tgt, s.one_m_tau), __fmul_rn(p, s.tau));
+// Adam (+Polyak) on register operands for the TF32 path.  The weight gradient g already carries ~1e-3 of tf32
+// rounding, so the IEEE-exact divide / square root of adam_update (gemm_simt.cuh: ~40 dependent instructions per
+// element, 40 % of this kernel's instruction stream in profiles/r01b) buy nothing here: MUFU sqrt / reciprocal
+// (2 ulp) and fused multiply-adds instead.  inv_bc2 = 1 / sqrt(1 - beta2^t).
+__device__ __forceinline__ void adam_core(float g, float& p, float& m, float& v, float& tgt, bool has_tgt, const AdamScalars& s,
+                                          float inv_bc2) {
+    m = fmaf(m, s.beta1, s.one_m_beta1 * g);
+    v = fmaf(v, s.beta2, s.one_m_beta2 * g * g);
+    float sq, rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    const float denom = fmaf(sq, inv_bc2, s.eps);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(denom));
+    p = fmaf(-s.step_size * m, rc, p);
+    if (has_tgt) tgt = fmaf(tgt, s.one_m_tau, p * s.tau);
 }
 
 template <bool A_MN, bool B_MN>
@@ -140,8 +151,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
     const uint32_t tmem = s_tmem;
 
     auto decode = [&](int g, int& seed, int& j, int& tm, int& tn) {
-        seed = g / wp.tiles_per_seed;
-        const int r = g - seed * wp.tiles_per_seed;
+        // seed is the FAST index: the CTAs of a round work on the same tile of different seeds, so every round costs
+        // every CTA the same; tasks are sorted by cost, so the ragged last round is made of the cheapest tiles
+        const int r = g / wp.n_seeds;
+        seed = g - r * wp.n_seeds;
         j = 0;
         while (r >= s_tile0[j + 1]) ++j;
         const int t = r - s_tile0[j];
@@ -151,20 +164,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
-            int slot = 0; uint32_t ph = 0;
-            for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x) {
-                int seed, j, tm, tn;
-                decode(g, seed, j, tm, tn);
-                const GemmTask& T = tasks[j];
+        int slot = 0; uint32_t ph = 0;
+        for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x) {
+            int seed, j, tm, tn;
+            decode(g, seed, j, tm, tn);
+            const GemmTask& T = tasks[j];
+            const int bn = T.bn;
+            const int m0 = tm * WS_BM, n0 = tn * bn;
+            if (lane == 0) {
                 const CUtensorMap* ta = wp.tmaps + 2 * j;
                 const CUtensorMap* tb = ta + 1;
-                const int bn = T.bn;
-                const int m0 = tm * WS_BM, n0 = tn * bn;
                 const int nch = (T.K + WS_KC - 1) / WS_KC;
                 const uint32_t bytes = WS_A_BYTES + (uint32_t)bn * (WS_KC * 4);
                 for (int c = 0; c < nch; ++c) {
-                    mbar_wait(&s_empty[slot], ph ^ 1u);
+                    mbar_wait_relaxed(&s_empty[slot], ph ^ 1u);
                     const uint32_t sa = smem_u32(ring + (size_t)slot * wp.slot_bytes), sb = sa + WS_A_BYTES;
                     const uint32_t bar = smem_u32(&s_full[slot]);
                     mbar_expect_tx(bar, bytes);
@@ -178,6 +191,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                     if (++slot == wp.n_slots) { slot = 0; ph ^= 1u; }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
@@ -193,13 +207,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                 const int bn = T.bn, K = T.K;
                 const int nch = (K + WS_KC - 1) / WS_KC;
                 const int buf = tl & 1;
-                mbar_wait(&s_tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+                mbar_wait_relaxed(&s_tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_main = tmem + (uint32_t)(buf * 256), d_bias = d_main + WS_BIAS_COL;
                 const uint32_t idesc = umma_idesc_tf32(WS_BM, bn, A_MN, B_MN);
-                const bool bias_mma = A_MN && B_MN && T.epi == EPI_ADAM && T.has_bias && tn == 0;
+                const bool bias_mma = A_MN && B_MN && (T.epi == EPI_ADAM || T.epi == EPI_GRAD) && T.has_bias && tn == 0;
                 for (int c = 0; c < nch; ++c) {
-                    mbar_wait(&s_full[slot], ph);
+                    mbar_wait_relaxed(&s_full[slot], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(ring + (size_t)slot * wp.slot_bytes), sb = sa + WS_A_BYTES;
                     const int ksteps = (min(WS_KC, K - c * WS_KC) + 7) >> 3;
@@ -231,6 +245,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
         float* __restrict__ m2 = sp.as.base[AR_ADAM_V];
         float* __restrict__ pb0 = sp.as.base[AR_PARAM];
         const int rsub = lane >> 4, c4 = (lane & 15) << 2;
+        // Adam tiles stream 16 B per element of param / moments / target through registers, which caps the bytes in
+        // flight at ~64 KB per SM (one DRAM latency per batch: 3.6 TB/s in profiles/r01c).  Each warp therefore pulls
+        // its NEXT slab towards L2 (cp.async.bulk.prefetch.L2, no registers held) before it starts on the current one,
+        // so the register loads find their lines in L2.
+        auto prefetch_slab = [&](int g, int sl) {
+            if (g >= wp.total_tiles) return;
+            int seed, j, tm, tn;
+            decode(g, seed, j, tm, tn);
+            const GemmTask& T = tasks[j];
+            if (T.epi != EPI_ADAM) return;
+            const int n0 = tn * T.bn + sl * WS_SLAB;
+            const int nlim = min(T.N, tn * T.bn + T.bn);
+            const int m = tm * WS_BM + q * 32 + lane;
+            if (n0 >= nlim || m >= T.M) return;
+            const uint32_t bytes = (uint32_t)min(WS_SLAB, (nlim - n0 + 3) & ~3) * 4u;
+            const long long eo = (long long)m * T.ldc + n0;
+            l2_prefetch(resolve(sp.as, T.C, seed) + eo, bytes);
+            l2_prefetch(m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off + eo, bytes);
+            l2_prefetch(m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off + eo, bytes);
+            if (T.target_off >= 0) l2_prefetch(pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off + eo, bytes);
+        };
+        prefetch_slab(blockIdx.x, hsel);
         int tl = 0;
         for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x, ++tl) {
             int seed, j, tm, tn;
@@ -241,26 +277,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
             const int nlim = min(N, n0 + bn);
             const int buf = tl & 1;
             float* __restrict__ C = resolve(sp.as, T.C, seed);
-            const bool is_adam = epi == EPI_ADAM;
+            // the operand layouts pin the epilogue class (dW products are the only (MN, MN) tasks, masked dX products
+            // the only (K, MN) ones): dead epilogues are compiled out, which keeps their registers out of the live set
+            constexpr bool CAN_ADAM = A_MN && B_MN, CAN_MASK = !A_MN && B_MN;
+            const bool is_adam = CAN_ADAM && epi == EPI_ADAM;
+            const bool is_grad = CAN_ADAM && epi == EPI_GRAD;        // plain store of dW; Adam streams later (adam_stream.cuh)
             AdamScalars s;
+            float inv_bc2 = 1.f;
             float* __restrict__ am = nullptr; float* __restrict__ av = nullptr; float* __restrict__ tg = nullptr;
             if (is_adam) {
                 const int32_t* cnt = sp.as.counters + seed * sp.as.n_counters;
                 s = make_adam_scalars_fast(sp.hyper, T.lr, cnt[T.counter], cnt[CNT_TRAIN_STEPS]);
+                inv_bc2 = 1.0f / s.bc2_sqrt;
                 am = m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off;
                 av = m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off;
                 if (T.target_off >= 0 && s.do_polyak) tg = pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off;
             }
             const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
-            const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+            const float* __restrict__ mask = (CAN_MASK && epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
             const int ldmask = T.ldmask;
 
-            mbar_wait(&s_tfull[buf], ((uint32_t)tl >> 1) & 1u);
+            mbar_wait_relaxed(&s_tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
             const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
+            if (is_adam && !rows_live) prefetch_slab(g + gridDim.x, hsel);
             for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
                 const int c0 = sl * WS_SLAB;
+                if (is_adam) {
+                    if ((sl + 2) * WS_SLAB < nlim - n0) prefetch_slab(g, sl + 2);
+                    else prefetch_slab(g + gridDim.x, hsel);
+                }
+                // ReLU-mask epilogue: all 16 mask loads of this lane fly while the accumulator is read back and
+                // transposed (one at a time they cost a DRAM latency each: 21 us per K=1 tile in profiles/r01c)
+                float4 k4[16];
+                const bool mask_vec = mask != nullptr && (n0 + c0 + c4 + 3 < nlim);
+                if (mask_vec) {
+#pragma unroll
+                    for (int rp = 0; rp < 16; ++rp) {
+                        const int m = m0 + q * 32 + 2 * rp + rsub;
+                        k4[rp] = (m < M) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n0 + c0 + c4))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {                 // 32 columns at a time: 32 live registers
                     if (c0 + 32 * hf >= bn) break;
@@ -299,10 +358,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                                 if (eo[r] < 0) continue;
                                 if (vec) {
                                     const bool ht = tg != nullptr;
-                                    adam_core(x[r].x, p4[r].x, a4[r].x, v4[r].x, t4[r].x, ht, s);
-                                    adam_core(x[r].y, p4[r].y, a4[r].y, v4[r].y, t4[r].y, ht, s);
-                                    adam_core(x[r].z, p4[r].z, a4[r].z, v4[r].z, t4[r].z, ht, s);
-                                    adam_core(x[r].w, p4[r].w, a4[r].w, v4[r].w, t4[r].w, ht, s);
+                                    adam_core(x[r].x, p4[r].x, a4[r].x, v4[r].x, t4[r].x, ht, s, inv_bc2);
+                                    adam_core(x[r].y, p4[r].y, a4[r].y, v4[r].y, t4[r].y, ht, s, inv_bc2);
+                                    adam_core(x[r].z, p4[r].z, a4[r].z, v4[r].z, t4[r].z, ht, s, inv_bc2);
+                                    adam_core(x[r].w, p4[r].w, a4[r].w, v4[r].w, t4[r].w, ht, s, inv_bc2);
                                     *reinterpret_cast<float4*>(C + eo[r]) = p4[r];
                                     *reinterpret_cast<float4*>(am + eo[r]) = a4[r];
                                     *reinterpret_cast<float4*>(av + eo[r]) = v4[r];
@@ -314,7 +373,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                                         const float xj = jj == 0 ? x[r].x : (jj == 1 ? x[r].y : x[r].z);
                                         const long long ee = eo[r] + jj;
                                         float pp = C[ee], mm = am[ee], vv = av[ee], tt = tg ? tg[ee] : 0.f;
-                                        adam_core(xj, pp, mm, vv, tt, tg != nullptr, s);
+                                        adam_core(xj, pp, mm, vv, tt, tg != nullptr, s, inv_bc2);
                                         C[ee] = pp; am[ee] = mm; av[ee] = vv;
                                         if (tg) tg[ee] = tt;
                                     }
@@ -327,7 +386,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                             if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
                             else { b4.x = __ldg(bias + n); if (n + 1 < nlim) b4.y = __ldg(bias + n + 1); if (n + 2 < nlim) b4.z = __ldg(bias + n + 2); }
                         }
-#pragma unroll 4
+#pragma unroll
                         for (int rp = 0; rp < 16; ++rp) {
                             const int row = 2 * rp + rsub, m = m0 + q * 32 + row;
                             if (m >= M) continue;
@@ -337,9 +396,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                             float* dst = C + (long long)m * ldc + n;
                             if (vec) {
                                 if (mask != nullptr) {
-                                    const float4 k4 = __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n));
-                                    x.x = k4.x > 0.f ? x.x : 0.f; x.y = k4.y > 0.f ? x.y : 0.f;
-                                    x.z = k4.z > 0.f ? x.z : 0.f; x.w = k4.w > 0.f ? x.w : 0.f;
+                                    x.x = k4[rp].x > 0.f ? x.x : 0.f; x.y = k4[rp].y > 0.f ? x.y : 0.f;
+                                    x.z = k4[rp].z > 0.f ? x.z : 0.f; x.w = k4[rp].w > 0.f ? x.w : 0.f;
                                 }
                                 *reinterpret_cast<float4*>(dst) = x;
                             } else {
@@ -357,6 +415,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                 __syncwarp();                                    // slab is rewritten by the next pass
             }
             // bias block of a dW task: column sums of dY sit in the spare TMEM columns (every column is the row sum)
+            if (is_grad && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
+                const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
+                const int m = m0 + q * 32 + lane;
+                if (m < M) resolve(sp.as, T.bias, seed)[m] = T.train_bias ? gsum : 0.f;      // a frozen bias gets a zero gradient
+            }
             if (is_adam && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
                 const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
                 const int m = m0 + q * 32 + lane;

@@ -48,7 +48,8 @@ enum Epilogue {
     EPI_BIAS = 1,        // C = acc + bias[n]
     EPI_BIAS_RELU = 2,   // C = max(acc + bias[n], 0)
     EPI_MASK = 3,        // C = acc * (mask[m, n] > 0)
-    EPI_ADAM = 4         // acc is dW for the parameter block at C: Adam step (+ Polyak of `target`)
+    EPI_ADAM = 4,        // acc is dW for the parameter block at C: Adam step (+ Polyak of `target`)
+    EPI_GRAD = 5         // acc is dW, stored to the gradient block at C (bias gradient to `bias`); Adam streams later
 };
 
 struct GemmTask {

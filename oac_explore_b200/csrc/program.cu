@@ -13,6 +13,7 @@
 //   G-OAC : mean/std critic regression -> Adam -> upper-bound policy and mean target-policy
 //           updates through the updated critic.               trainer/gaussian_trainer.py:177-388
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -20,10 +21,12 @@
 #include "glue.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
+#include "adam_stream.cuh"
 #include "oac_error.h"
 
 namespace oac {
 
+constexpr int OAC_E_SPLIT_UNAVAILABLE = -100;      // internal: finalize() asks for a rebuild without gradient-store stages
 static inline int pad4(int x) { return (x + 3) & ~3; }
 static inline long long pad4ll(long long x) { return (x + 3) & ~3ll; }
 
@@ -117,7 +120,7 @@ static int build_layout(const OacConfig& c, OacLayout& L, NetIds& ids) {
 // ------------------------------------------------------------------------------------
 // program
 // ------------------------------------------------------------------------------------
-enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3 };
+enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3, ST_ADAM = 4 };
 
 struct Stage {
     int kind;
@@ -127,6 +130,7 @@ struct Stage {
     CriticHeadParams chp;
     std::vector<PolicyGradTask> pg;
     PolicyGradParams pgp;
+    AdamStreamParams asp;       // ST_ADAM
     // launch
     void* dev = nullptr;        // task table / params on the device
     int small_tiles = 0;
@@ -162,6 +166,7 @@ struct OacTrainer {
     int n_opt = 0;
     long long* tc_dbg = nullptr;
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
+    bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
 };
 
 namespace oac {
@@ -178,6 +183,32 @@ struct Builder {
     explicit Builder(OacTrainer& tr) : t(tr), c(tr.cfg), L(tr.lay) {
         O = c.obs_dim; A = c.act_dim; H = c.hidden; B = c.batch;
         tensor_glue = c.gemm_path == OAC_GEMM_TF32 && (long long)c.n_seeds * c.batch >= 2048;
+        split_adam = tensor_glue && tr.allow_split && tr.allow_ws;
+        if (split_adam) grad = work(L.adam_floats);
+    }
+    // Same regime: the weight-gradient GEMMs store plain gradients (laid out like the trainable prefix of the
+    // parameter arena) and a streaming kernel applies Adam + Polyak to whole nets (adam_stream.cuh).
+    bool split_adam;
+    Ref grad{AR_WORK, 0};
+    std::vector<AdamSeg> pending_segs;
+    void adam_seg(int ni, int ti, float lr, int counter) {
+        if (!split_adam) return;
+        const OacNetLayout& n = net(ni);
+        AdamSeg sg;
+        sg.off = n.off_w0; sg.len = n.size; sg.grad_off = grad.off + n.off_w0;
+        sg.target_off = ti >= 0 ? net(ti).off_w0 : -1;
+        sg.lr = lr; sg.counter = CNT_OPT0 + counter;
+        pending_segs.push_back(sg);
+    }
+    void flush_adam(const char* name) {
+        if (!split_adam || pending_segs.empty()) return;
+        Stage& s = add_stage(ST_ADAM, name);
+        memset(&s.asp, 0, sizeof(s.asp));
+        s.asp.n_seg = (int)pending_segs.size();
+        long long tot = 0;
+        for (size_t i = 0; i < pending_segs.size(); ++i) { s.asp.seg[i] = pending_segs[i]; tot += pending_segs[i].len >> 2; }
+        s.asp.total4 = tot;
+        pending_segs.clear();
     }
     Ref work(long long n) {
         Ref r{AR_WORK, t.work_cursor};
@@ -227,6 +258,10 @@ struct Builder {
         g.B = x; g.ldb = ldx; g.b_trans = 1;
         g.C = P(w_off); g.ldc = ldw; g.M = Nout; g.N = Kin; g.K = rows;
         g.epi = EPI_ADAM; g.bias = P(b_off); g.has_bias = 1; g.train_bias = train_bias;
+        if (split_adam) {
+            g.epi = EPI_GRAD;
+            g.C = Ref{AR_WORK, grad.off + w_off}; g.bias = Ref{AR_WORK, grad.off + b_off};
+        }
         g.adam_off = w_off; g.adam_bias_off = b_off;
         g.target_off = tw_off; g.target_bias_off = tb_off;
         g.lr = lr; g.counter = CNT_OPT0 + counter;
@@ -316,6 +351,7 @@ struct Builder {
         dw(s, dh2, H, h1, H, B, H, H, n.off_w1, H, n.off_b1, tn ? tn->off_w1 : -1, tn ? tn->off_b1 : -1, lr, counter, 1);
         dw(s, dq, pad4(n.n_out), h2, H, B, n.n_out, H, n.off_w2, H, n.off_b2, tn ? tn->off_w2 : -1, tn ? tn->off_b2 : -1,
            lr, counter, c.train_bias);
+        adam_seg(ni, ti, lr, counter);
     }
     // policy backward from dhead [B,2A] at rows [row0,row0+B) of a policy activation set
     struct PolGrad { Ref dhead, dh2, dh1; };
@@ -337,6 +373,7 @@ struct Builder {
         dw(s, g.dh1, H, X(xblk), L.x_ld, B, H, O, n.off_w0, n.in_ld, n.off_b0, -1, -1, lr, counter, 1);
         dw(s, g.dh2, H, Ref{a.h1.arena, a.h1.off + ro}, H, B, H, H, n.off_w1, H, n.off_b1, -1, -1, lr, counter, 1);
         dw(s, g.dhead, pad4(2 * A), Ref{a.h2.arena, a.h2.off + ro}, H, B, 2 * A, H, n.off_w2, H, n.off_b2, -1, -1, lr, counter, 1);
+        adam_seg(ni, -1, lr, counter);
     }
     // policy-loss gradient task: critics (dh1 rows, fc0 weights) -> dhead, and the policy's own dh2
     // crit_da_refs (tensor_glue): per critic, where the pi_da GEMM stage left dh1 W0[:, O:O+A] for these rows
@@ -445,6 +482,7 @@ void Builder::build_sac() {
     if (mode_b) policy_grad_stage();
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
+    flush_adam("critic_adam_apply");
     if (!mode_b) {
         { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
         { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
@@ -452,6 +490,7 @@ void Builder::build_sac() {
     }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
+    flush_adam("policy_adam_apply");
 }
 
 void Builder::build_poac() {
@@ -483,6 +522,7 @@ void Builder::build_poac() {
     { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); for (int i = 0; i < n; ++i) crit_dh1(s, t.ids.qf[i], qa[i], 0); }
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       for (int i = 0; i < n; ++i) crit_adam(s, t.ids.qf[i], t.ids.tf[i], qa[i], 0, 2, c.qf_lr, 2 + i); }
+    flush_adam("critic_adam_apply");
     // policy phase through the UPDATED critics
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 1, pa_q[i]); }
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pa_q[i]); }
@@ -500,6 +540,7 @@ void Builder::build_poac() {
     if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
+    flush_adam("policy_adam_apply");
 }
 
 void Builder::build_goac() {
@@ -533,6 +574,7 @@ void Builder::build_goac() {
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       for (int i = 0; i < n; ++i)
           crit_adam(s, t.ids.qf[i], t.ids.tf[i], qa[i], 0, 2, i == 0 ? c.qf_lr : c.std_lr, 2 + i); }
+    flush_adam("critic_adam_apply");
     // policy (rows [B,2B) = block 1) and target policy (rows [0,B) = block 0) through the updated critic
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l1"); for (int i = 0; i < n; ++i) crit_l1(s, t.ids.qf[i], 0, pq[i]); }
     { Stage& s = add_stage(ST_GEMM, "pi_critic_l2"); for (int i = 0; i < n; ++i) crit_l2(s, t.ids.qf[i], pq[i]); }
@@ -561,6 +603,7 @@ void Builder::build_goac() {
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); pol_dh1(s, tpol, tpa, 0, tpg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam");
       pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); pol_adam(s, tpol, tpa, 0, 2, tpg, c.policy_lr, 1); }
+    flush_adam("policy_adam_apply");
 }
 
 // ------------------------------------------------------------------------------------
@@ -617,7 +660,8 @@ static bool ws_eligible(const OacTrainer& t, const Stage& s) {
         if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
         if (!al16(resolve(as, g.A, 0)) || !al16(resolve(as, g.B, 0)) || !al16(resolve(as, g.C, 0))) return false;
         if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_RELU) && !al16(resolve(as, g.bias, 0))) return false;
-        if (g.epi == EPI_MASK && ((g.ldmask & 3) || !al16(resolve(as, g.mask, 0)))) return false;
+        if (g.epi == EPI_MASK && ((g.ldmask & 3) || !al16(resolve(as, g.mask, 0)) || g.a_trans || !g.b_trans)) return false;
+        if (g.epi == EPI_GRAD && !(g.a_trans && g.b_trans)) return false;
         if (g.epi == EPI_ADAM) {
             if ((g.adam_off & 3) || (g.target_off >= 0 && (g.target_off & 3))) return false;
             if (!al16(as.base[AR_ADAM_M]) || !al16(as.base[AR_ADAM_V]) || !al16(as.base[AR_PARAM])) return false;
@@ -631,7 +675,7 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     const int seeds = t.cfg.n_seeds;
     const int gran = s.b_trans ? 32 : 16;                      // MN-major B tiles come in 32-column TMA boxes
     auto width = [&](const GemmTask& g, int cap) {             // tile width for a column cap: even split, rounded up
-        const int lim = (g.epi == EPI_ADAM && g.has_bias) ? std::min(cap, (int)WS_BN_MAX_BIAS) : cap;
+        const int lim = ((g.epi == EPI_ADAM || g.epi == EPI_GRAD) && g.has_bias) ? std::min(cap, (int)WS_BN_MAX_BIAS) : cap;
         const int tn = (g.N + lim - 1) / lim;
         int bn = (((g.N + tn - 1) / tn) + gran - 1) / gran * gran;
         return std::max(bn, gran);
@@ -644,6 +688,12 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     // widest tiles that still give every SM work; the narrowest ones when even those cannot (single seed: latency)
     int cap = 256;
     while (cap > 32 && tiles(cap) * seeds < sm_count()) cap >>= 1;
+    // heaviest tiles first (epilogue elements dominate; an Adam element moves 8x the bytes of a stored one)
+    auto tile_cost = [&](const GemmTask& g) {
+        const double rows = std::min(g.M, (int)WS_BM), cols = std::min(g.N, width(g, cap));
+        return rows * cols * (g.epi == EPI_ADAM ? 8.0 : (g.epi == EPI_MASK ? 2.0 : 1.0)) + 0.05 * WS_BM * cols * g.K / 32.0;
+    };
+    std::stable_sort(s.gemm.begin(), s.gemm.end(), [&](const GemmTask& a, const GemmTask& b) { return tile_cost(a) > tile_cost(b); });
     int t0 = 0, bn_max = 0;
     for (auto& g : s.gemm) {
         g.bn = width(g, cap);
@@ -723,6 +773,8 @@ static int finalize(OacTrainer& t) {
                     if (int e = ws_plan(t, s)) return e;
                     continue;
                 }
+                for (auto& g : s.gemm)
+                    if (g.epi == EPI_GRAD) return set_error(OAC_E_SPLIT_UNAVAILABLE, "gradient-store stages need the TMA path");
                 // tcgen05 path: 128 x BN tiles.  Pick the largest BN that still fills the chip.
                 s.use_tc = 1;
                 const int bn_min = s.b_trans ? 32 : 16;
@@ -803,6 +855,9 @@ static int finalize(OacTrainer& t) {
             s.chp.iters = s.glue_iters;
             s.chp.as = t.as;
             if (int e = upload(t, &s.chp, 1, &s.dev)) return e;
+        } else if (s.kind == ST_ADAM) {
+            s.asp.as = t.as; s.asp.hyper = t.hyper;
+            if (int e = upload(t, &s.asp, 1, &s.dev)) return e;
         } else if (s.kind == ST_POLICY_GRAD) {
             glue_plan(s, (long long)t.cfg.batch * s.pg.size() * seeds, !s.pgp.da_from_gemm);
             if (int e = upload(t, s.pg.data(), s.pg.size(), &s.dev)) return e;
@@ -839,7 +894,7 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
             if (s.use_ws) {
                 WsParams wp; wp.sp = sp; wp.tmaps = (const CUtensorMap*)s.ws_tmaps; wp.n_tasks = (int)s.gemm.size();
-                wp.tiles_per_seed = s.ws_tiles_per_seed; wp.total_tiles = s.ws_tiles_per_seed * seeds;
+                wp.tiles_per_seed = s.ws_tiles_per_seed; wp.n_seeds = seeds; wp.total_tiles = s.ws_tiles_per_seed * seeds;
                 wp.n_slots = s.ws_slots; wp.slot_bytes = s.ws_slot_bytes;
                 const dim3 wg(s.ws_grid), wb(WS_THREADS);
                 if (!s.a_trans && !s.b_trans) launch_pdl(gemm_ws_kernel<false, false>, wg, wb, s.smem, st, wp);
@@ -881,6 +936,10 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
                                                 : (size_t)2 * t.cfg.act_dim * t.cfg.hidden + 2 * t.cfg.act_dim * (1 + spc));
             if (s.glue_g == 1) launch_pdl(policy_head_kernel<1>, grid, dim3(GLUE_THREADS), smem, st, p);
             else launch_pdl(policy_head_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
+        } else if (s.kind == ST_ADAM) {
+            const long long per_cta = (long long)ADAM_THREADS * ADAM_UNROLL;
+            dim3 grid((unsigned)((s.asp.total4 + per_cta - 1) / per_cta), seeds, 1);
+            launch_pdl(adam_stream_kernel, grid, dim3(ADAM_THREADS), 0, st, (const AdamStreamParams*)s.dev);
         } else if (s.kind == ST_CRITIC_HEAD) {
             const int per_cta = (GLUE_WARPS / s.glue_g) * s.glue_iters;       // iters is part of the uploaded CriticHeadParams
             dim3 grid((t.cfg.batch + per_cta - 1) / per_cta, seeds, 1);
@@ -977,7 +1036,21 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
-    if (int e = finalize(*t)) { oac_trainer_destroy(t); return e; }
+    int fe = finalize(*t);
+    if (fe == OAC_E_SPLIT_UNAVAILABLE) {
+        // no TMA path for a gradient-store stage (tensor maps unavailable / misaligned buffers): rebuild the program
+        // with the fused Adam epilogues
+        for (void* p : t->dev_allocs) cudaFree(p);
+        t->dev_allocs.clear(); t->stages.clear(); t->work_cursor = 0;
+        t->allow_split = false;
+        Builder b2(*t);
+        if (cfg->algo == OAC_ALGO_SAC) b2.build_sac();
+        else if (cfg->algo == OAC_ALGO_POAC) b2.build_poac();
+        else b2.build_goac();
+        if (t->work_cursor > t->lay.work_floats) { oac_trainer_destroy(t); return set_error(OAC_E_INVALID, "internal: work arena"); }
+        fe = finalize(*t);
+    }
+    if (fe) { oac_trainer_destroy(t); return fe; }
     { const char* np_ = getenv("OAC_PDL"); g_use_pdl = (np_ && np_[0] == '1'); }
     const char* ng = getenv("OAC_NO_GRAPH");
     t->use_graph = !(ng && ng[0] == '1');
