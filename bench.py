@@ -384,10 +384,14 @@ def main():
     ap.add_argument("--algo", default="sac", choices=["sac", "poac", "goac"])
     ap.add_argument("--seeds-per-gpu", type=int, default=1,
                     help="independent OAC seeds batched per GPU (BASELINE config 5: 64 total)")
-    ap.add_argument("--gemm-path", default="tf32x3", choices=list(GEMM_PATHS),
-                    help="fp32: SIMT FFMA; tf32: tcgen05 kind::tf32; tf32x3: tcgen05 3xTF32 (fp32-grade accuracy)")
+    ap.add_argument("--gemm-path", default="auto", choices=["auto"] + list(GEMM_PATHS),
+                    help="fp32: SIMT FFMA (reference-matching numerics, <=1e-5); tf32: TMA + tcgen05 kind::tf32 (<=1e-3); "
+                         "tf32x3: tcgen05 3xTF32 (fp32-grade accuracy).  auto: fp32 for one seed per GPU (the step is "
+                         "latency-bound there and the FFMA path is the fastest at reference numerics), tf32 for batched seeds")
     args = ap.parse_args()
     global GEMM_PATH
+    if args.gemm_path == "auto":
+        args.gemm_path = "fp32" if args.seeds_per_gpu == 1 else "tf32"
     GEMM_PATH = GEMM_PATHS[args.gemm_path]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

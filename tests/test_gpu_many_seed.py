@@ -1,0 +1,103 @@
+"""The many-seed regime of the tensor-core path (>= 2048 batch rows per launch): head layers, dQ/da and the policy's
+first backward step run as TMA + tcgen05 GEMM stages, weight gradients are stored and Adam streams
+(adam_stream.cuh).  Checked against the fp32 path / the oracle at the TF32 tolerance of BASELINE.json (1e-3 on values;
+gradients carry the ReLU-mask-flip noise explained in test_gpu_tensorcore.py)."""
+import pytest
+import torch
+
+from oracle import oac_oracle as orc
+from tests.util import synth_batch, synth_eps, rel_err, max_abs
+from tests.gpu_util import net_cpu
+from tests.test_gpu_sac import make_trainer, NETS
+from tests.test_gpu_poac_goac import make_poac, make_goac
+
+pytestmark = pytest.mark.gpu
+
+
+def test_group_of_eight_tensor_path_vs_fp32_singles():
+    from oac_explore_b200.seed_group import SACSeedGroup
+    O, A, B, H = 376, 17, 256, 256
+    ids = [0, 1, 2, 3, 4, 5, 6, 7]
+    grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=1)
+    e = grp.engine
+    # every GEMM stage runs on the warp-specialised TMA kernel, Adam is a stage of its own
+    assert e.ws_stages >= 13 and e.launches_per_step == 18, (e.ws_stages, e.launches_per_step)
+    singles = []
+    for sid in ids:
+        torch.manual_seed(sid)
+        singles.append(make_trainer(O, A, H, gemm_path=0))
+    for step in range(2):
+        for slot, sid in enumerate(ids):
+            batch = synth_batch(B, O, A, seed=1000 * sid + step)
+            eps = synth_eps(2, B, A, seed=77 * sid + step)
+            grp.load_batch(slot, batch)
+            grp.inject_noise(slot, eps[0], eps[1])
+            singles[slot].inject_noise(eps[0], eps[1])
+            singles[slot].train_from_torch({k: v.cuda() for k, v in batch.items()})
+        grp.step(external_eps=True)
+        if step == 0:
+            for slot in range(len(ids)):
+                se = singles[slot]._engine
+                for off, shape in ((e.lay.off_q_pred, (B, 2)), (e.lay.off_q_target, (B, 2)), (e.lay.off_log_pi, (3 * B,))):
+                    r = rel_err(e.io_view(off, shape, seed=slot).cpu(), se.io_view(off, shape).cpu())
+                    assert r <= 1e-3, (slot, off, r)
+                for idx in (0, 1, 2):       # first-step gradients = exp_avg / (1 - beta1)
+                    mg, ms = e.net_views(idx, seed=slot, arena=e.adam_m), se.net_views(idx, arena=se.adam_m)
+                    for k in mg:
+                        r = rel_err(mg[k].cpu(), ms[k].cpu())
+                        assert r <= 3e-2, (slot, idx, k, r)
+    torch.cuda.synchronize()
+    for slot in range(len(ids)):
+        for n in NETS:
+            a, b = net_cpu(grp.nets[slot][n]), net_cpu(getattr(singles[slot], n))
+            for k in a:
+                # Adam's first steps move every weight by ~lr * sign(g): an element whose tiny gradient changes sign under
+                # tf32 rounding differs by 2 * lr per step (lr = 3e-4, two steps)
+                assert rel_err(a[k], b[k]) <= 2e-3 or max_abs(a[k], b[k]) <= 1.25e-3, (slot, n, k, rel_err(a[k], b[k]))
+
+
+@pytest.mark.parametrize("share", [True, False])
+def test_poac_goac_large_batch_tensor_path(share):
+    """P-OAC and G-OAC reach the same regime with a 2048-row batch (their program builders have their own stage lists)."""
+    O, A, B, H, P = 24, 4, 2048, 64, 5
+    # separate particle nets only receive gradient where they sit at their own rank: tf32 noise
+    # on the particle values flips ranks as well as ReLU masks, so their gradients are noisier than the shared trunk's
+    gtol = 3e-2 if share else 6e-2
+    torch.manual_seed(1)
+    tr = make_poac(O, A, H, P, share, False)
+    tr.gemm_path = 1
+    tr._make_engine(B)
+    assert tr._engine.ws_stages >= 12
+    torch.manual_seed(1)
+    st = orc.ParticleState(O, A, hidden=(H, H), n_estimators=P, share_layers=share, q_min=0., q_max=500.)
+    batch = synth_batch(B, O, A, seed=20)
+    eps = synth_eps(2, B, A, seed=200)
+    o = orc.poac_step(st, batch, eps[0], eps[1])
+    tr.inject_noise(eps_obs=eps[1], eps_next=eps[0])
+    tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
+    e = tr._engine
+    assert rel_err(e.io_view(e.lay.off_q_target, (B, P)).cpu().t(), o['q_target'][:, :, 0]) <= 1e-3
+    m = e.net_views(0, arena=e.adam_m)
+    for k, gref in o['grad_policy'].items():
+        assert rel_err(m[k].cpu() / 0.1, gref) <= gtol, ('poac policy', k, rel_err(m[k].cpu() / 0.1, gref))
+    m = e.net_views(1, arena=e.adam_m)
+    for k, gref in o['grad_qf'][0].items():
+        assert rel_err(m[k].cpu() / 0.1, gref) <= gtol, ('poac qf', k, rel_err(m[k].cpu() / 0.1, gref))
+
+    torch.manual_seed(2)
+    tg = make_goac(O, A, H, share, False)
+    tg.gemm_path = 1
+    tg._make_engine(B)
+    assert tg._engine.ws_stages >= 12
+    torch.manual_seed(2)
+    sg = orc.GaussianState(O, A, hidden=(H, H), share_layers=share, q_min=0., q_max=500.)
+    batch = synth_batch(B, O, A, seed=30)
+    og = orc.goac_step(sg, batch)
+    tg.train_from_torch({k: v.cuda() for k, v in batch.items()})
+    e = tg._engine
+    for idx, gname in ((0, 'grad_policy'), (1, 'grad_target_policy'), (2, 'grad_q')):
+        m = e.net_views(idx, arena=e.adam_m)
+        for k, gref in og[gname].items():
+            if gref is None:
+                continue
+            assert rel_err(m[k].cpu() / 0.1, gref) <= 3e-2, (gname, k, rel_err(m[k].cpu() / 0.1, gref))
