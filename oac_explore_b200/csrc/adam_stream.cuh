@@ -43,7 +43,7 @@ __device__ __forceinline__ void adam_elem(float g, float& p, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_stream_kernel(const AdamStreamParams* __restrict__ pp) {
-    pdl_prologue();
+    pdl_wait();
     const AdamStreamParams& P = *pp;
     __shared__ AdamScalars s_sc[ADAM_MAX_SEGS];
     __shared__ long long s_start4[ADAM_MAX_SEGS + 1];

@@ -26,12 +26,15 @@ struct StageParams {
 
 __device__ __forceinline__ float relu(float x) { return x > 0.f ? x : 0.f; }
 
-// Programmatic dependent launch: let the next stage's grid be scheduled now, then wait until the previous
-// stage's results are visible.  Both are no-ops for a kernel launched without the PDL attribute.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-}
+// Programmatic dependent launch (both are no-ops for a kernel launched without the PDL attribute).
+//   pdl_wait   : first thing in every kernel -- blocks until the previous stage's grid has completed and its writes
+//                are visible.  Everything above it (none here) could overlap the predecessor.
+//   pdl_trigger: placed AFTER a kernel's main loop.  Once every CTA of the grid has executed it (or exited), the next
+//                stage's grid may be scheduled, so its launch latency and CTA set-up overlap this kernel's epilogue
+//                and drain instead of following them.  Triggering at the top of the kernel (first attempt, r01) let the
+//                dependent CTAs take SM slots from this kernel's own not-yet-started CTAs and was slower than no PDL.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 // torch.optim.Adam (1.4 formula order, trainer/trainer.py:75-91) on one element; no FMA
 // contraction so the rounding sequence is the reference's: mul, add; mul, addcmul; sqrt,
@@ -131,6 +134,17 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ sm, int sld, cons
     }
 }
 
+// N adjacent floats (N = 2 or 4, pointer aligned to N * 4 bytes) with one shared-memory load
+template <int N>
+__device__ __forceinline__ void load_adjacent(const float* p, float (&v)[N]) {
+    if (N == 2) { const float2 x = *reinterpret_cast<const float2*>(p); v[0] = x.x; v[1] = x.y; }
+    else if (N == 4) { const float4 x = *reinterpret_cast<const float4*>(p); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = p[i];
+    }
+}
+
 template <int BM, int BN, int TM, int TN, bool AT, bool BT>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_stage_kernel(StageParams sp) {
@@ -138,7 +152,7 @@ gemm_stage_kernel(StageParams sp) {
     extern __shared__ __align__(16) float smem[];
     __shared__ AdamScalars s_adam;
 
-    pdl_prologue();
+    pdl_wait();
     const GemmTask& T = sp.tasks[blockIdx.y];
     const int tile = blockIdx.x;
     if (tile >= T.tiles_m * T.tiles_n) return;
@@ -215,9 +229,7 @@ gemm_stage_kernel(StageParams sp) {
                 for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + i * TY) * a_ld + k);
                 float b[4][TN];
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) b[kk][j] = Bs[(k + kk) * b_ld + tx + j * TX];
+                for (int kk = 0; kk < 4; ++kk) load_adjacent<TN>(Bs + (k + kk) * b_ld + tx * TN, b[kk]);
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -233,10 +245,12 @@ gemm_stage_kernel(StageParams sp) {
 #pragma unroll 4
             for (int k = 0; k < kn; ++k) {
                 float a[TM], b[TN];
+                load_adjacent<TM>(As + k * a_ld + ty * TM, a);
+                if (BT) load_adjacent<TN>(Bs + k * b_ld + tx * TN, b);
+                else {
 #pragma unroll
-                for (int i = 0; i < TM; ++i) a[i] = As[k * a_ld + ty + i * TY];
-#pragma unroll
-                for (int j = 0; j < TN; ++j) b[j] = BT ? Bs[k * b_ld + tx + j * TX] : Bs[(tx + j * TX) * b_ld + k];
+                    for (int j = 0; j < TN; ++j) b[j] = Bs[(tx + j * TX) * b_ld + k];
+                }
 #pragma unroll
                 for (int i = 0; i < TM; ++i) {
                     if (bias_on) bsum[i] += a[i];
@@ -247,7 +261,13 @@ gemm_stage_kernel(StageParams sp) {
         }
     }
 
+    pdl_trigger();
     // ---- epilogue ----
+    // An M/N-contiguous operand gives a thread ADJACENT rows / columns (one 8- or 16-byte shared load per k instead of
+    // TM / TN scalar ones: the transposed products are bound by shared-memory wavefronts), a K-contiguous one interleaved
+    // rows / columns (conflict-free float4 loads along k).
+    auto rowi = [&](int i) { return AT ? ty * TM + i : ty + i * TY; };
+    auto colj = [&](int j) { return BT ? tx * TN + j : tx + j * TX; };
     float* __restrict__ C = resolve(sp.as, T.C, seed);
     const int ldc = T.ldc;
     const int epi = T.epi;
@@ -258,11 +278,11 @@ gemm_stage_kernel(StageParams sp) {
         const AdamScalars s = s_adam;
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-            const int m = m0 + ty + i * TY;
+            const int m = m0 + rowi(i);
             if (m >= M) continue;
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                const int n = n0 + tx + j * TX;
+                const int n = n0 + colj(j);
                 if (n >= N) continue;
                 const long long e = (long long)m * ldc + n;
                 float* tgt = T.target_off >= 0 ? pbase + T.target_off + e : nullptr;
@@ -285,11 +305,11 @@ gemm_stage_kernel(StageParams sp) {
     const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const int m = m0 + ty + i * TY;
+        const int m = m0 + rowi(i);
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const int n = n0 + tx + j * TX;
+            const int n = n0 + colj(j);
             if (n >= N) continue;
             float v = acc[i][j];
             if (epi == EPI_BIAS) v += bias[n];

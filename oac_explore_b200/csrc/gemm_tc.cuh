@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(TcStageParams tp
     __shared__ uint32_t s_tmem;
     __shared__ AdamScalars s_adam;
 
-    pdl_prologue();
+    pdl_wait();
     const StageParams& sp = tp.sp;
     const GemmTask& T = sp.tasks[blockIdx.y];
     const int tile = blockIdx.x;
@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(TcStageParams tp
     tc_fence_after();
     if (dbg) dbg[5] = clock64();
 
+    pdl_trigger();
     // ---- epilogue: TMEM -> registers -> shared (row-major slab) -> coalesced global ----
     // TMEM hands each thread one accumulator ROW (lane = row); writing rows straight to global would touch 32
     // different rows per store.  The tile is therefore parked in shared memory, SLAB columns at a time (the

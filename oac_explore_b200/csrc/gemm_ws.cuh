@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
     __shared__ uint32_t s_tmem;
     __shared__ int s_tile0[WS_MAX_TASKS + 1];
 
-    pdl_prologue();
+    pdl_wait();
     const StageParams& sp = wp.sp;
     const GemmTask* __restrict__ tasks = sp.tasks;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

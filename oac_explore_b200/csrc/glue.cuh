@@ -76,7 +76,7 @@ template <int G>
 __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
     constexpr int SPC = GLUE_WARPS / G;                    // rows per group (G warps share a row)
     extern __shared__ __align__(16) float s_ph[];
-    pdl_prologue();
+    pdl_wait();
     const PolicyHeadTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
     if (it + 1 < p.iters) group_sync<G>();                 // outv is rewritten by the next group
     }
 
+    pdl_trigger();
     // ---- last CTA of this seed: bump step counters, entropy-temperature Adam step ----
     __shared__ int s_last;
     __shared__ float s_red[GLUE_THREADS];
@@ -300,7 +301,7 @@ __device__ __forceinline__ void head_dots(const CriticHeadParams& p, int seed, i
 template <int G>
 __global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
     constexpr int SPC = GLUE_WARPS / G;
-    pdl_prologue();
+    pdl_wait();
     const CriticHeadParams& p = *pp;
     __shared__ float s_vals[SPC][MAX_VALS];
     __shared__ float s_dq[SPC][MAX_VALS];
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const Crit
     }
     }   // lane 0
     group_sync<G>();
+    if (it + 1 == p.iters) pdl_trigger();
     // ---- dh2 = (dq W3) * relu'(h2) for the critics whose backward starts with the current weights ----
     for (int s = 0; s < p.n_src && live; ++s) {
         const HeadSrc& S = p.src[s];
@@ -498,7 +500,7 @@ template <int G>
 __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
     constexpr int SPC = GLUE_WARPS / G;
     extern __shared__ __align__(16) float s_pg[];
-    pdl_prologue();
+    pdl_wait();
     const PolicyGradTask& T = p.tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -595,6 +597,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradPar
             }
         }
     }
+    pdl_trigger();
     if (from_gemm) return;                                  // dh2 is a GEMM stage of its own
     __syncthreads();
     // ---- policy backward, first step: dh2 = (dhead Wh) * relu'(h2) ----

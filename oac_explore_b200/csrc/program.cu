@@ -145,6 +145,9 @@ struct Stage {
     int max_rows = 0;
     int glue_iters = 1;         // glue kernels: sample groups per CTA (> 1 when many seeds share a launch)
     int glue_g = 4;             // ... and warps cooperating on one sample
+    // two-lane schedule (latency regime): lane 1 stages run on a side stream, forked from the main lane where they are
+    // listed and joined before the first later stage that sets `join` (or at the end of the step)
+    int lane = 0, join = 0;
     const char* name = "";
 };
 
@@ -162,11 +165,14 @@ struct OacTrainer {
     std::vector<void*> dev_allocs;
     long long work_cursor = 0;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaStream_t side = nullptr;            // lane 1
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool use_graph = true;
     int n_opt = 0;
     long long* tc_dbg = nullptr;
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
+    bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
 };
 
 namespace oac {
@@ -317,6 +323,16 @@ struct Builder {
         const OacNetLayout& n = net(ni);
         fwd(s, a.h1, H, a.rows, H, P(n.off_w1), H, P(n.off_b1), H, a.h2, H, true);
     }
+    // the same two layers restricted to rows [row0, row0+B) of the activation set (X block blk)
+    void crit_l1_rows(Stage& s, int ni, int blk, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        fwd(s, X(blk), L.x_ld, B, O + A, P(n.off_w0), n.in_ld, P(n.off_b0), H, Ref{a.h1.arena, a.h1.off + (long long)row0 * H}, H, true);
+    }
+    void crit_l2_rows(Stage& s, int ni, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        const long long ro = (long long)row0 * H;
+        fwd(s, Ref{a.h1.arena, a.h1.off + ro}, H, B, H, P(n.off_w1), H, P(n.off_b1), H, Ref{a.h2.arena, a.h2.off + ro}, H, true);
+    }
     HeadSrc head_src(int ni, const CritAct& a, int row0) {
         const OacNetLayout& n = net(ni);
         HeadSrc h; memset(&h, 0, sizeof(h));
@@ -339,19 +355,20 @@ struct Builder {
            Ref{a.dh1.arena, a.dh1.off + ro}, H, Ref{a.h1.arena, a.h1.off + ro}, H, true);
     }
     // Adam on all three layers of a critic from rows [row0,row0+B) (inputs: X block xblk)
-    void crit_adam(Stage& s, int ni, int ti, const CritAct& a, int row0, int xblk, float lr, int counter) {
+    // layers: bit 0 fc0, bit 1 fc1, bit 2 head
+    void crit_adam(Stage& s, int ni, int ti, const CritAct& a, int row0, int xblk, float lr, int counter, int layers = 7) {
         const OacNetLayout& n = net(ni);
         const OacNetLayout* tn = ti >= 0 ? &net(ti) : nullptr;
         long long ro = (long long)row0 * H;
         Ref dh1{a.dh1.arena, a.dh1.off + ro}, dh2{a.dh2.arena, a.dh2.off + ro};
         Ref h1{a.h1.arena, a.h1.off + ro}, h2{a.h2.arena, a.h2.off + ro};
         Ref dq{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)};
-        dw(s, dh1, H, X(xblk), L.x_ld, B, H, O + A, n.off_w0, n.in_ld, n.off_b0,
-           tn ? tn->off_w0 : -1, tn ? tn->off_b0 : -1, lr, counter, 1);
-        dw(s, dh2, H, h1, H, B, H, H, n.off_w1, H, n.off_b1, tn ? tn->off_w1 : -1, tn ? tn->off_b1 : -1, lr, counter, 1);
-        dw(s, dq, pad4(n.n_out), h2, H, B, n.n_out, H, n.off_w2, H, n.off_b2, tn ? tn->off_w2 : -1, tn ? tn->off_b2 : -1,
-           lr, counter, c.train_bias);
-        adam_seg(ni, ti, lr, counter);
+        if (layers & 1) dw(s, dh1, H, X(xblk), L.x_ld, B, H, O + A, n.off_w0, n.in_ld, n.off_b0,
+                           tn ? tn->off_w0 : -1, tn ? tn->off_b0 : -1, lr, counter, 1);
+        if (layers & 2) dw(s, dh2, H, h1, H, B, H, H, n.off_w1, H, n.off_b1, tn ? tn->off_w1 : -1, tn ? tn->off_b1 : -1, lr, counter, 1);
+        if (layers & 4) dw(s, dq, pad4(n.n_out), h2, H, B, n.n_out, H, n.off_w2, H, n.off_b2, tn ? tn->off_w2 : -1, tn ? tn->off_b2 : -1,
+                           lr, counter, c.train_bias);
+        if (layers == 7) adam_seg(ni, ti, lr, counter);
     }
     // policy backward from dhead [B,2A] at rows [row0,row0+B) of a policy activation set
     struct PolGrad { Ref dhead, dh2, dh1; };
@@ -450,16 +467,30 @@ void Builder::build_sac() {
     CritAct ta1 = alloc_crit(1, 1), ta2 = alloc_crit(1, 1);   // block 3
     PolGrad pg = alloc_polgrad();
     const bool mode_b = c.stale_graph_mode == 1;
+    // Latency regime (few seeds): a step is a chain of small kernels that leave most SMs idle, so independent work runs
+    // on a second lane: the critics' forward on the DATA rows does not depend on the policy and overlaps its forward.
+    const bool two_lanes = !tensor_glue && c.n_seeds * (long long)B <= 1024 && t.allow_lanes;
+    if (two_lanes) {
+        { Stage& s = add_stage(ST_GEMM, "critic_l1_data"); s.lane = 1; crit_l1_rows(s, q1, 2, ca1, B); crit_l1_rows(s, q2, 2, ca2, B); }
+        { Stage& s = add_stage(ST_GEMM, "critic_l2_data"); s.lane = 1; crit_l2_rows(s, q1, ca1, B); crit_l2_rows(s, q2, ca2, B); }
+    }
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
     if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
+    if (two_lanes) {
+        { Stage& s = add_stage(ST_GEMM, "critic_l1_pi");
+          crit_l1_rows(s, q1, 1, ca1, 0); crit_l1_rows(s, q2, 1, ca2, 0); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
+        { Stage& s = add_stage(ST_GEMM, "critic_l2_pi");
+          crit_l2_rows(s, q1, ca1, 0); crit_l2_rows(s, q2, ca2, 0); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
+    } else {
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
       crit_l1(s, q1, 1, ca1); crit_l1(s, q2, 1, ca2); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2");
+    }
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2"); s.join = 1;
       memset(&s.chp, 0, sizeof(s.chp));
       s.chp.src[0] = head_src(q1, ca1, 0); s.chp.src[1] = head_src(q2, ca2, 0);
       s.chp.src[2] = head_src(q1, ca1, B); s.chp.src[3] = head_src(q2, ca2, B);
@@ -474,15 +505,25 @@ void Builder::build_sac() {
     auto policy_grad_stage = [&]() {
         if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
         Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
+        s.join = 1;
         s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic, {ca1.da, ca2.da}));
         fill_pgp(s);
         if (tensor_glue) { Stage& s2 = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s2, pol, pa, 0, pg); }
     };
     // NB mode B reads fc0.weight's action columns too: its policy_grad stage runs before the critic Adam
     if (mode_b) policy_grad_stage();
+    if (two_lanes && !mode_b) {
+        // mode A: pi_dh2 / pi_dh1 read the POST-step head and fc1 weights, policy_grad the post-step fc0 action columns:
+        // the (largest) fc0 Adam runs on lane 1 next to the two dX stages
+        { Stage& s = add_stage(ST_GEMM, "critic_adam_fc0"); s.lane = 1;
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 1); }
+        { Stage& s = add_stage(ST_GEMM, "critic_adam_fc1+head");
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 6); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 6); }
+    } else {
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
     flush_adam("critic_adam_apply");
+    }
     if (!mode_b) {
         { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
         { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
@@ -868,11 +909,11 @@ static int finalize(OacTrainer& t) {
     return 0;
 }
 
-// Launch with Programmatic Dependent Launch: the next stage's grid is scheduled as soon as every CTA of the
-// current one has started (each kernel executes griddepcontrol.launch_dependents first and
-// griddepcontrol.wait before touching global memory), which hides the launch + CTA-scheduling latency of
-// the dependent stages of a step.  Measured on B200 inside the CUDA graph it is a LOSS (209 vs 181 us per step),
-// so it is off unless OAC_PDL=1.
+// Launch with Programmatic Dependent Launch: each kernel waits for its predecessor first thing (griddepcontrol.wait)
+// and releases its successor after its main loop (griddepcontrol.launch_dependents), so the successor's launch latency
+// and CTA set-up could overlap the epilogue and drain of the current stage.  Measured on B200 inside the CUDA graph it is
+// a LOSS either way (trigger at kernel entry: 209 vs 181 us per step; trigger after the main loop: 179 vs 164 us), so
+// the attribute is only set with OAC_PDL=1.
 static bool g_use_pdl = false;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -886,9 +927,40 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
-    const int seeds = t.cfg.n_seeds;
+static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStream_t st);
+
+// Runs the stage list.  Lane-1 stages go to the side stream: it is forked from the main stream at the first lane-1
+// stage after a join (event record / wait, which also works under stream capture: the side stream joins the capture),
+// and joined back before a stage that asks for it and at the end of the step.
+static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t main_st) {
+    bool side_busy = false;
+    auto join = [&]() -> int {
+        if (!side_busy) return 0;
+        OAC_CUDA(cudaEventRecord(t.ev_join, t.side));
+        OAC_CUDA(cudaStreamWaitEvent(main_st, t.ev_join, 0));
+        side_busy = false;
+        return 0;
+    };
     for (Stage& s : t.stages) {
+        cudaStream_t st = main_st;
+        if (s.lane == 1 && t.side != nullptr) {
+            if (!side_busy) {
+                OAC_CUDA(cudaEventRecord(t.ev_fork, main_st));
+                OAC_CUDA(cudaStreamWaitEvent(t.side, t.ev_fork, 0));
+                side_busy = true;
+            }
+            st = t.side;
+        } else if (s.join) {
+            if (int e = join()) return e;
+        }
+        if (int e = launch_stage(t, s, use_external_eps, st)) return e;
+    }
+    return join();
+}
+
+static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStream_t st) {
+    const int seeds = t.cfg.n_seeds;
+    {
         if (s.kind == ST_GEMM) {
             StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
@@ -901,7 +973,7 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
                 else if (!s.a_trans) launch_pdl(gemm_ws_kernel<false, true>, wg, wb, s.smem, st, wp);
                 else launch_pdl(gemm_ws_kernel<true, true>, wg, wb, s.smem, st, wp);
                 OAC_CUDA(cudaGetLastError());
-                continue;
+                return 0;
             }
             if (s.use_tc) {
                 TcStageParams tp; tp.sp = sp; tp.bn = s.bn; tp.kc = s.kc; tp.tmem_cols = s.tmem_cols; tp.n_main = s.n_main; tp.dbg = t.tc_dbg;
@@ -917,7 +989,7 @@ static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t st) {
                     else launch_pdl(gemm_tc_kernel<true, true, false>, grid, dim3(TC_THREADS), s.smem, st, tp);
                 }
                 OAC_CUDA(cudaGetLastError());
-                continue;
+                return 0;
             }
             const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
             switch (sel) {
@@ -988,6 +1060,8 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     OacTrainer* t = new OacTrainer();
     t->cfg = *cfg;
     if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
+    { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
+    { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
     else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
@@ -1035,7 +1109,6 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_in((const void*)policy_grad_kernel<4>);
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
-    { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     int fe = finalize(*t);
     if (fe == OAC_E_SPLIT_UNAVAILABLE) {
         // no TMA path for a gradient-store stage (tensor maps unavailable / misaligned buffers): rebuild the program
@@ -1054,6 +1127,16 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     { const char* np_ = getenv("OAC_PDL"); g_use_pdl = (np_ && np_[0] == '1'); }
     const char* ng = getenv("OAC_NO_GRAPH");
     t->use_graph = !(ng && ng[0] == '1');
+    {
+        bool lanes = false;
+        for (const Stage& s : t->stages) lanes = lanes || s.lane == 1;
+        if (lanes) {
+            cudaError_t e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
+            if (e != cudaSuccess) { oac_trainer_destroy(t); return set_cuda_error(e, "side stream"); }
+        }
+    }
     *out = t;
     return 0;
 }
@@ -1061,6 +1144,9 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
 extern "C" int oac_trainer_destroy(OacTrainer* t) {
     if (!t) return 0;
     for (int i = 0; i < 2; ++i) if (t->graph[i]) cudaGraphExecDestroy(t->graph[i]);
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->side) cudaStreamDestroy(t->side);
     for (void* p : t->dev_allocs) cudaFree(p);
     delete t;
     return 0;
