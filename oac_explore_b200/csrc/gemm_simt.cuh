@@ -26,6 +26,15 @@ struct StageParams {
 
 __device__ __forceinline__ float relu(float x) { return x > 0.f ? x : 0.f; }
 
+// Plain (coherent) global load.  The glue kernels read activations / weights that an earlier stage wrote; inside the
+// single-launch step those writes happen in the SAME kernel, where ld.global.nc (__ldg, or what nvcc derives from
+// const __restrict__) may return stale lines.  volatile: never hoisted above a grid barrier.
+__device__ __forceinline__ float ld_g(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // Programmatic dependent launch (both are no-ops for a kernel launched without the PDL attribute).
 //   pdl_wait   : first thing in every kernel -- blocks until the previous stage's grid has completed and its writes
 //                are visible.  Everything above it (none here) could overlap the predecessor.
@@ -145,18 +154,19 @@ __device__ __forceinline__ void load_adjacent(const float* p, float (&v)[N]) {
     }
 }
 
+// One (tile, task, seed) block of a GEMM stage.  A device function so that the same code runs as its own kernel
+// (gemm_stage_kernel) and as a phase of the single-launch step (mega.cuh); global data produced by earlier stages is
+// read with cp.async / plain loads only (no ld.global.nc), which stay coherent across the grid barriers of that kernel.
 template <int BM, int BN, int TM, int TN, bool AT, bool BT>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
-gemm_stage_kernel(StageParams sp) {
+__device__ __forceinline__ void gemm_stage_body(const StageParams& sp, int bx, int by, int bz) {
     constexpr int TY = BM / TM, TX = BN / TN, NT = TX * TY;
     extern __shared__ __align__(16) float smem[];
     __shared__ AdamScalars s_adam;
 
-    pdl_wait();
-    const GemmTask& T = sp.tasks[blockIdx.y];
-    const int tile = blockIdx.x;
+    const GemmTask& T = sp.tasks[by];
+    const int tile = bx;
     if (tile >= T.tiles_m * T.tiles_n) return;
-    const int seed = blockIdx.z;
+    const int seed = bz;
     const int tm = tile / T.tiles_n, tn = tile - tm * T.tiles_n;
     const int m0 = tm * BM, n0 = tn * BN;
     const int tid = threadIdx.x;
@@ -301,8 +311,8 @@ gemm_stage_kernel(StageParams sp) {
         }
         return;
     }
-    const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
-    const float* __restrict__ mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+    const float* bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
+    const float* mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int m = m0 + rowi(i);
@@ -318,6 +328,212 @@ gemm_stage_kernel(StageParams sp) {
             C[(long long)m * ldc + n] = v;
         }
     }
+}
+
+template <int BM, int BN, int TM, int TN, bool AT, bool BT>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_stage_kernel(StageParams sp) {
+    pdl_wait();
+    gemm_stage_body<BM, BN, TM, TN, AT, BT>(sp, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Latency-regime tile: 32 x 32 outputs per CTA, 256 threads = 4 k-groups x 64 threads, 4 x 4 outputs per thread.
+// A single seed's stages have too few outputs to give every thread a large register tile AND fill the chip, and the
+// 2 x 2-per-thread tile this replaces was bound by shared-memory wavefronts (4 LDS.128 per 16 FFMA; 37 % of its stall
+// samples at the first FFMA after the loads, profiles/r01_gemm_simt).  Splitting K four ways inside the CTA keeps
+// 256 threads per tile with 4 x 4 register tiles (8 LDS.128 per 64 FFMA); the four partial tiles meet in shared
+// memory and every thread finishes one row x 4 adjacent columns (128-byte rows of global traffic in the epilogue).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SK_BM = 32, SK_BN = 32, SK_T = 4, SK_KS = 4, SK_THREADS = 256, SK_PLD = 33;
+
+template <bool AT, bool BT>
+__device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int by, int bz) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ AdamScalars s_adam;
+    __shared__ float s_bsum[SK_KS][SK_BM];
+
+    const GemmTask& T = sp.tasks[by];
+    const int tile = bx;
+    if (tile >= T.tiles_m * T.tiles_n) return;
+    const int seed = bz;
+    const int tm = tile / T.tiles_n, tn = tile - tm * T.tiles_n;
+    const int m0 = tm * SK_BM, n0 = tn * SK_BN;
+    const int tid = threadIdx.x;
+    const int kg = tid >> 6, t64 = tid & 63;
+    const int tx = t64 & 7, ty = t64 >> 3;
+
+    const float* A = resolve(sp.as, T.A, seed);
+    const float* B = resolve(sp.as, T.B, seed);
+    const int M = T.M, N = T.N, K = T.K;
+    const int lda = T.lda, ldb = T.ldb;
+    const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+    const int kc = sp.kc;
+    const int kp = kpad_of(kc);
+    const int a_ld = AT ? SK_BM : kp;
+    const int b_ld = BT ? SK_BN : kp;
+    float* As = smem;
+    float* Bs = smem + (AT ? kc * SK_BM : SK_BM * kp);
+
+    const bool is_adam = T.epi == EPI_ADAM;
+    if (is_adam && tid == 0) {
+        int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
+        int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
+        s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
+    }
+    float acc[SK_T][SK_T];
+#pragma unroll
+    for (int i = 0; i < SK_T; ++i)
+#pragma unroll
+        for (int j = 0; j < SK_T; ++j) acc[i][j] = 0.f;
+    float bsum[SK_T] = {0.f, 0.f, 0.f, 0.f};
+    const bool bias_on = AT && is_adam && T.has_bias && tn == 0;
+    // rows / columns of this thread: adjacent for an M/N-contiguous operand (one LDS.128 per k), interleaved by 8 for a
+    // K-contiguous one (conflict-free LDS.128 along k)
+    const int r0 = AT ? ty * SK_T : ty, rs = AT ? 1 : 8;
+    const int c0 = BT ? tx * SK_T : tx, cs = BT ? 1 : 8;
+
+    for (int k0 = 0; k0 < K; k0 += kc) {
+        const int kn = min(kc, K - k0);
+        if (k0 > 0) __syncthreads();
+        const int kn4 = (kn + 3) & ~3;            // k tails are zero-filled
+        if (!AT) stage_tile<SK_THREADS>(As, a_ld, A, lda, m0, SK_BM, M, k0, kn, K, a_vec);
+        else     stage_tile<SK_THREADS>(As, a_ld, A, lda, k0, kn4, K, m0, SK_BM, M, a_vec);
+        if (!BT) stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, n0, SK_BN, N, k0, kn, K, b_vec);
+        else     stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, k0, kn4, K, n0, SK_BN, N, b_vec);
+        cp_async_wait_all();
+        __syncthreads();
+        const int ks = ((kn4 >> 2) + SK_KS - 1) / SK_KS * 4;          // this chunk's k per group (multiple of 4)
+        const int kb = kg * ks, ke = min(kb + ks, kn4);
+        if (!AT && !BT) {
+#pragma unroll 2
+            for (int k = kb; k < ke; k += 4) {
+                float4 a[SK_T], b[SK_T];
+#pragma unroll
+                for (int i = 0; i < SK_T; ++i) a[i] = *reinterpret_cast<const float4*>(As + (r0 + i * rs) * a_ld + k);
+#pragma unroll
+                for (int j = 0; j < SK_T; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (c0 + j * cs) * b_ld + k);
+#pragma unroll
+                for (int i = 0; i < SK_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < SK_T; ++j) {
+                        acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+                    }
+            }
+        } else if (!AT && BT) {
+#pragma unroll 2
+            for (int k = kb; k < ke; k += 4) {
+                float4 a[SK_T];
+#pragma unroll
+                for (int i = 0; i < SK_T; ++i) a[i] = *reinterpret_cast<const float4*>(As + (r0 + i * rs) * a_ld + k);
+                float b[4][SK_T];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) load_adjacent<SK_T>(Bs + (k + kk) * b_ld + c0, b[kk]);
+#pragma unroll
+                for (int i = 0; i < SK_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < SK_T; ++j) {
+                        acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
+                        acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
+                        acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
+                    }
+            }
+        } else {
+#pragma unroll 4
+            for (int k = kb; k < ke; ++k) {
+                float a[SK_T], b[SK_T];
+                load_adjacent<SK_T>(As + k * a_ld + r0, a);
+                if (BT) load_adjacent<SK_T>(Bs + k * b_ld + c0, b);
+                else {
+#pragma unroll
+                    for (int j = 0; j < SK_T; ++j) b[j] = Bs[(c0 + j * cs) * b_ld + k];
+                }
+#pragma unroll
+                for (int i = 0; i < SK_T; ++i) {
+                    if (bias_on) bsum[i] += a[i];
+#pragma unroll
+                    for (int j = 0; j < SK_T; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
+            }
+        }
+    }
+    pdl_trigger();
+    // ---- the four k-groups' partial tiles meet in shared memory (the operand tiles are dead) ----
+    __syncthreads();
+    float* part = smem;                                           // [SK_KS][32][SK_PLD]
+#pragma unroll
+    for (int i = 0; i < SK_T; ++i)
+#pragma unroll
+        for (int j = 0; j < SK_T; ++j) part[(kg * SK_BM + r0 + i * rs) * SK_PLD + c0 + j * cs] = acc[i][j];
+    if (bias_on && tx == 0) {
+#pragma unroll
+        for (int i = 0; i < SK_T; ++i) s_bsum[kg][r0 + i * rs] = bsum[i];
+    }
+    __syncthreads();
+    // ---- epilogue: thread -> one row, 4 adjacent columns ----
+    const int er = tid >> 3, ec = (tid & 7) << 2;
+    float v[SK_T];
+#pragma unroll
+    for (int j = 0; j < SK_T; ++j) {
+        float x = part[er * SK_PLD + ec + j];
+#pragma unroll
+        for (int g = 1; g < SK_KS; ++g) x += part[(g * SK_BM + er) * SK_PLD + ec + j];
+        v[j] = x;
+    }
+    const int m = m0 + er;
+    if (m >= M) return;
+    float* __restrict__ C = resolve(sp.as, T.C, seed);
+    const int ldc = T.ldc;
+    const int epi = T.epi;
+    if (is_adam) {
+        float* __restrict__ m1 = sp.as.base[AR_ADAM_M] + (long long)seed * sp.as.stride[AR_ADAM_M];
+        float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
+        float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
+        const AdamScalars s = s_adam;
+#pragma unroll
+        for (int j = 0; j < SK_T; ++j) {
+            const int n = n0 + ec + j;
+            if (n >= N) continue;
+            const long long e = (long long)m * ldc + n;
+            float* tgt = T.target_off >= 0 ? pbase + T.target_off + e : nullptr;
+            adam_update(v[j], C + e, m1 + T.adam_off + e, m2 + T.adam_off + e, tgt, s);
+        }
+        if (bias_on && ec == 0) {
+            const float bs_ = ((s_bsum[0][er] + s_bsum[1][er]) + s_bsum[2][er]) + s_bsum[3][er];
+            float* pb = resolve(sp.as, T.bias, seed) + m;
+            float* tgt = T.target_bias_off >= 0 ? pbase + T.target_bias_off + m : nullptr;
+            if (T.train_bias) {
+                adam_update(bs_, pb, m1 + T.adam_bias_off + m, m2 + T.adam_bias_off + m, tgt, s);
+            } else if (tgt != nullptr && s.do_polyak) {
+                *tgt = __fadd_rn(__fmul_rn(*tgt, s.one_m_tau), __fmul_rn(*pb, s.tau));   // a frozen bias still takes part in soft_update_from_to
+            }
+        }
+        return;
+    }
+    const float* bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
+    const float* mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+#pragma unroll
+    for (int j = 0; j < SK_T; ++j) {
+        const int n = n0 + ec + j;
+        if (n >= N) continue;
+        float x = v[j];
+        if (epi == EPI_BIAS) x += bias[n];
+        else if (epi == EPI_BIAS_RELU) x = relu(x + bias[n]);
+        else if (epi == EPI_MASK) x = mask[(long long)m * T.ldmask + n] > 0.f ? x : 0.f;
+        C[(long long)m * ldc + n] = x;
+    }
+}
+
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(SK_THREADS) gemm_sk_kernel(StageParams sp) {
+    pdl_wait();
+    gemm_sk_body<AT, BT>(sp, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 }  // namespace oac

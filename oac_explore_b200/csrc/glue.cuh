@@ -73,12 +73,12 @@ struct PolicyHeadParams {
 // share one row (each keeps the hidden row in registers and reduces every GLUE_G-th pair of dot products with
 // shuffles), then one of them runs the per-action-dim sampling math.  dyn smem: (2A*H + 2A + SPC*2A) floats.
 template <int G>
-__global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
+__device__ __forceinline__ void policy_head_body(const PolicyHeadParams& p, int use_external_eps, int bx, int by, int bz,
+                                                 int gdx, int gdy) {
     constexpr int SPC = GLUE_WARPS / G;                    // rows per group (G warps share a row)
     extern __shared__ __align__(16) float s_ph[];
-    pdl_wait();
-    const PolicyHeadTask& T = p.tasks[blockIdx.y];
-    const int seed = blockIdx.z;
+    const PolicyHeadTask& T = p.tasks[by];
+    const int seed = bz;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = warp / G, g = warp % G;
     const int A = p.A, B = p.B, H = p.H;
@@ -94,24 +94,24 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
         stage_contig(Ws, resolve(p.as, T.w, seed), 2 * A * H);
         stage_contig(bs, resolve(p.as, T.b, seed), 2 * A);
     }
-    const float* __restrict__ h2 = resolve(p.as, T.h2, seed);
-    const float* __restrict__ head_in = from_gemm ? resolve(p.as, T.head_in, seed) : nullptr;
+    const float* h2 = resolve(p.as, T.h2, seed);
+    const float* head_in = from_gemm ? resolve(p.as, T.head_in, seed) : nullptr;
     // the staged head weights serve p.iters row groups (many-seed launches: 16 -> 1/16 of the staging traffic)
     float hreg[GLUE_MAX_HR];
     auto load_row = [&](int row) {
         if (row < T.rows && !from_gemm) {
-            const float* __restrict__ h = h2 + (long long)row * H;
+            const float* h = h2 + (long long)row * H;
 #pragma unroll
-            for (int c = 0; c < GLUE_MAX_HR; ++c) hreg[c] = (lane + 32 * c < H) ? __ldg(h + lane + 32 * c) : 0.f;
+            for (int c = 0; c < GLUE_MAX_HR; ++c) hreg[c] = (lane + 32 * c < H) ? ld_g(h + lane + 32 * c) : 0.f;
         }
     };
-    load_row(blockIdx.x * p.iters * SPC + sl);
+    load_row(bx * p.iters * SPC + sl);
     cp_async_wait_all();
     __syncthreads();
     for (int it = 0; it < p.iters; ++it) {
-    const int row = (blockIdx.x * p.iters + it) * SPC + sl;
+    const int row = (bx * p.iters + it) * SPC + sl;
     if (row < T.rows && from_gemm) {
-        if (g == 0) for (int j = lane; j < 2 * A; j += 32) outv[j] = __ldg(head_in + (long long)row * T.head_ld + j);
+        if (g == 0) for (int j = lane; j < 2 * A; j += 32) outv[j] = ld_g(head_in + (long long)row * T.head_ld + j);
     } else if (row < T.rows) {
         for (int j = g; j < A; j += G) {
             const float* wm = Ws + j * H;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
             if (p.deterministic) {
                 action = tanhf(mean_j);
             } else {
-                if (p.use_external_eps)
+                if (use_external_eps)
                     eps = io[p.off_eps + ((long long)T.eps_slot[blk] * B + b) * A + j];
                 else
                     eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)seed,
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        int total = gridDim.x * gridDim.y;
+        int total = gdx * gdy;
         int prev = atomicAdd(&cnt[CNT_TICKET0], 1);
         s_last = (prev == total - 1);
     }
@@ -215,6 +215,12 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadPar
             sc[SC_ALPHA_LOSS] = 0.f;
         }
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
+    pdl_wait();
+    policy_head_body<G>(p, p.use_external_eps, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y);
 }
 
 // =====================================================================================
@@ -275,8 +281,8 @@ __device__ __forceinline__ void head_dots(const CriticHeadParams& p, int seed, i
 #pragma unroll
                 for (int c = 0; c < HR; ++c) {
                     const int k = lane + 32 * c;
-                    hv[u][c] = k < H ? __ldg(h + k) : 0.f;
-                    wv[u][c] = k < H ? __ldg(w + k) : 0.f;
+                    hv[u][c] = k < H ? ld_g(h + k) : 0.f;
+                    wv[u][c] = k < H ? ld_g(w + k) : 0.f;
                 }
             }
         }
@@ -288,7 +294,7 @@ __device__ __forceinline__ void head_dots(const CriticHeadParams& p, int seed, i
 #pragma unroll
                 for (int c = 0; c < HR; ++c) acc = fmaf(hv[u][c], wv[u][c], acc);
                 acc = warp_sum(acc);
-                if (lane == 0) vals[pi] = acc + __ldg(resolve(p.as, p.src[pair_src[pi]].b3, seed) + pair_hd[pi]);
+                if (lane == 0) vals[pi] = acc + ld_g(resolve(p.as, p.src[pair_src[pi]].b3, seed) + pair_hd[pi]);
             }
         }
     }
@@ -299,16 +305,14 @@ __device__ __forceinline__ void head_dots(const CriticHeadParams& p, int seed, i
 // one lane then evaluates the algorithm's targets and dLoss/dq, and all GLUE_G warps emit
 // dh2 = (dq W3) * relu'(h2) for the critics whose backward starts here.
 template <int G>
-__global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+__device__ __forceinline__ void critic_head_body(const CriticHeadParams& p, int bx, int by) {
     constexpr int SPC = GLUE_WARPS / G;
-    pdl_wait();
-    const CriticHeadParams& p = *pp;
     __shared__ float s_vals[SPC][MAX_VALS];
     __shared__ float s_dq[SPC][MAX_VALS];
     __shared__ int s_goff[MAX_HEAD_SRC];
     __shared__ short s_pair_src[MAX_VALS], s_pair_hd[MAX_VALS];
     __shared__ int s_npairs;
-    const int seed = blockIdx.y;
+    const int seed = by;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = warp / G, g = warp % G;
     const int B = p.B, H = p.H;
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const Crit
     __syncthreads();
     for (int it = 0; it < p.iters; ++it) {                 // p.iters sample groups per CTA (many-seed launches)
     if (it > 0) group_sync<G>();                           // s_vals / s_dq are rewritten
-    const int b = (blockIdx.x * p.iters + it) * SPC + sl;
+    const int b = (bx * p.iters + it) * SPC + sl;
     const bool live = b < B;
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
     float* vals = s_vals[sl];
@@ -453,13 +457,19 @@ __global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const Crit
         const int g0 = s_goff[s];
 #pragma unroll 4
         for (int k = g * 32 + lane; k < H; k += 32 * G) {
-            const float hv = __ldg(h + k);
+            const float hv = ld_g(h + k);
             float acc = 0.f;
-            for (int hd = 0; hd < S.n_heads; ++hd) acc = fmaf(dqv[g0 + hd], __ldg(w + (long long)hd * H + k), acc);
+            for (int hd = 0; hd < S.n_heads; ++hd) acc = fmaf(dqv[g0 + hd], ld_g(w + (long long)hd * H + k), acc);
             out[k] = hv > 0.f ? acc : 0.f;
         }
     }
     }   // it
+}
+
+template <int G>
+__global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+    pdl_wait();
+    critic_head_body<G>(*pp, blockIdx.x, blockIdx.y);
 }
 
 // =====================================================================================
@@ -497,18 +507,17 @@ struct PolicyGradParams {
 // to the policy head outputs, and the policy's first backward step dh2 = (dhead Wh) * relu'(h2).
 // GLUE_G warps share one sample.  dyn smem: Wa [H*AS] | Wh [2A*H] | ga [SPC][A] | dhead [SPC][2A]  (AS = A | 1)
 template <int G>
-__global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
+__device__ __forceinline__ void policy_grad_body(const PolicyGradParams& p, int bx, int by, int bz) {
     constexpr int SPC = GLUE_WARPS / G;
     extern __shared__ __align__(16) float s_pg[];
-    pdl_wait();
-    const PolicyGradTask& T = p.tasks[blockIdx.y];
-    const int seed = blockIdx.z;
+    const PolicyGradTask& T = p.tasks[by];
+    const int seed = bz;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = warp / G, g = warp % G;
     const int A = p.A, H = p.H, B = p.B, O = p.O;
     const int AS = A | 1;                                   // odd stride: conflict-free column reads
     const int iters = p.iters;                              // sample groups per CTA: the staged weights serve all of them
-    const int b0 = blockIdx.x * iters * SPC + sl;      // this warp's sample in group it: b0 + it*SPC
+    const int b0 = bx * iters * SPC + sl;      // this warp's sample in group it: b0 + it*SPC
     const bool from_gemm = p.da_from_gemm != 0;             // dyn smem is then only the sga / sdh rows
     float* Wa = s_pg;
     float* Whs = Wa + (from_gemm ? 0 : H * AS);
@@ -522,7 +531,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradPar
                 float* sga = sga_all + (it * SPC + sl) * A;
                 for (int j = lane; j < A; j += 32) {
                     float acc = 0.f;
-                    for (int s = 0; s < T.n_src; ++s) acc += __ldg(resolve(p.as, T.da[s], seed) + (long long)b * T.da_ld + j);
+                    for (int s = 0; s < T.n_src; ++s) acc += ld_g(resolve(p.as, T.da[s], seed) + (long long)b * T.da_ld + j);
                     sga[j] = acc;
                 }
             }
@@ -541,7 +550,7 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradPar
             if (b < B) {
                 const float* __restrict__ dh = dh_base + (long long)b * H;
 #pragma unroll
-                for (int c = 0; c < GLUE_MAX_HR; ++c) dreg[c] = (lane + 32 * c < H) ? __ldg(dh + lane + 32 * c) : 0.f;
+                for (int c = 0; c < GLUE_MAX_HR; ++c) dreg[c] = (lane + 32 * c < H) ? ld_g(dh + lane + 32 * c) : 0.f;
             }
         };
         load_row(b0);
@@ -609,12 +618,18 @@ __global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradPar
         float* __restrict__ out = resolve(p.as, T.dhp2, seed) + (long long)b * H;
 #pragma unroll 2
         for (int n = g * 32 + lane; n < H; n += 32 * G) {
-            const float hv = __ldg(hp2 + n);
+            const float hv = ld_g(hp2 + n);
             float acc = 0.f;
             for (int j = 0; j < 2 * A; ++j) acc = fmaf(sdh[j], Whs[j * H + n], acc);
             out[n] = hv > 0.f ? acc : 0.f;
         }
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(GLUE_THREADS) policy_grad_kernel(PolicyGradParams p) {
+    pdl_wait();
+    policy_grad_body<G>(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 }  // namespace oac

@@ -22,6 +22,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
 #include "adam_stream.cuh"
+#include "mega.cuh"
 #include "oac_error.h"
 
 namespace oac {
@@ -165,6 +166,13 @@ struct OacTrainer {
     std::vector<void*> dev_allocs;
     long long work_cursor = 0;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    // single-launch step (mega.cuh)
+    void* mega_prog = nullptr;              // device MegaProgram
+    int mega_grid = 0, mega_phases = 0;
+    unsigned long long* mega_dbg = nullptr;
+    std::vector<std::string> mega_names;
+    int mega_dbg_calls = 0;
+    size_t mega_smem = 0;
     cudaStream_t side = nullptr;            // lane 1
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool use_graph = true;
@@ -173,6 +181,7 @@ struct OacTrainer {
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
+    bool allow_mega = false;   // OAC_MEGA=1: the whole latency-regime step as one cooperative kernel (mega.cuh; measured slower)
 };
 
 namespace oac {
@@ -878,6 +887,7 @@ static int finalize(OacTrainer& t) {
             const size_t budget = s.small_tiles ? 100 * 1024 : 208 * 1024;   // small tiles: keep 2 CTAs / SM
             while (kc > 16 && bytes_of(kc) > budget) kc = ((kc / 2) + 3) & ~3;
             s.kc = kc; s.smem = bytes_of(kc);
+            if (s.small_tiles) s.smem = std::max(s.smem, sizeof(float) * SK_KS * SK_BM * SK_PLD);   // the k-groups' partial tiles
             s.max_tiles = 0;
             for (auto& g : s.gemm) {
                 g.tiles_m = (g.M + bm - 1) / bm; g.tiles_n = (g.N + bm - 1) / bm;
@@ -993,9 +1003,9 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             }
             const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
             switch (sel) {
-                case 0: launch_pdl(gemm_stage_kernel<32, 32, 2, 2, false, false>, grid, dim3(256), s.smem, st, sp); break;
-                case 1: launch_pdl(gemm_stage_kernel<32, 32, 2, 2, false, true>, grid, dim3(256), s.smem, st, sp); break;
-                case 2: launch_pdl(gemm_stage_kernel<32, 32, 2, 2, true, true>, grid, dim3(256), s.smem, st, sp); break;
+                case 0: launch_pdl(gemm_sk_kernel<false, false>, grid, dim3(SK_THREADS), s.smem, st, sp); break;
+                case 1: launch_pdl(gemm_sk_kernel<false, true>, grid, dim3(SK_THREADS), s.smem, st, sp); break;
+                case 2: launch_pdl(gemm_sk_kernel<true, true>, grid, dim3(SK_THREADS), s.smem, st, sp); break;
                 case 3: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, false>, grid, dim3(256), s.smem, st, sp); break;
                 case 4: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, true>, grid, dim3(256), s.smem, st, sp); break;
                 default: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, true, true>, grid, dim3(256), s.smem, st, sp); break;
@@ -1031,6 +1041,138 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
     return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// single-launch step: phases, device program, cooperative grid size
+// ------------------------------------------------------------------------------------
+static size_t glue_smem(const OacTrainer& t, const Stage& s) {
+    const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
+    const int spc = GLUE_WARPS / s.glue_g, per_cta = spc * s.glue_iters;
+    if (s.kind == ST_POLICY_HEAD)
+        return sizeof(float) * (s.php.head_from_gemm ? (size_t)2 * A_ * spc : (size_t)2 * A_ * H_ + 2 * A_ * (1 + spc));
+    if (s.kind == ST_POLICY_GRAD)
+        return sizeof(float) * ((s.pgp.da_from_gemm ? 0 : (size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_) + (size_t)per_cta * 3 * A_);
+    return 0;
+}
+
+static int mega_plan(OacTrainer& t) {
+    const int seeds = t.cfg.n_seeds;
+    if (!t.allow_mega || t.cfg.gemm_path != OAC_GEMM_FP32 || (long long)seeds * t.cfg.batch > 1024) return 0;
+    for (const Stage& s : t.stages) {
+        if (s.kind == ST_GEMM) { if (s.use_tc || s.use_ws || !s.small_tiles || (s.a_trans && !s.b_trans)) return 0; }
+        else if (s.kind == ST_ADAM) return 0;
+        else if (s.glue_g != 4 || s.glue_iters != 1) return 0;
+    }
+    MegaProgram mp;
+    memset(&mp, 0, sizeof(mp));
+    size_t smem = 0;
+    std::vector<const Stage*> pending;                  // lane-1 stages waiting for a critical-chain stage to share a phase with
+    auto add_to = [&](MegaPhase& P, const Stage& s) -> int {
+        MegaStage& m = P.st[P.n++];
+        const int spc = GLUE_WARPS / s.glue_g;
+        if (s.kind == ST_GEMM) {
+            m.kind = s.a_trans ? MK_GEMM_TT : (s.b_trans ? MK_GEMM_NT : MK_GEMM_NN);
+            m.gx = s.max_tiles; m.gy = (int)s.gemm.size(); m.gz = seeds;
+            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
+            void* d = nullptr;
+            if (int e = upload(t, &sp, 1, &d)) return e;
+            m.params = d;
+            smem = std::max(smem, s.smem);
+        } else if (s.kind == ST_POLICY_HEAD) {
+            m.kind = MK_POLICY_HEAD;
+            m.gx = (s.max_rows + spc - 1) / spc; m.gy = (int)s.ph.size(); m.gz = seeds;
+            PolicyHeadParams p = s.php; p.iters = 1; p.use_external_eps = 0;
+            void* d = nullptr;
+            if (int e = upload(t, &p, 1, &d)) return e;
+            m.params = d;
+            smem = std::max(smem, glue_smem(t, s));
+        } else if (s.kind == ST_CRITIC_HEAD) {
+            m.kind = MK_CRITIC_HEAD;
+            m.gx = (t.cfg.batch + spc - 1) / spc; m.gy = seeds; m.gz = 1;
+            m.params = s.dev;
+        } else {
+            m.kind = MK_POLICY_GRAD;
+            m.gx = (t.cfg.batch + spc - 1) / spc; m.gy = (int)s.pg.size(); m.gz = seeds;
+            PolicyGradParams p = s.pgp; p.iters = 1;
+            void* d = nullptr;
+            if (int e = upload(t, &p, 1, &d)) return e;
+            m.params = d;
+            smem = std::max(smem, glue_smem(t, s));
+        }
+        m.nvb = m.gx * m.gy * m.gz;
+        P.total_vb += m.nvb;
+        return 0;
+    };
+    auto new_phase = [&]() -> MegaPhase* { return mp.n_phases < MEGA_MAX_PHASES ? &mp.ph[mp.n_phases++] : nullptr; };
+    auto flush_pending = [&]() -> int {                 // a join: what is still pending runs as phases of its own, in order
+        for (const Stage* ps : pending) {
+            MegaPhase* P = new_phase();
+            if (!P) return -1;
+            if (int e = add_to(*P, *ps)) return e;
+        }
+        pending.clear();
+        return 0;
+    };
+    for (const Stage& s : t.stages) {
+        if (s.lane == 1) { pending.push_back(&s); continue; }
+        if (s.join) { if (flush_pending()) return 0; }
+        MegaPhase* P = new_phase();
+        if (!P) return 0;
+        if (int e = add_to(*P, s)) return e;
+        if (!pending.empty()) {                         // the oldest independent stage shares this phase
+            const Stage* ps = pending.front();
+            pending.erase(pending.begin());
+            if (int e = add_to(*P, *ps)) return e;
+        }
+    }
+    if (flush_pending()) return 0;
+    // persistent grid: every CTA resident at once (cooperative launch), 2 per SM when registers / shared memory allow
+    cudaError_t ce = cudaFuncSetAttribute((const void*)step_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_mega_kernel, MEGA_THREADS, smem);
+    int dev = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (ce != cudaSuccess || per_sm < 1 || !coop) { cudaGetLastError(); return 0; }
+    unsigned* bar = nullptr;
+    OAC_CUDA(cudaMalloc(&bar, sizeof(unsigned)));
+    t.dev_allocs.push_back(bar);
+    OAC_CUDA(cudaMemset(bar, 0, sizeof(unsigned)));
+    mp.barrier = bar;
+    if (getenv("OAC_MEGA_DEBUG") && getenv("OAC_MEGA_DEBUG")[0] == '1') {
+        OAC_CUDA(cudaMalloc(&mp.dbg, sizeof(unsigned long long) * (2 * MEGA_MAX_PHASES + 1)));
+        t.dev_allocs.push_back(mp.dbg);
+        t.mega_dbg = mp.dbg;
+        int i = 0;
+        for (int ph = 0; ph < mp.n_phases; ++ph) {
+            std::string nm;
+            for (int k = 0; k < mp.ph[ph].n; ++k) nm += std::string(k ? " | " : "") + std::to_string(mp.ph[ph].st[k].nvb) + " vb kind " + std::to_string(mp.ph[ph].st[k].kind);
+            t.mega_names.push_back(nm);
+            ++i;
+        }
+    }
+    if (int e = upload(t, &mp, 1, &t.mega_prog)) return e;
+    t.mega_grid = std::min(per_sm, 2) * sm_count();
+    t.mega_phases = mp.n_phases;
+    t.mega_smem = smem;
+    return 0;
+}
+
+static int launch_mega(OacTrainer& t, int use_external_eps, cudaStream_t st) {
+    const MegaProgram* prog = (const MegaProgram*)t.mega_prog;
+    void* args[2] = {(void*)&prog, (void*)&use_external_eps};
+    OAC_CUDA(cudaLaunchCooperativeKernel((const void*)step_mega_kernel, dim3(t.mega_grid), dim3(MEGA_THREADS), args, t.mega_smem, st));
+    if (t.mega_dbg && ++t.mega_dbg_calls == 200) {           // measurement aid: one warm step, phase by phase
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(2 * MEGA_MAX_PHASES + 1);
+        cudaMemcpy(h.data(), t.mega_dbg, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+        for (int ph = 0; ph < t.mega_phases; ++ph)
+            fprintf(stderr, "[mega] phase %2d: work %6.2f us, barrier wait %6.2f us   (%s)\n", ph, (h[2 * ph + 1] - h[2 * ph]) * 1e-3,
+                    (h[2 * ph + 2] - h[2 * ph + 1]) * 1e-3, t.mega_names[ph].c_str());
+        fprintf(stderr, "[mega] total %.2f us, grid %d, smem %zu\n", (h[2 * t.mega_phases] - h[0]) * 1e-3, t.mega_grid, t.mega_smem);
+    }
+    return 0;
+}
+
 }  // namespace oac
 
 // =====================================================================================
@@ -1062,6 +1204,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
+    { const char* nm = getenv("OAC_MEGA"); t->allow_mega = (nm && nm[0] == '1'); }      // measured slower than the graph: opt-in
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
     else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
@@ -1086,9 +1229,9 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         const int big = 212 * 1024;
         cudaError_t e = cudaSuccess;
         auto opt_in = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, big); };
-        opt_in((const void*)gemm_stage_kernel<32, 32, 2, 2, false, false>);
-        opt_in((const void*)gemm_stage_kernel<32, 32, 2, 2, false, true>);
-        opt_in((const void*)gemm_stage_kernel<32, 32, 2, 2, true, true>);
+        opt_in((const void*)gemm_sk_kernel<false, false>);
+        opt_in((const void*)gemm_sk_kernel<false, true>);
+        opt_in((const void*)gemm_sk_kernel<true, true>);
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>);
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>);
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>);
@@ -1124,6 +1267,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         fe = finalize(*t);
     }
     if (fe) { oac_trainer_destroy(t); return fe; }
+    if (int e = mega_plan(*t)) { oac_trainer_destroy(t); return e; }
     { const char* np_ = getenv("OAC_PDL"); g_use_pdl = (np_ && np_[0] == '1'); }
     const char* ng = getenv("OAC_NO_GRAPH");
     t->use_graph = !(ng && ng[0] == '1');
@@ -1153,7 +1297,8 @@ extern "C" int oac_trainer_destroy(OacTrainer* t) {
 }
 
 extern "C" int oac_trainer_launches_per_step(const OacTrainer* t) {
-    return t ? (int)t->stages.size() : 0;
+    if (!t) return 0;
+    return t->mega_prog ? 1 : (int)t->stages.size();
 }
 
 extern "C" int oac_trainer_ws_stages(const OacTrainer* t) {
@@ -1166,6 +1311,7 @@ extern "C" int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* s
     if (!t) return set_error(OAC_E_INVALID, "null trainer");
     cudaStream_t st = (cudaStream_t)stream;
     const int gi = use_external_eps ? 1 : 0;
+    if (t->mega_prog) return launch_mega(*t, gi, st);          // the whole step is one cooperative kernel
     if (!t->use_graph) return launch_stages(*t, gi, st);
     if (!t->graph[gi]) {
         // capture on a private stream so the caller's stream state is untouched
@@ -1259,9 +1405,9 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
     s.gemm.push_back(g);
     {
         const int big = 212 * 1024;
-        cudaFuncSetAttribute((const void*)gemm_stage_kernel<32, 32, 2, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute((const void*)gemm_stage_kernel<32, 32, 2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute((const void*)gemm_stage_kernel<32, 32, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_sk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
