@@ -4,6 +4,7 @@
 // particles, G-OAC mean/std), and the policy-loss gradient w.r.t. the policy
 // outputs.  One warp per sample; everything is fp32.
 #pragma once
+#include <type_traits>
 #include "gemm_simt.cuh"
 #include "device_util.cuh"
 
@@ -500,6 +501,7 @@ struct PolicyGradParams {
     int O, A, H, B;
     int iters;        // sample groups (of GLUE_SPC samples) per CTA
     int da_from_gemm; // 1: dQ/da and the policy's dh2 run as tensor-core GEMM stages; this kernel is the chain rule only
+    int wa_sources;   // critics whose fc0 action columns are staged together (1 or 2)
 };
 
 // Fused: dLoss/d(action) through every critic's first layer (only the A action columns of fc0.weight are
@@ -520,7 +522,7 @@ __device__ __forceinline__ void policy_grad_body(const PolicyGradParams& p, int 
     const int b0 = bx * iters * SPC + sl;      // this warp's sample in group it: b0 + it*SPC
     const bool from_gemm = p.da_from_gemm != 0;             // dyn smem is then only the sga / sdh rows
     float* Wa = s_pg;
-    float* Whs = Wa + (from_gemm ? 0 : H * AS);
+    float* Whs = Wa + (from_gemm ? 0 : p.wa_sources * H * AS);
     float* sga_all = Whs + (from_gemm ? 0 : 2 * A * H);     // [iters][SPC][A]
     float* sdh_all = sga_all + iters * SPC * A;        // [iters][SPC][2A]
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
@@ -537,42 +539,68 @@ __device__ __forceinline__ void policy_grad_body(const PolicyGradParams& p, int 
             }
         }
     } else stage_contig(Whs, resolve(p.as, T.wh, seed), 2 * A * H);       // consumed in the last phase
-    for (int s = 0; s < T.n_src && !from_gemm; ++s) {
-        const float* __restrict__ w1 = resolve(p.as, T.w1[s], seed);
-        const int ld = T.ld[s];
-        __syncthreads();
-        // action columns of fc0.weight: row n -> Wa[n*AS + j]; one warp per row, lanes over j (no division)
-        for (int n = warp; n < H; n += GLUE_WARPS)
-            for (int j = lane; j < A; j += 32) cp_async4(Wa + n * AS + j, w1 + (long long)n * ld + O + j);
-        const float* __restrict__ dh_base = resolve(p.as, T.dh1[s], seed);
-        float dreg[GLUE_MAX_HR];
-        auto load_row = [&](int b) {
-            if (b < B) {
-                const float* __restrict__ dh = dh_base + (long long)b * H;
-#pragma unroll
-                for (int c = 0; c < GLUE_MAX_HR; ++c) dreg[c] = (lane + 32 * c < H) ? ld_g(dh + lane + 32 * c) : 0.f;
+    // dQ/da: the action columns of up to two critics' fc0.weight are staged together (the twin-critic case: one L2 round
+    // trip instead of two), more sources take turns.  HR = hidden / 32 registers per lane hold a dh1 row.
+    const int n_stage = p.wa_sources;                       // 1 or 2 (host: min(n_src, 2) when the shared memory fits)
+    auto dq_da = [&](auto hr_tag) {
+        constexpr int HR = decltype(hr_tag)::value;
+        for (int s0 = 0; s0 < T.n_src; s0 += n_stage) {
+            const int ns = min(n_stage, T.n_src - s0);
+            __syncthreads();
+            for (int u = 0; u < ns; ++u) {
+                const float* w1 = resolve(p.as, T.w1[s0 + u], seed);
+                const int ld = T.ld[s0 + u];
+                float* Wu = Wa + u * H * AS;
+                // row n -> Wu[n*AS + j]; one warp per row, lanes over j (no division)
+                for (int n = warp; n < H; n += GLUE_WARPS)
+                    for (int j = lane; j < A; j += 32) cp_async4(Wu + n * AS + j, w1 + (long long)n * ld + O + j);
             }
-        };
-        load_row(b0);
-        cp_async_wait_all();
-        __syncthreads();
-        for (int it = 0; it < iters; ++it) {
-            const int b = b0 + it * SPC;
-            float* sga = sga_all + (it * SPC + sl) * A;
-            if (b < B) {
-                for (int j = g; j < A; j += G) {
-                    float acc = 0.f;
+            float dreg[2][HR];
+            auto load_rows = [&](int b) {
+                if (b < B) {
 #pragma unroll
-                    for (int c = 0; c < GLUE_MAX_HR; ++c) {
-                        const int n = lane + 32 * c;
-                        if (n < H) acc = fmaf(dreg[c], Wa[n * AS + j], acc);
+                    for (int u = 0; u < 2; ++u) {
+                        if (u < ns) {
+                            const float* dh = resolve(p.as, T.dh1[s0 + u], seed) + (long long)b * H;
+#pragma unroll
+                            for (int c = 0; c < HR; ++c) dreg[u][c] = (lane + 32 * c < H) ? ld_g(dh + lane + 32 * c) : 0.f;
+                        }
                     }
-                    acc = warp_sum(acc);
-                    if (lane == 0) sga[j] = (s == 0 ? 0.f : sga[j]) + acc;  // column j belongs to warp g only
                 }
+            };
+            load_rows(b0);
+            cp_async_wait_all();
+            __syncthreads();
+            for (int it = 0; it < iters; ++it) {
+                const int b = b0 + it * SPC;
+                float* sga = sga_all + (it * SPC + sl) * A;
+                if (b < B) {
+                    for (int j = g; j < A; j += G) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (u < ns) {
+                                const float* Wu = Wa + u * H * AS + j;
+                                float au = 0.f;                 // per-critic sums are added in source order, as before
+#pragma unroll
+                                for (int c = 0; c < HR; ++c) {
+                                    const int n = lane + 32 * c;
+                                    if (HR * 32 <= 256 || n < H) au = fmaf(dreg[u][c], Wu[n * AS], au);
+                                }
+                                au = warp_sum(au);
+                                acc = (u == 0) ? au : acc + au;
+                            }
+                        }
+                        if (lane == 0) sga[j] = (s0 == 0 ? 0.f : sga[j]) + acc;  // column j belongs to warp g only
+                    }
+                }
+                if (it + 1 < iters) load_rows(b + SPC);
             }
-            if (it + 1 < iters) load_row(b + SPC);
         }
+    };
+    if (!from_gemm) {
+        if (H == 256) dq_da(std::integral_constant<int, 8>());
+        else dq_da(std::integral_constant<int, GLUE_MAX_HR>());
     }
     __syncthreads();
     for (int it = 0; it < iters; ++it) {

@@ -64,7 +64,7 @@ static int validate(const OacConfig& c) {
         return set_error(OAC_E_INVALID, "dims must be positive");
     if (c.act_dim > 128) return set_error(OAC_E_UNSUPPORTED, "act_dim > 128");
     if (c.hidden > 512) return set_error(OAC_E_UNSUPPORTED, "hidden > 512 (glue kernels keep a hidden row in registers)");
-    if ((size_t)c.hidden * (c.act_dim | 1) + (size_t)2 * c.act_dim * c.hidden + 16 * GLUE_WARPS * 3 * c.act_dim > 50000)
+    if ((size_t)2 * c.hidden * (c.act_dim | 1) + (size_t)2 * c.act_dim * c.hidden + 16 * GLUE_WARPS * 3 * c.act_dim > 50000)
         return set_error(OAC_E_UNSUPPORTED, "hidden*act_dim too large for the fused glue kernels' shared memory");
     if (c.algo == OAC_ALGO_POAC && (c.n_particles < 2 || c.n_particles > 16))
         return set_error(OAC_E_UNSUPPORTED, "P-OAC needs 2 <= n_particles <= 16");
@@ -937,6 +937,24 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// critics whose fc0 action columns the policy_grad kernel stages together: both of a twin pair, else one at a time
+static int pg_wa_sources(const OacTrainer& t, const Stage& s) {
+    int n = 0;
+    for (const auto& g : s.pg) n = std::max(n, g.n_src);
+    (void)t;
+    return n >= 2 ? 2 : 1;
+}
+static size_t glue_smem(const OacTrainer& t, const Stage& s) {
+    const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
+    const int spc = GLUE_WARPS / s.glue_g, per_cta = spc * s.glue_iters;
+    if (s.kind == ST_POLICY_HEAD)
+        return sizeof(float) * (s.php.head_from_gemm ? (size_t)2 * A_ * spc : (size_t)2 * A_ * H_ + 2 * A_ * (1 + spc));
+    if (s.kind == ST_POLICY_GRAD)
+        return sizeof(float) * ((s.pgp.da_from_gemm ? 0 : (size_t)pg_wa_sources(t, s) * H_ * (A_ | 1) + (size_t)2 * A_ * H_) +
+                                (size_t)per_cta * 3 * A_);
+    return 0;
+}
+
 static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStream_t st);
 
 // Runs the stage list.  Lane-1 stages go to the side stream: it is forked from the main stream at the first lane-1
@@ -1014,8 +1032,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps; p.iters = s.glue_iters;
             const int spc = GLUE_WARPS / s.glue_g, per_cta = spc * s.glue_iters;
             dim3 grid((s.max_rows + per_cta - 1) / per_cta, (unsigned)s.ph.size(), seeds);
-            const size_t smem = sizeof(float) * (p.head_from_gemm ? (size_t)2 * t.cfg.act_dim * spc
-                                                : (size_t)2 * t.cfg.act_dim * t.cfg.hidden + 2 * t.cfg.act_dim * (1 + spc));
+            const size_t smem = glue_smem(t, s);
             if (s.glue_g == 1) launch_pdl(policy_head_kernel<1>, grid, dim3(GLUE_THREADS), smem, st, p);
             else launch_pdl(policy_head_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
         } else if (s.kind == ST_ADAM) {
@@ -1028,11 +1045,10 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             if (s.glue_g == 1) launch_pdl(critic_head_kernel<1>, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
             else launch_pdl(critic_head_kernel<4>, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
         } else {
-            PolicyGradParams p = s.pgp; p.iters = s.glue_iters;
+            PolicyGradParams p = s.pgp; p.iters = s.glue_iters; p.wa_sources = pg_wa_sources(t, s);
             const int per_cta = (GLUE_WARPS / s.glue_g) * s.glue_iters;
             dim3 grid((t.cfg.batch + per_cta - 1) / per_cta, (unsigned)s.pg.size(), seeds);
-            const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
-            const size_t smem = sizeof(float) * ((p.da_from_gemm ? 0 : (size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_) + (size_t)per_cta * 3 * A_);
+            const size_t smem = glue_smem(t, s);
             if (s.glue_g == 1) launch_pdl(policy_grad_kernel<1>, grid, dim3(GLUE_THREADS), smem, st, p);
             else launch_pdl(policy_grad_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
         }
@@ -1044,16 +1060,6 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
 // ------------------------------------------------------------------------------------
 // single-launch step: phases, device program, cooperative grid size
 // ------------------------------------------------------------------------------------
-static size_t glue_smem(const OacTrainer& t, const Stage& s) {
-    const int A_ = t.cfg.act_dim, H_ = t.cfg.hidden;
-    const int spc = GLUE_WARPS / s.glue_g, per_cta = spc * s.glue_iters;
-    if (s.kind == ST_POLICY_HEAD)
-        return sizeof(float) * (s.php.head_from_gemm ? (size_t)2 * A_ * spc : (size_t)2 * A_ * H_ + 2 * A_ * (1 + spc));
-    if (s.kind == ST_POLICY_GRAD)
-        return sizeof(float) * ((s.pgp.da_from_gemm ? 0 : (size_t)H_ * (A_ | 1) + (size_t)2 * A_ * H_) + (size_t)per_cta * 3 * A_);
-    return 0;
-}
-
 static int mega_plan(OacTrainer& t) {
     const int seeds = t.cfg.n_seeds;
     if (!t.allow_mega || t.cfg.gemm_path != OAC_GEMM_FP32 || (long long)seeds * t.cfg.batch > 1024) return 0;
@@ -1092,7 +1098,7 @@ static int mega_plan(OacTrainer& t) {
         } else {
             m.kind = MK_POLICY_GRAD;
             m.gx = (t.cfg.batch + spc - 1) / spc; m.gy = (int)s.pg.size(); m.gz = seeds;
-            PolicyGradParams p = s.pgp; p.iters = 1;
+            PolicyGradParams p = s.pgp; p.iters = 1; p.wa_sources = pg_wa_sources(t, s);
             void* d = nullptr;
             if (int e = upload(t, &p, 1, &d)) return e;
             m.params = d;
