@@ -49,6 +49,19 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(seeds, gemm_path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant GEMM kernel per launch, from the committed
+    `ncu --set full` summary of the same configuration (profiles/traffic.json, written by tools/summarize_profiles.py);
+    None when that configuration was not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None
+    try:
+        return json.load(open(p)).get("%d:%s" % (seeds, gemm_path))
+    except Exception:
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -225,6 +238,32 @@ class _Group(object):
     api = "SACSeedGroup.gather(replay, host indices [S,256]) + .step() + D2H per-seed scalars, sync per step"
 
 
+def batched_brief(rb, dev, pk, S=64, steps=20):
+    from oac_explore_b200.seed_group import SACSeedGroup
+    grp = SACSeedGroup(list(range(S)), O, A, hidden=H, batch=B, gemm_path=GEMM_PATHS["tf32"], **HP)
+    idx = torch.from_numpy(np.random.randint(0, N_REPLAY, (steps + 3, S, B))).to(dev)
+    for i in range(3):
+        grp.gather(rb, idx[i]); grp.step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(3, 3 + steps):
+        grp.gather(rb, idx[i]); grp.step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    prof = grp.engine.profile(iters=5)
+    gemm_ms = sum(p[1] for p in prof if p[2])
+    flops = FLOP_PER_UPDATE["sac"] * S
+    tf32_peak = pk["bf16"] / 2.0
+    return {"seeds_per_gpu": S, "gemm_path": "tf32", "value": S / (ms * 1e-3), "unit": "seed-updates/s", "ms_per_step": ms,
+            "launches_per_step": grp.engine.launches_per_step + 1, "tma_tcgen05_stages": grp.engine.ws_stages,
+            "roofline": {"bound": "tensor", "kernel": "gemm_ws_kernel (TMA + tcgen05 kind::tf32), all GEMM stages of one step",
+                         "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": flops / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "whole_step_frac": flops / (ms * 1e-3) / 1e12 / tf32_peak,
+                         "traffic": ncu_traffic(S, "tf32")}}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from oac_explore_b200.replay_buffer import ReplayBuffer
@@ -302,7 +341,7 @@ def run_ours(args):
     if rank == 0:
         # ---------------- roofline of the dominant kernel + cpu baseline (rank 0, N=1 only) --------
         pk = peaks()
-        roof, cpu = None, None
+        roof, cpu, roof_b = None, None, None
         if world == 1:
             if S == 1:
                 scratch = build_trainer(args.algo, seed=99)
@@ -319,12 +358,13 @@ def run_ours(args):
             all_ms = sum(p[1] for p in prof)
             tf32_peak = pk["bf16"] / 2.0          # kind::tf32 runs at half the bf16 rate
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-            kname = {0: "gemm_stage_kernel (fp32 SIMT FFMA)", 1: "gemm_tc_kernel (tcgen05 kind::tf32, TMEM accumulators)",
+            kname = {0: "gemm_sk_kernel (fp32 FFMA, 4-way split-K 32x32 tiles)" if S * B <= 1024 else "gemm_stage_kernel (fp32 FFMA)",
+                     1: "gemm_ws_kernel (TMA + tcgen05 kind::tf32, warp-specialised, TMEM accumulators)",
                      2: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32 split, TMEM accumulators)"}[GEMM_PATH]
             roof = {"bound": "tensor", "kernel": kname + ", all GEMM stages of one step",
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                     "peak_source": "%s bf16 %.1f TFLOP/s / 2 (tf32 rate)" % (pk["source"], pk["bf16"]),
-                    "traffic": None, "share_of_step_kernel_time": gemm_ms / all_ms,
+                    "traffic": ncu_traffic(S, args.gemm_path), "share_of_step_kernel_time": gemm_ms / all_ms,
                     "algorithmic_flops_per_step": FLOP_PER_UPDATE[args.algo] * S, "executed_flops_per_step": gemm_flops,
                     "stages_ms": {p[0] + "#%d" % i: round(p[1], 5) for i, p in enumerate(prof)}}
             # replay gather: HBM roofline, timed alone over many launches
@@ -340,6 +380,20 @@ def run_ours(args):
                                      "unit": "GB/s", "frac": S * GATHER_BYTES / (g_ms * 1e-3) / 1e9 / pk["hbm"],
                                      "us_per_launch": g_ms * 1e3, "algorithmic_bytes": S * GATHER_BYTES,
                                      "note": "launch time includes the Python/ctypes call overhead at S=1"}
+            if S > 1:
+                # config 5 is HBM-bound before it is tensor-bound: algorithmic state traffic per seed-update
+                # = read 838 695 W + r/w 1 009 738 m,v + write 504 869 + 333 826 W floats = 14.8 MB
+                state_bytes = 4.0 * (838695 + 2 * 1009738 + 504869 + 333826)
+                hb = S * state_bytes / (ms_dev / K * 1e-3) / 1e9
+                roof["hbm_state_traffic"] = {"bound": "hbm", "achieved": hb, "peak": pk["hbm"], "unit": "GB/s", "frac": hb / pk["hbm"],
+                                             "algorithmic_bytes_per_seed_update": state_bytes,
+                                             "note": "whole step: weights + Adam state only; activations (~28 MB per seed-update at "
+                                                     "64 seeds) also stream through HBM"}
+            else:
+                # the batched-seed configuration (BASELINE config 5) in brief, so that the default run also shows the
+                # tensor-core path: 64 seeds, TMA + tcgen05 kind::tf32, device-resident timing
+                del scratch, se
+                roof_b = batched_brief(rb, dev, pk)
             threads = os.cpu_count() or 1
             n_cpu = 150
             rate_all, _ = cpu_reference_rate(n_cpu, 5, threads)
@@ -368,6 +422,8 @@ def run_ours(args):
                 "launches_per_step": e.launches_per_step + 1}
         if roof is not None:
             line["roofline"] = roof
+        if roof_b is not None:
+            line["batched_seeds"] = roof_b
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -18,7 +18,7 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "dram__bytes_read.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
-        "launch__shared_mem_per_block_dynamic", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum"]
 
 
@@ -60,9 +60,35 @@ def full_report(rep, out_name):
     print(out_name, "written,", len(rows) - 2, "launches")
 
 
+def traffic(rep, kernel_substr):
+    """dram read+write bytes per launch of the longest launch of the named kernel in a --set full report."""
+    path = os.path.join(G, rep)
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    best = None
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if kernel_substr not in d.get("Kernel Name", ""):
+            continue
+        t = float(d["gpu__time_duration.sum"].replace(",", ""))
+        if best is None or t > best[0]:
+            u = dict(zip(hdr, units))
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(d["dram__bytes_read.sum"].replace(",", "")) * scale[u["dram__bytes_read.sum"]]
+            wr = float(d["dram__bytes_write.sum"].replace(",", "")) * scale[u["dram__bytes_write.sum"]]
+            best = (t, rd + wr)
+    return None if best is None else best[1]
+
+
 if __name__ == "__main__":
-    launch_list("r01_launches_sac_fp32.csv", 14)
-    launch_list("r01_launches_64seeds_tf32.csv", 14)
-    full_report("r01_gemm_simt.ncu-rep", "r01_gemm_simt_full.txt")
-    full_report("r01_gemm_tc_64seeds.ncu-rep", "r01_gemm_tc_64seeds_full.txt")
-    full_report("r01_gather.ncu-rep", "r01_replay_gather_full.txt")
+    import json
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01f"
+    launch_list(tag + "_launches_single_fp32.csv", 17)
+    launch_list(tag + "_launches_64seeds_tf32.csv", 19)
+    full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
+    full_report(tag + "_64seeds_tf32.ncu-rep", tag + "_64seeds_tf32_full.txt")
+    tr = {"1:fp32": traffic(tag + "_single_fp32.ncu-rep", "gemm_sk_kernel"),
+          "64:tf32": traffic(tag + "_64seeds_tf32.ncu-rep", "gemm_ws_kernel")}
+    json.dump(tr, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    print(tr)
