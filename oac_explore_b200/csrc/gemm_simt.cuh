@@ -56,6 +56,15 @@ struct AdamScalars {
     int do_polyak;
 };
 
+// beta^t for integer t by squaring (double): agrees with pow() to ~1e-15 relative, far below the fp32 rounding of
+// the two scalars derived from it, at a few dozen DP multiplies instead of two DP pow() calls -- which cost ~4 us on
+// one thread and sat on the critical path of every Adam stage of the single-seed step.
+__device__ __forceinline__ double ipow(double b, int t) {
+    double r = 1.0;
+    while (t > 0) { if (t & 1) r *= b; b *= b; t >>= 1; }
+    return r;
+}
+
 __device__ __forceinline__ AdamScalars make_adam_scalars(const AdamHyper& h, float lr, int t, int train_steps_done) {
     AdamScalars s;
     double b1 = (double)h.beta1, b2 = (double)h.beta2;
@@ -63,8 +72,8 @@ __device__ __forceinline__ AdamScalars make_adam_scalars(const AdamHyper& h, flo
     // Recover them by rounding to 6 decimals (exact for the defaults and any sane setting).
     b1 = rint(b1 * 1e6) * 1e-6;
     b2 = rint(b2 * 1e6) * 1e-6;
-    double bc1 = 1.0 - pow(b1, (double)t);
-    double bc2 = 1.0 - pow(b2, (double)t);
+    double bc1 = 1.0 - ipow(b1, t);
+    double bc2 = 1.0 - ipow(b2, t);
     s.step_size = (float)((double)lr / bc1);
     s.bc2_sqrt = (float)sqrt(bc2);
     s.beta1 = (float)b1; s.beta2 = (float)b2;
@@ -351,7 +360,7 @@ template <bool AT, bool BT>
 __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int by, int bz) {
     extern __shared__ __align__(16) float smem[];
     __shared__ AdamScalars s_adam;
-    __shared__ float s_bsum[SK_KS][SK_BM];
+    __shared__ float s_bsum[8][SK_BM];
 
     const GemmTask& T = sp.tasks[by];
     const int tile = bx;
@@ -378,17 +387,11 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     float* Bs = smem + (AT ? kc * SK_BM : SK_BM * kp);
 
     const bool is_adam = T.epi == EPI_ADAM;
-    if (is_adam && tid == 0) {
-        int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
-        int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
-        s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
-    }
     float acc[SK_T][SK_T];
 #pragma unroll
     for (int i = 0; i < SK_T; ++i)
 #pragma unroll
         for (int j = 0; j < SK_T; ++j) acc[i][j] = 0.f;
-    float bsum[SK_T] = {0.f, 0.f, 0.f, 0.f};
     const bool bias_on = AT && is_adam && T.has_bias && tn == 0;
     // rows / columns of this thread: adjacent for an M/N-contiguous operand (one LDS.128 per k), interleaved by 8 for a
     // K-contiguous one (conflict-free LDS.128 along k)
@@ -403,6 +406,11 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
         else     stage_tile<SK_THREADS>(As, a_ld, A, lda, k0, kn4, K, m0, SK_BM, M, a_vec);
         if (!BT) stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, n0, SK_BN, N, k0, kn, K, b_vec);
         else     stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, k0, kn4, K, n0, SK_BN, N, b_vec);
+        if (is_adam && k0 == 0 && tid == 0) {      // the step's Adam scalars: computed while the operand loads fly
+            int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
+            int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
+            s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
+        }
         cp_async_wait_all();
         __syncthreads();
         const int ks = ((kn4 >> 2) + SK_KS - 1) / SK_KS * 4;          // this chunk's k per group (multiple of 4)
@@ -455,11 +463,17 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
                     for (int j = 0; j < SK_T; ++j) b[j] = Bs[(c0 + j * cs) * b_ld + k];
                 }
 #pragma unroll
-                for (int i = 0; i < SK_T; ++i) {
-                    if (bias_on) bsum[i] += a[i];
+                for (int i = 0; i < SK_T; ++i)
 #pragma unroll
                     for (int j = 0; j < SK_T; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-                }
+            }
+            // bias gradient = column sums of the staged dY^T tile: 8 k-slices x 32 rows, one thread each (kept out of the
+            // FFMA loop, where it cost 4 FADD per k on every thread)
+            if (bias_on) {
+                const int br = tid & 31, bs_ = tid >> 5;
+                float sum = 0.f;
+                for (int k = bs_; k < kn; k += 8) sum += As[k * a_ld + br];
+                s_bsum[bs_][br] = (k0 == 0 ? 0.f : s_bsum[bs_][br]) + sum;
             }
         }
     }
@@ -471,10 +485,6 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     for (int i = 0; i < SK_T; ++i)
 #pragma unroll
         for (int j = 0; j < SK_T; ++j) part[(kg * SK_BM + r0 + i * rs) * SK_PLD + c0 + j * cs] = acc[i][j];
-    if (bias_on && tx == 0) {
-#pragma unroll
-        for (int i = 0; i < SK_T; ++i) s_bsum[kg][r0 + i * rs] = bsum[i];
-    }
     __syncthreads();
     // ---- epilogue: thread -> one row, 4 adjacent columns ----
     const int er = tid >> 3, ec = (tid & 7) << 2;
@@ -496,16 +506,39 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
         float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
         float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
         const AdamScalars s = s_adam;
+        const long long e0 = (long long)m * ldc + n0 + ec;
+        float* pm = m1 + T.adam_off + e0;
+        float* pv = m2 + T.adam_off + e0;
+        float* pt = (T.target_off >= 0 && s.do_polyak) ? pbase + T.target_off + e0 : nullptr;
+        const bool vec = (n0 + ec + 3 < N) && ((ldc & 3) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(C + e0) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv) |
+                            reinterpret_cast<uintptr_t>(pt)) & 15) == 0);
+        if (vec) {
+            // one 16-byte load per array instead of four dependent scalar round trips (the loads of element j+1 may not
+            // pass the stores of element j: 40 % of this kernel's stall samples sat on them, profiles/r01f)
+            float4 p4 = *reinterpret_cast<const float4*>(C + e0);
+            float4 a4 = *reinterpret_cast<const float4*>(pm);
+            float4 v4 = *reinterpret_cast<const float4*>(pv);
+            float4 t4 = pt ? *reinterpret_cast<const float4*>(pt) : make_float4(0.f, 0.f, 0.f, 0.f);
+            adam_update(v[0], &p4.x, &a4.x, &v4.x, pt ? &t4.x : nullptr, s);
+            adam_update(v[1], &p4.y, &a4.y, &v4.y, pt ? &t4.y : nullptr, s);
+            adam_update(v[2], &p4.z, &a4.z, &v4.z, pt ? &t4.z : nullptr, s);
+            adam_update(v[3], &p4.w, &a4.w, &v4.w, pt ? &t4.w : nullptr, s);
+            *reinterpret_cast<float4*>(C + e0) = p4;
+            *reinterpret_cast<float4*>(pm) = a4;
+            *reinterpret_cast<float4*>(pv) = v4;
+            if (pt) *reinterpret_cast<float4*>(pt) = t4;
+        } else {
 #pragma unroll
-        for (int j = 0; j < SK_T; ++j) {
-            const int n = n0 + ec + j;
-            if (n >= N) continue;
-            const long long e = (long long)m * ldc + n;
-            float* tgt = T.target_off >= 0 ? pbase + T.target_off + e : nullptr;
-            adam_update(v[j], C + e, m1 + T.adam_off + e, m2 + T.adam_off + e, tgt, s);
+            for (int j = 0; j < SK_T; ++j) {
+                if (n0 + ec + j >= N) continue;
+                adam_update(v[j], C + e0 + j, pm + j, pv + j, pt ? pt + j : nullptr, s);
+            }
         }
         if (bias_on && ec == 0) {
-            const float bs_ = ((s_bsum[0][er] + s_bsum[1][er]) + s_bsum[2][er]) + s_bsum[3][er];
+            float bs_ = s_bsum[0][er];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) bs_ += s_bsum[g][er];
             float* pb = resolve(sp.as, T.bias, seed) + m;
             float* tgt = T.target_bias_off >= 0 ? pbase + T.target_bias_off + m : nullptr;
             if (T.train_bias) {

@@ -82,13 +82,6 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-// beta^t for integer t by squaring (double): agrees with pow() to ~1e-15 relative, far below the fp32 rounding of
-// the two scalars derived from it, at a few dozen DP multiplies instead of a DP pow per tile.
-__device__ __forceinline__ double ipow(double b, int t) {
-    double r = 1.0;
-    while (t > 0) { if (t & 1) r *= b; b *= b; t >>= 1; }
-    return r;
-}
 __device__ __forceinline__ AdamScalars make_adam_scalars_fast(const AdamHyper& h, float lr, int t, int train_steps_done) {
     AdamScalars s;
     const double b1 = rint((double)h.beta1 * 1e6) * 1e-6, b2 = rint((double)h.beta2 * 1e6) * 1e-6;
