@@ -551,9 +551,14 @@ __device__ __forceinline__ void policy_grad_body(const PolicyGradParams& p, int 
                 const float* w1 = resolve(p.as, T.w1[s0 + u], seed);
                 const int ld = T.ld[s0 + u];
                 float* Wu = Wa + u * H * AS;
-                // row n -> Wu[n*AS + j]; one warp per row, lanes over j (no division)
-                for (int n = warp; n < H; n += GLUE_WARPS)
-                    for (int j = lane; j < A; j += 32) cp_async4(Wu + n * AS + j, w1 + (long long)n * ld + O + j);
+                // element (n, j) -> Wu[n*AS + j], flat over the H*A elements with every lane busy; (n, j) advance
+                // incrementally (one division per thread, none per element)
+                const int dn = GLUE_THREADS / A, dj = GLUE_THREADS - dn * A;
+                int n = (int)threadIdx.x / A, j = (int)threadIdx.x - n * A;
+                for (; n < H; n += dn, j += dj) {
+                    if (j >= A) { j -= A; ++n; if (n >= H) break; }
+                    cp_async4(Wu + n * AS + j, w1 + (long long)n * ld + O + j);
+                }
             }
             float dreg[2][HR];
             auto load_rows = [&](int b) {
