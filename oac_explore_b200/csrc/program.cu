@@ -146,8 +146,9 @@ struct Stage {
     int max_rows = 0;
     int glue_iters = 1;         // glue kernels: sample groups per CTA (> 1 when many seeds share a launch)
     int glue_g = 4;             // ... and warps cooperating on one sample
-    // two-lane schedule (latency regime): lane 1 stages run on a side stream, forked from the main lane where they are
-    // listed and joined before the first later stage that sets `join` (or at the end of the step)
+    // multi-lane schedule (latency regime): lane 1 / 2 stages run on side streams; each waits for the main lane's
+    // position where it is listed (and for its own lane's earlier stages).  `join` is a bit mask of the side lanes the
+    // main lane waits for before this stage (bit 0: lane 1, bit 1: lane 2); everything is joined at the end of the step.
     int lane = 0, join = 0;
     const char* name = "";
 };
@@ -173,8 +174,8 @@ struct OacTrainer {
     std::vector<std::string> mega_names;
     int mega_dbg_calls = 0;
     size_t mega_smem = 0;
-    cudaStream_t side = nullptr;            // lane 1
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};            // lanes 1, 2
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     bool use_graph = true;
     int n_opt = 0;
     long long* tc_dbg = nullptr;
@@ -499,7 +500,7 @@ void Builder::build_sac() {
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
     }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2"); s.join = 1;
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2"); s.join = 3;
       memset(&s.chp, 0, sizeof(s.chp));
       s.chp.src[0] = head_src(q1, ca1, 0); s.chp.src[1] = head_src(q2, ca2, 0);
       s.chp.src[2] = head_src(q1, ca1, B); s.chp.src[3] = head_src(q2, ca2, B);
@@ -509,12 +510,19 @@ void Builder::build_sac() {
       // mode A (torch 1.4) multiplies by the POST-step W3 -> separate stage after the critic Adam
       if (mode_b) s.chp.src[0].write_dh2 = s.chp.src[1].write_dh2 = 1;
       s.chp.n_src = 6; fill_chp(s, CM_SAC, 2); }
+    if (two_lanes && !mode_b) {
+        // mode A: pi_dh2 needs the POST-step head weights, and the head gradient (dq^T h2) is complete after critic_head:
+        // head Adam + pi_dh2 leave the critical chain for lane 2 and run next to qloss_dh1 / the fc1 Adam
+        { Stage& s = add_stage(ST_GEMM, "critic_adam_head"); s.lane = 2;
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 4); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 4); }
+        { Stage& s = add_stage(ST_GEMM, "pi_dh2"); s.lane = 2; crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
+    }
     { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); crit_dh1(s, q1, ca1, B); crit_dh1(s, q2, ca2, B);
       if (mode_b) { crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); } }
     auto policy_grad_stage = [&]() {
         if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
         Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
-        s.join = 1;
+        s.join = 3;
         s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic, {ca1.da, ca2.da}));
         fill_pgp(s);
         if (tensor_glue) { Stage& s2 = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s2, pol, pa, 0, pg); }
@@ -526,16 +534,16 @@ void Builder::build_sac() {
         // the (largest) fc0 Adam runs on lane 1 next to the two dX stages
         { Stage& s = add_stage(ST_GEMM, "critic_adam_fc0"); s.lane = 1;
           crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 1); }
-        { Stage& s = add_stage(ST_GEMM, "critic_adam_fc1+head");
-          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 6); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 6); }
+        { Stage& s = add_stage(ST_GEMM, "critic_adam_fc1");
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 2); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 2); }
     } else {
     { Stage& s = add_stage(ST_GEMM, "critic_adam");
       crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
     flush_adam("critic_adam_apply");
     }
     if (!mode_b) {
-        { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
-        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
+        if (!two_lanes) { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
+        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); s.join = 2; crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
         policy_grad_stage();
     }
     { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
@@ -961,29 +969,31 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
 // stage after a join (event record / wait, which also works under stream capture: the side stream joins the capture),
 // and joined back before a stage that asks for it and at the end of the step.
 static int launch_stages(OacTrainer& t, int use_external_eps, cudaStream_t main_st) {
-    bool side_busy = false;
-    auto join = [&]() -> int {
-        if (!side_busy) return 0;
-        OAC_CUDA(cudaEventRecord(t.ev_join, t.side));
-        OAC_CUDA(cudaStreamWaitEvent(main_st, t.ev_join, 0));
-        side_busy = false;
+    bool busy[2] = {false, false};
+    auto join = [&](int mask) -> int {
+        for (int l = 0; l < 2; ++l) {
+            if (!(mask & (1 << l)) || !busy[l]) continue;
+            OAC_CUDA(cudaEventRecord(t.ev_join[l], t.side[l]));
+            OAC_CUDA(cudaStreamWaitEvent(main_st, t.ev_join[l], 0));
+            busy[l] = false;
+        }
         return 0;
     };
     for (Stage& s : t.stages) {
         cudaStream_t st = main_st;
-        if (s.lane == 1 && t.side != nullptr) {
-            if (!side_busy) {
-                OAC_CUDA(cudaEventRecord(t.ev_fork, main_st));
-                OAC_CUDA(cudaStreamWaitEvent(t.side, t.ev_fork, 0));
-                side_busy = true;
-            }
-            st = t.side;
+        if (s.lane >= 1 && t.side[s.lane - 1] != nullptr) {
+            const int l = s.lane - 1;
+            // the side lane picks up the main lane's current position (under capture: a dependency edge)
+            OAC_CUDA(cudaEventRecord(t.ev_fork[l], main_st));
+            OAC_CUDA(cudaStreamWaitEvent(t.side[l], t.ev_fork[l], 0));
+            busy[l] = true;
+            st = t.side[l];
         } else if (s.join) {
-            if (int e = join()) return e;
+            if (int e = join(s.join)) return e;
         }
         if (int e = launch_stage(t, s, use_external_eps, st)) return e;
     }
-    return join();
+    return join(3);
 }
 
 static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStream_t st) {
@@ -1119,7 +1129,7 @@ static int mega_plan(OacTrainer& t) {
         return 0;
     };
     for (const Stage& s : t.stages) {
-        if (s.lane == 1) { pending.push_back(&s); continue; }
+        if (s.lane >= 1) { pending.push_back(&s); continue; }
         if (s.join) { if (flush_pending()) return 0; }
         MegaPhase* P = new_phase();
         if (!P) return 0;
@@ -1278,12 +1288,12 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     const char* ng = getenv("OAC_NO_GRAPH");
     t->use_graph = !(ng && ng[0] == '1');
     {
-        bool lanes = false;
-        for (const Stage& s : t->stages) lanes = lanes || s.lane == 1;
-        if (lanes) {
-            cudaError_t e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
+        int lanes = 0;
+        for (const Stage& s : t->stages) lanes = std::max(lanes, s.lane);
+        for (int l = 0; l < lanes && l < 2; ++l) {
+            cudaError_t e = cudaStreamCreateWithFlags(&t->side[l], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork[l], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join[l], cudaEventDisableTiming);
             if (e != cudaSuccess) { oac_trainer_destroy(t); return set_cuda_error(e, "side stream"); }
         }
     }
@@ -1294,9 +1304,11 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
 extern "C" int oac_trainer_destroy(OacTrainer* t) {
     if (!t) return 0;
     for (int i = 0; i < 2; ++i) if (t->graph[i]) cudaGraphExecDestroy(t->graph[i]);
-    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
-    if (t->ev_join) cudaEventDestroy(t->ev_join);
-    if (t->side) cudaStreamDestroy(t->side);
+    for (int l = 0; l < 2; ++l) {
+        if (t->ev_fork[l]) cudaEventDestroy(t->ev_fork[l]);
+        if (t->ev_join[l]) cudaEventDestroy(t->ev_join[l]);
+        if (t->side[l]) cudaStreamDestroy(t->side[l]);
+    }
     for (void* p : t->dev_allocs) cudaFree(p);
     delete t;
     return 0;
