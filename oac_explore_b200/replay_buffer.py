@@ -126,19 +126,36 @@ class ReplayBuffer(object):
     def _draw_indices(self, batch_size):
         return np.random.randint(0, self._size, batch_size)
 
+    # The gather kernel reads the int64 indices straight from pinned host memory (unified addressing: a pinned
+    # allocation is device-accessible under the same pointer), so a batch costs no host->device copy call.  The host
+    # runs ahead of the device (nothing on this path synchronises), so the indices go through a ring of pinned slots;
+    # a slot group is only reused after the gathers that read it have completed (one event per group).
+    _RING_GROUPS, _RING_GROUP_SLOTS = 4, 256
+
     def _upload_indices(self, indices):
         n = len(indices)
-        if self._idx_host is None or self._idx_host.shape[0] < n:
-            self._idx_host = torch.zeros(n, dtype=torch.int64).pin_memory()
-            self._idx_dev = torch.zeros(n, dtype=torch.int64, device=self._device)
+        if self._idx_host is None or self._idx_host.shape[1] < n:
+            slots = self._RING_GROUPS * self._RING_GROUP_SLOTS
+            self._idx_host = torch.zeros((slots, n), dtype=torch.int64).pin_memory()
             self._idx_np = self._idx_host.numpy()
-        if n == self._idx_host.shape[0]:
-            self._idx_np[:] = indices
-            self._idx_dev.copy_(self._idx_host, non_blocking=True)
-        else:
-            self._idx_np[:n] = indices
-            self._idx_dev[:n].copy_(self._idx_host[:n], non_blocking=True)
-        return self._idx_dev
+            self._idx_slot = 0
+            self._idx_events = [None] * self._RING_GROUPS
+        slot = self._idx_slot
+        g, in_g = divmod(slot, self._RING_GROUP_SLOTS)
+        if in_g == 0 and self._idx_events[g] is not None:
+            self._idx_events[g].synchronize()               # the device is done with this group's previous round
+        self._idx_np[slot, :n] = indices
+        self._idx_last_slot = slot
+        self._idx_slot = (slot + 1) % (self._RING_GROUPS * self._RING_GROUP_SLOTS)
+        return self._idx_host[slot]
+
+    def _indices_consumed(self):
+        """Call after the kernel reading the last uploaded slot has been launched."""
+        g, in_g = divmod(self._idx_last_slot, self._RING_GROUP_SLOTS)
+        if in_g == self._RING_GROUP_SLOTS - 1:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._idx_events[g] = ev
 
     def _gather_desc(self, engine, seed, n_seeds):
         key = (id(engine), seed, n_seeds)
@@ -190,8 +207,11 @@ class ReplayBuffer(object):
             tr._ensure_engine(batch_size)
             e = tr._engine
             self.gather_into(e, idx_dev, batch_size)
+            self._indices_consumed()
             return self._resident_views(e, batch_size)
-        return self._numpy_batch(self.gather_dense(idx_dev, batch_size))
+        out = self.gather_dense(idx_dev, batch_size)
+        self._indices_consumed()
+        return self._numpy_batch(out)
 
     def gather_dense(self, idx_dev, batch_size):
         """Five dense fp32 device tensors (the "fast" return type of SURVEY.md section 8b)."""
