@@ -18,25 +18,48 @@ constexpr int EX_THREADS = 512;
 constexpr int EX_WARPS = EX_THREADS / 32;
 constexpr int EX_MAX_H = 512;
 
-// out[n] = act(sum_k W[n*ld + k] x[k] + b[n]) for n in [0,N): one warp per output row
+// out[n] = act(sum_k W[n*ld + k] x[k] + b[n]) for n in [0,N): one warp per output row, FOUR rows at a time -- the
+// loads of four rows (12 x 16 B per lane at K = 376) are in flight before the first reduction, so a layer costs ~4
+// L2 round trips per warp instead of 16 (the batch-1 exploration kernel is pure load latency: 2 MB of weights, 1.3 MFLOP)
 __device__ __forceinline__ void gemv_rows(const float* __restrict__ W, int ld, const float* __restrict__ b,
                                           const float* x, int K, int N, float* out, bool relu_) {
+    constexpr int RB = 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
     const int K4 = vec ? (K & ~3) : 0;
-    for (int n = warp; n < N; n += EX_WARPS) {
-        const float* w = W + (long long)n * ld;
-        float acc = 0.f;
+    for (int n0 = warp * RB; n0 < N; n0 += EX_WARPS * RB) {
+        float acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
         for (int k = lane * 4; k < K4; k += 128) {
-            float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
-            acc = fmaf(wv.x, x[k], acc); acc = fmaf(wv.y, x[k + 1], acc);
-            acc = fmaf(wv.z, x[k + 2], acc); acc = fmaf(wv.w, x[k + 3], acc);
+            float4 wv[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                wv[r] = (n0 + r < N) ? __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ld + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float x0 = x[k], x1 = x[k + 1], x2 = x[k + 2], x3 = x[k + 3];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                acc[r] = fmaf(wv[r].x, x0, acc[r]); acc[r] = fmaf(wv[r].y, x1, acc[r]);
+                acc[r] = fmaf(wv[r].z, x2, acc[r]); acc[r] = fmaf(wv[r].w, x3, acc[r]);
+            }
         }
-        for (int k = K4 + lane; k < K; k += 32) acc = fmaf(__ldg(w + k), x[k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            float v = acc + __ldg(b + n);
-            out[n] = relu_ ? fmaxf(v, 0.f) : v;
+        for (int k = K4 + lane; k < K; k += 32) {
+            const float xk = x[k];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                if (n0 + r < N) acc[r] = fmaf(__ldg(W + (long long)(n0 + r) * ld + k), xk, acc[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        }
+        if (lane < RB && n0 + lane < N) {
+            float sel = acc[0];
+#pragma unroll
+            for (int r = 1; r < RB; ++r) sel = (lane == r) ? acc[r] : sel;
+            const float v = sel + __ldg(b + n0 + lane);
+            out[n0 + lane] = relu_ ? fmaxf(v, 0.f) : v;
         }
     }
 }
@@ -49,14 +72,23 @@ __device__ __forceinline__ void gemv_cols(const float* __restrict__ W, int ld, i
     float acc[EX_MAX_H / 32];
 #pragma unroll
     for (int c = 0; c < EX_MAX_H / 32; ++c) acc[c] = 0.f;
-    for (int n = warp; n < N; n += EX_WARPS) {
-        const float vn = v[n];
-        if (vn == 0.f) continue;                       // ReLU-masked rows contribute nothing
-        const float* w = W + (long long)n * ld + col0;
+    // four rows at a time: their loads are issued together (one L2 round trip per four rows); ReLU-masked rows
+    // (vn == 0) are skipped without touching their weights
+    constexpr int RB = 4;
+    for (int n0 = warp * RB; n0 < N; n0 += EX_WARPS * RB) {
+        float vn[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) vn[r] = (n0 + r < N) ? v[n0 + r] : 0.f;
 #pragma unroll
         for (int c = 0; c < EX_MAX_H / 32; ++c) {
-            int k = c * 32 + lane;
-            if (k < K) acc[c] = fmaf(vn, __ldg(w + k), acc[c]);
+            const int k = c * 32 + lane;
+            if (c * 32 >= K) break;
+            float wv[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                wv[r] = (k < K && vn[r] != 0.f) ? __ldg(W + (long long)(n0 + r) * ld + col0 + k) : 0.f;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[c] = fmaf(vn[r], wv[r], acc[c]);
         }
     }
 #pragma unroll

@@ -30,23 +30,23 @@ def _buffers(O, A, n):
                   out_dev=torch.zeros((3, n, A), dtype=torch.float32, device=dev),
                   out_host=torch.zeros((3, n, A), dtype=torch.float32).pin_memory(),
                   eps_dev=torch.zeros((n, A), dtype=torch.float32, device=dev),
-                  calls=0)
+                  calls=0, args={}, lib=_lib.lib(), byref=C.byref)
+        st['ob_np'], st['out_np'] = st['ob_host'].numpy(), st['out_host'].numpy()
         _STATE[key] = st
     return st
 
 
-def explore_batch(obs, policy, qfs, hyper_params, trainer=None, deterministic=False, eps=None, rng_seed=0):
-    """Vectorised entry point: ``obs`` [n, O] numpy -> (actions [n, A], mu_E [n, A], grad [n, A])
-    float32 numpy.  One launch for all observations (SURVEY.md section 8f rank 1)."""
-    if isinstance(policy, MakeDeterministic):
-        policy = policy.stochastic_policy
-    policy._ensure_bound()
-    for q in qfs:
-        q._ensure_bound()
-    obs = np.asarray(obs)
-    n, O = obs.shape
-    A = policy.action_dim
-    st = _buffers(O, A, n)
+_ZERO_COPY_MAX_OBS = 16      # up to this many observations travel through mapped pinned memory (no copy calls)
+
+
+def _explore_args(policy, qfs, trainer, deterministic, n, st):
+    """The OacExploreArgs of one (policy, critics, mode, n) configuration, built once: only the noise pointer, the RNG
+    offset and beta / delta change between calls.  Re-built when a net is re-bound to a new arena (engine resize)."""
+    key = (id(policy), policy._arena.data_ptr(), tuple((id(q), q._arena.data_ptr()) for q in qfs),
+           type(trainer), getattr(trainer, 'delta_index', None), bool(deterministic))
+    a = st['args'].get(key)
+    if a is not None:
+        return a
     a = OacExploreArgs()
     a.policy, a.policy_lay = policy._rel()
     nq = len(qfs)
@@ -63,22 +63,50 @@ def explore_batch(obs, policy, qfs, hyper_params, trainer=None, deterministic=Fa
     else:
         a.mode = _lib.EXPLORE_ENSEMBLE      # the except branch (:47-58): mean + beta * unbiased std
     a.deterministic = int(bool(deterministic))
-    a.beta_UB, a.delta = float(hyper_params['beta_UB']), float(hyper_params['delta'])
     a.n_obs = n
-    st['ob_host'].numpy()[...] = obs                      # f64 -> f32 (ptu.from_numpy, :22)
-    st['ob_dev'].copy_(st['ob_host'], non_blocking=True)
-    a.obs = st['ob_dev'].data_ptr()
+    zero_copy = n <= _ZERO_COPY_MAX_OBS
+    # unified addressing: a pinned host allocation is device-accessible under the same pointer, so for a few
+    # observations the kernel reads the observation from, and writes the action to, host memory directly
+    a.obs = (st['ob_host'] if zero_copy else st['ob_dev']).data_ptr()
+    out = st['out_host'] if zero_copy else st['out_dev']
+    a.action, a.mu_E, a.grad = out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()
+    st['args'] = {key: a}                   # one live configuration per (O, A, n)
+    return a
+
+
+def explore_batch(obs, policy, qfs, hyper_params, trainer=None, deterministic=False, eps=None, rng_seed=0):
+    """Vectorised entry point: ``obs`` [n, O] numpy -> (actions [n, A], mu_E [n, A], grad [n, A])
+    float32 numpy.  One launch for all observations (SURVEY.md section 8f rank 1)."""
+    if isinstance(policy, MakeDeterministic):
+        policy = policy.stochastic_policy
+    policy._ensure_bound()
+    for q in qfs:
+        q._ensure_bound()
+    obs = np.asarray(obs)
+    n, O = obs.shape
+    A = policy.action_dim
+    st = _buffers(O, A, n)
+    a = _explore_args(policy, qfs, trainer, deterministic, n, st)
+    a.beta_UB, a.delta = float(hyper_params['beta_UB']), float(hyper_params['delta'])
+    zero_copy = n <= _ZERO_COPY_MAX_OBS
+    st['ob_np'][...] = obs                                # f64 -> f32 (ptu.from_numpy, :22)
+    if not zero_copy:
+        st['ob_dev'].copy_(st['ob_host'], non_blocking=True)
     if eps is not None:
         st['eps_dev'].copy_(torch.as_tensor(np.asarray(eps, dtype=np.float32)).reshape(n, A))
         a.eps = st['eps_dev'].data_ptr()
+    else:
+        a.eps = None
     a.rng_seed, a.rng_offset = rng_seed, st['calls']
     st['calls'] += 1
-    out = st['out_dev']
-    a.action, a.mu_E, a.grad = out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()
-    _lib.check(_lib.lib().oac_explore(C.byref(a), _lib.current_stream()), "oac_explore")
-    st['out_host'].copy_(out, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    res = st['out_host'].numpy()
+    stream = torch.cuda.current_stream()
+    rc = st['lib'].oac_explore(st['byref'](a), C.c_void_p(stream.cuda_stream))
+    if rc:
+        _lib.check(rc, "oac_explore")
+    if not zero_copy:
+        st['out_host'].copy_(st['out_dev'], non_blocking=True)
+    stream.synchronize()
+    res = st['out_np']
     return res[0].copy(), res[1].copy(), res[2].copy()
 
 
