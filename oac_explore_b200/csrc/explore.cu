@@ -6,7 +6,10 @@
 // 1.3 MFLOP; at batch 1 the work is bounded by reading the ~2 MB
 // of weights once.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "device_util.cuh"
 #include "../../include/oac_b200.h"
@@ -21,13 +24,14 @@ constexpr int EX_MAX_H = 512;
 // out[n] = act(sum_k W[n*ld + k] x[k] + b[n]) for n in [0,N): one warp per output row, FOUR rows at a time -- the
 // loads of four rows (12 x 16 B per lane at K = 376) are in flight before the first reduction, so a layer costs ~4
 // L2 round trips per warp instead of 16 (the batch-1 exploration kernel is pure load latency: 2 MB of weights, 1.3 MFLOP)
+template <int NW = 16>
 __device__ __forceinline__ void gemv_rows(const float* __restrict__ W, int ld, const float* __restrict__ b,
                                           const float* x, int K, int N, float* out, bool relu_) {
     constexpr int RB = 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
     const int K4 = vec ? (K & ~3) : 0;
-    for (int n0 = warp * RB; n0 < N; n0 += EX_WARPS * RB) {
+    for (int n0 = warp * RB; n0 < N; n0 += NW * RB) {
         float acc[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) acc[r] = 0.f;
@@ -72,23 +76,16 @@ __device__ __forceinline__ void gemv_cols(const float* __restrict__ W, int ld, i
     float acc[EX_MAX_H / 32];
 #pragma unroll
     for (int c = 0; c < EX_MAX_H / 32; ++c) acc[c] = 0.f;
-    // four rows at a time: their loads are issued together (one L2 round trip per four rows); ReLU-masked rows
-    // (vn == 0) are skipped without touching their weights
-    constexpr int RB = 4;
-    for (int n0 = warp * RB; n0 < N; n0 += EX_WARPS * RB) {
-        float vn[RB];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) vn[r] = (n0 + r < N) ? v[n0 + r] : 0.f;
+    // (throughput variant: many observations per launch keep the SMs busy, so rows are walked one at a time with few
+    // registers -- two CTAs per SM; the latency variant below batches its loads instead)
+    for (int n = warp; n < N; n += EX_WARPS) {
+        const float vn = v[n];
+        if (vn == 0.f) continue;                       // ReLU-masked rows contribute nothing
+        const float* w = W + (long long)n * ld + col0;
 #pragma unroll
         for (int c = 0; c < EX_MAX_H / 32; ++c) {
-            const int k = c * 32 + lane;
-            if (c * 32 >= K) break;
-            float wv[RB];
-#pragma unroll
-            for (int r = 0; r < RB; ++r)
-                wv[r] = (k < K && vn[r] != 0.f) ? __ldg(W + (long long)(n0 + r) * ld + col0 + k) : 0.f;
-#pragma unroll
-            for (int r = 0; r < RB; ++r) acc[c] = fmaf(vn[r], wv[r], acc[c]);
+            int k = c * 32 + lane;
+            if (k < K) acc[c] = fmaf(vn, __ldg(w + k), acc[c]);
         }
     }
 #pragma unroll
@@ -259,6 +256,248 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
     }
 }
 
+// =====================================================================================
+// Latency variant: one thread-block CLUSTER of 8 CTAs per observation.
+// A single CTA reads the ~2 MB of weights through one SM and walks ~13 dependent GEMV layers, each a few L2 round
+// trips deep (~60 us).  Here every layer is split eight ways: forward layers by OUTPUT ROWS (each CTA computes H/8
+// neurons and stores them into all eight CTAs' shared memory through DSMEM), the backward products by OUTPUT COLUMNS
+// (no cross-CTA reduction), with one cluster barrier per exchanged layer; the tiny head layers, the coefficient math
+// and dQ/da are computed redundantly by every CTA instead of being exchanged.  Used for up to EXC_MAX_OBS observations
+// per call (the per-environment-step case); larger batches keep one CTA per observation.
+// =====================================================================================
+namespace cg = cooperative_groups;
+constexpr int EXC_CS = 8;              // CTAs per cluster (portable maximum)
+constexpr int EXC_THREADS = 256;
+constexpr int EXC_WARPS = EXC_THREADS / 32;
+constexpr int EXC_MAX_OBS = 16;
+
+// rows [r0, r1) of  out = act(W x + b), stored into `out` of EVERY CTA of the cluster (same shared-memory offset)
+__device__ __forceinline__ void gemv_rows_bcast(cg::cluster_group& cl, const float* __restrict__ W, int ld, const float* __restrict__ b,
+                                                const float* x, int K, int r0, int r1, float* out, bool relu_) {
+    constexpr int RB = 4;              // RB * EXC_CS == 32: lane -> (row r = lane & 3, destination rank = lane >> 2)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    const int K4 = vec ? (K & ~3) : 0;
+    for (int n0 = r0 + warp * RB; n0 < r1; n0 += EXC_WARPS * RB) {
+        float acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+        for (int k = lane * 4; k < K4; k += 128) {
+            float4 wv[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                wv[r] = (n0 + r < r1) ? __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ld + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float x0 = x[k], x1 = x[k + 1], x2 = x[k + 2], x3 = x[k + 3];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                acc[r] = fmaf(wv[r].x, x0, acc[r]); acc[r] = fmaf(wv[r].y, x1, acc[r]);
+                acc[r] = fmaf(wv[r].z, x2, acc[r]); acc[r] = fmaf(wv[r].w, x3, acc[r]);
+            }
+        }
+        for (int k = K4 + lane; k < K; k += 32) {
+            const float xk = x[k];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                if (n0 + r < r1) acc[r] = fmaf(__ldg(W + (long long)(n0 + r) * ld + k), xk, acc[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        }
+        const int r = lane & (RB - 1), rank = lane >> 2;
+        if (n0 + r < r1) {
+            float sel = acc[0];
+#pragma unroll
+            for (int q = 1; q < RB; ++q) sel = (r == q) ? acc[q] : sel;
+            float v = sel + __ldg(b + n0 + r);
+            v = relu_ ? fmaxf(v, 0.f) : v;
+            cl.map_shared_rank(out, rank)[n0 + r] = v;
+        }
+    }
+}
+
+// columns [k0, k1) of  out[k] = mask[k] > 0 ? sum_n v[n] W[n*ld + col0 + k] : 0  over rows n in [0, N); `bcast`: stored
+// into every CTA's `out`, else only locally (accumulating when `accumulate`).  part: scratch [EXC_WARPS][k1 - k0]
+__device__ __forceinline__ void gemv_cols_slice(cg::cluster_group& cl, const float* __restrict__ W, int ld, int col0, const float* v, int N,
+                                                int k0, int k1, const float* mask, float* out, float* part, bool bcast, bool accumulate) {
+    constexpr int RB = 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int width = k1 - k0;
+    for (int kb = 0; kb < width; kb += 32) {
+        const int k = k0 + kb + lane;
+        float acc = 0.f;
+        for (int n0 = warp * RB; n0 < N; n0 += EXC_WARPS * RB) {
+            float vn[RB], wv[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) vn[r] = (n0 + r < N) ? v[n0 + r] : 0.f;
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                wv[r] = (k < k1 && vn[r] != 0.f) ? __ldg(W + (long long)(n0 + r) * ld + col0 + k) : 0.f;   // ReLU-masked rows are skipped
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc = fmaf(vn[r], wv[r], acc);
+        }
+        if (kb + lane < width) part[warp * width + kb + lane] = acc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < width; t += EXC_THREADS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < EXC_WARPS; ++w) sum += part[w * width + t];
+        const int k = k0 + t;
+        if (mask && !(mask[k] > 0.f)) sum = 0.f;
+        if (bcast) {
+#pragma unroll
+            for (int rk = 0; rk < EXC_CS; ++rk) cl.map_shared_rank(out, rk)[k] = sum;
+        } else {
+            out[k] = accumulate ? out[k] + sum : sum;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExploreParams p) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int O = p.O, A = p.A, H = p.H;
+    const int ob = blockIdx.x / EXC_CS;
+    float* x = sm;
+    float* h1 = x + ((O + A + 3) & ~3);
+    float* h2 = h1 + H;
+    float* head = h2 + H;
+    float* qh1 = head + ((2 * A + 3) & ~3);
+    float* qh2 = qh1 + p.n_q * H;
+    float* qv = qh2 + p.n_q * H;
+    float* cf = qv + 64;
+    float* g2 = cf + 64;                       // [n_q][H]
+    float* g1 = g2 + p.n_q * H;                // [n_q][H]
+    float* da = g1 + p.n_q * H;
+    float* part = da + ((A + 3) & ~3);
+    const int tid = threadIdx.x;
+    const int hs = (H + EXC_CS - 1) / EXC_CS;  // this CTA's neurons / columns of a hidden layer: [s0, s1)
+    const int s0 = min(H, rank * hs), s1 = min(H, s0 + hs);
+
+    for (int i = tid; i < O; i += EXC_THREADS) x[i] = p.obs[(long long)ob * O + i];
+    cl.sync();                                 // also: every CTA of the cluster is running before the first remote store
+    // ---- policy forward: hidden layers split by rows, the 2A head rows on every CTA ----
+    gemv_rows_bcast(cl, p.policy.w0, p.policy.in_ld, p.policy.b0, x, O, s0, s1, h1, true);
+    cl.sync();
+    gemv_rows_bcast(cl, p.policy.w1, H, p.policy.b1, h1, H, s0, s1, h2, true);
+    cl.sync();
+    gemv_rows<EXC_WARPS>(p.policy.w2, H, p.policy.b2, h2, H, 2 * A, head, false);     // 2A short rows, redundantly per CTA
+    __syncthreads();
+    for (int j = tid; j < A; j += EXC_THREADS) x[O + j] = tanhf(head[j]);
+    __syncthreads();
+    // ---- critics forward ----
+    for (int q = 0; q < p.n_q; ++q) gemv_rows_bcast(cl, p.q[q].w0, p.q[q].in_ld, p.q[q].b0, x, O + A, s0, s1, qh1 + q * H, true);
+    cl.sync();
+    for (int q = 0; q < p.n_q; ++q) gemv_rows_bcast(cl, p.q[q].w1, H, p.q[q].b1, qh1 + q * H, H, s0, s1, qh2 + q * H, true);
+    cl.sync();
+    int n_vals = 0;
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int q = 0; q < p.n_q; ++q) {
+            const NetPtrs& N = p.q[q];
+            for (int n = warp; n < N.n_out; n += EXC_WARPS) {
+                const float* w = N.w2 + (long long)n * H;
+                float acc = 0.f;
+                for (int k = lane; k < H; k += 32) acc = fmaf(__ldg(w + k), qh2[q * H + k], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) qv[n_vals + n] = acc + __ldg(N.b2 + n);
+            }
+            n_vals += N.n_out;
+        }
+    }
+    __syncthreads();
+    // ---- dQ_UB / d(head outputs): same arithmetic as explore_kernel, on every CTA ----
+    if (tid == 0) {
+        const int n_heads = p.q[0].n_out;
+        for (int i = 0; i < n_vals; ++i)
+            if ((p.exp_mask >> (i % n_heads)) & 1u) qv[i] = expf(qv[i]);
+        if (p.mode == OAC_EXPLORE_TWIN) {
+            float dlt = qv[0] - qv[n_heads];
+            float sg = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+            for (int i = 0; i < n_vals; ++i) cf[i] = 0.f;
+            cf[0] = 0.5f + 0.5f * p.beta * sg;
+            cf[n_heads] = 0.5f - 0.5f * p.beta * sg;
+        } else if (p.mode == OAC_EXPLORE_ENSEMBLE) {
+            float mean = 0.f;
+            for (int i = 0; i < n_vals; ++i) mean += qv[i];
+            mean /= (float)n_vals;
+            float var = 0.f;
+            for (int i = 0; i < n_vals; ++i) var += (qv[i] - mean) * (qv[i] - mean);
+            var /= (float)(n_vals - 1);
+            float sd = sqrtf(var);
+            for (int i = 0; i < n_vals; ++i)
+                cf[i] = 1.f / (float)n_vals + p.beta * (qv[i] - mean) / ((float)(n_vals - 1) * sd);
+        } else {
+            for (int i = 0; i < n_vals; ++i) {
+                int r = 0;
+                for (int j = 0; j < n_vals; ++j) r += (qv[j] < qv[i]) || (qv[j] == qv[i] && j < i);
+                cf[i] = (r == p.quantile_index) ? 1.f : 0.f;
+            }
+        }
+        for (int i = 0; i < n_vals; ++i)
+            if ((p.exp_mask >> (i % n_heads)) & 1u) cf[i] *= qv[i];
+    }
+    for (int j = tid; j < A; j += EXC_THREADS) da[j] = 0.f;
+    __syncthreads();
+    // ---- backward to the action: g2 locally, g1 split by columns and exchanged, dQ/da on every CTA ----
+    {
+        int v0 = 0;
+        for (int q = 0; q < p.n_q; ++q) {
+            const NetPtrs& N = p.q[q];
+            for (int n = tid; n < H; n += EXC_THREADS) {
+                float sacc = 0.f;
+                for (int hd = 0; hd < N.n_out; ++hd) sacc = fmaf(cf[v0 + hd], __ldg(N.w2 + (long long)hd * H + n), sacc);
+                g2[q * H + n] = qh2[q * H + n] > 0.f ? sacc : 0.f;
+            }
+            v0 += N.n_out;
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < p.n_q; ++q)
+        gemv_cols_slice(cl, p.q[q].w1, H, 0, g2 + q * H, H, s0, s1, qh1 + q * H, g1 + q * H, part, true, false);
+    cl.sync();
+    if (rank == 0) {
+        for (int q = 0; q < p.n_q; ++q)
+            gemv_cols_slice(cl, p.q[q].w0, p.q[q].in_ld, O, g1 + q * H, H, 0, A, nullptr, da, part, false, true);
+        // ---- shift + sample (one warp) ----
+        if (tid < 32) {
+            float num = 0.f;
+            for (int j = tid; j < A; j += 32) {
+                float a = x[O + j];
+                float g = da[j] * (1.f - a * a);
+                float sd = expf(fminf(fmaxf(head[A + j], LOG_SIG_MIN_F), LOG_SIG_MAX_F));
+                float S = p.deterministic ? 1.f : sd * sd;
+                num += g * g * S;
+            }
+            num = warp_sum(num);
+            const float denom = sqrtf(num) + 10e-6f;
+            for (int j = tid; j < A; j += 32) {
+                float a = x[O + j];
+                float g = da[j] * (1.f - a * a);
+                float sd = expf(fminf(fmaxf(head[A + j], LOG_SIG_MIN_F), LOG_SIG_MAX_F));
+                float S = p.deterministic ? 1.f : sd * sd;
+                float muE = head[j] + (p.sqrt_2delta * (S * g)) / denom;
+                float outv;
+                if (p.deterministic) {
+                    outv = muE;
+                } else {
+                    float e = p.eps ? p.eps[(long long)ob * A + j]
+                                    : philox_normal(p.rng_seed, 7u, (uint32_t)p.rng_offset, (uint32_t)(p.rng_offset >> 32) + ob, j);
+                    outv = tanhf(fmaf(sd, e, muE));
+                }
+                p.action[(long long)ob * A + j] = outv;
+                if (p.mu_E) p.mu_E[(long long)ob * A + j] = muE;
+                if (p.grad) p.grad[(long long)ob * A + j] = g;
+            }
+        }
+    }
+    cl.sync();          // no CTA exits while a sibling may still store into its shared memory
+}
+
 // ---- TanhGaussianPolicy.forward on n rows (one CTA per row) ----
 struct PolicyFwdParams {
     NetPtrs net;
@@ -372,6 +611,24 @@ extern "C" int oac_explore(const OacExploreArgs* a, void* stream) {
     p.action = a->action; p.mu_E = a->mu_E; p.grad = a->grad;
     size_t fl = ((O + A + 3) & ~3) + 2 * H + ((2 * A + 3) & ~3) + 2 * (size_t)p.n_q * H + 128 + 2 * H +
                 ((A + 3) & ~3) + (size_t)EX_WARPS * (H > A ? H : A);
+    static const bool no_cluster = getenv("OAC_NO_CLUSTER") && getenv("OAC_NO_CLUSTER")[0] == '1';
+    if (a->n_obs <= EXC_MAX_OBS && !no_cluster) {
+        // latency variant: a cluster of 8 CTAs per observation (layers split eight ways, activations through DSMEM)
+        const int wmax = (H + EXC_CS - 1) / EXC_CS > A ? (H + EXC_CS - 1) / EXC_CS : A;
+        size_t flc = ((O + A + 3) & ~3) + 2 * H + ((2 * A + 3) & ~3) + 2 * (size_t)p.n_q * H + 128 + 2 * (size_t)p.n_q * H +
+                     ((A + 3) & ~3) + (size_t)EXC_WARPS * wmax;
+        if (int e = ensure_smem(explore_cluster_kernel, flc * sizeof(float))) return e;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(a->n_obs * EXC_CS); cfg.blockDim = dim3(EXC_THREADS);
+        cfg.dynamicSmemBytes = flc * sizeof(float); cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = EXC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        OAC_CUDA(cudaLaunchKernelEx(&cfg, explore_cluster_kernel, p));
+        return 0;
+    }
     if (int e = ensure_smem(explore_kernel, fl * sizeof(float))) return e;
     explore_kernel<<<a->n_obs, EX_THREADS, fl * sizeof(float), (cudaStream_t)stream>>>(p);
     OAC_CUDA(cudaGetLastError());
