@@ -210,9 +210,35 @@ class TanhGaussianPolicy(Mlp):
         actions = self.get_actions(obs_np[None], deterministic=deterministic)
         return actions[0, :], {}
 
+    _ACT_ZERO_COPY_MAX = 16
+
     def get_actions(self, obs_np, deterministic=False):
-        out = self.forward(from_numpy(obs_np), deterministic=deterministic)[0]
-        return out.to('cpu').numpy()
+        """numpy observations -> numpy actions (trainer/policies.py:253-258).  Up to a few rows (the per-environment-step
+        case) travel through mapped pinned memory: the kernel reads the observation from, and writes the action to, host
+        memory directly, so a call is one launch and one stream synchronisation."""
+        obs_np = np.asarray(obs_np)
+        n = obs_np.shape[0]
+        if n > self._ACT_ZERO_COPY_MAX:
+            out = self.forward(from_numpy(obs_np), deterministic=deterministic)[0]
+            return out.to('cpu').numpy()
+        self._ensure_bound()
+        A, O = self.action_dim, self.input_size
+        st = getattr(self, '_act_state', None)
+        if st is None or st['n'] != n:
+            st = dict(n=n, obs=torch.zeros((n, O), dtype=torch.float32).pin_memory(),
+                      act=torch.zeros((n, A), dtype=torch.float32).pin_memory(), lib=_lib.lib())
+            st['obs_np'], st['act_np'] = st['obs'].numpy(), st['act'].numpy()
+            self._act_state = st
+        st['obs_np'][...] = obs_np                              # f64 -> f32 (ptu.from_numpy)
+        eps = None if deterministic else torch.randn((n, A), dtype=torch.float32, device=_device())
+        stream = torch.cuda.current_stream()
+        rc = st['lib'].oac_policy_forward(
+            _lib.ptr(self._arena), C.byref(self._lay), _lib.ptr(st['obs']), O, n, _lib.ptr(eps),
+            _lib.ptr(st['act']), None, None, None, None, None, C.c_void_p(stream.cuda_stream))
+        if rc:
+            _lib.check(rc, "oac_policy_forward")
+        stream.synchronize()
+        return st['act_np'].copy()
 
     def forward(self, obs, reparameterize=True, deterministic=False, return_log_prob=False):
         self._ensure_bound()

@@ -49,6 +49,15 @@ for n in args.n:
     dt = time.perf_counter() - t0
     out["batch_%d_us_per_call" % n] = 1e6 * dt / it
     out["batch_%d_actions_per_s" % n] = n * it / dt
+# policy.get_action (evaluation rollouts / warm-up collection, path_collector.py:216-220)
+from oac_explore_b200.networks import MakeDeterministic
+for name, pol in (("get_action_stochastic", tr.policy), ("get_action_deterministic", MakeDeterministic(tr.policy))):
+    for _ in range(50):
+        pol.get_action(ob)
+    t0 = time.perf_counter()
+    for _ in range(args.iters):
+        pol.get_action(ob)
+    out[name + "_us"] = 1e6 * (time.perf_counter() - t0) / args.iters
 # reference CPU path (oracle port), one thread (launcher_util.py:90) and all threads
 from oracle import oac_oracle as orc
 torch.manual_seed(0)
