@@ -100,3 +100,29 @@ def test_policy_and_q_forward_vs_oracle():
     act_np, info = pol.get_action(obs[0].numpy().astype(np.float64), deterministic=True)
     assert act_np.shape == (A,) and info == {}
     assert max_abs(act_np, ra.new_tensor(orc.policy_forward(opol, obs[:1], None, True)[0][0])) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["twin", "ensemble", "deterministic"])
+def test_cluster_and_per_cta_kernels_agree(mode):
+    """Up to 16 observations run on the 8-CTA-cluster latency kernel, more on the one-CTA-per-observation kernel: the
+    same 40 observations through both (one call of 40, five calls of 8) must agree to fp32 summation-order noise."""
+    from oac_explore_b200.optimistic_exploration import explore_batch
+    O, A, H = 376, 17, 256
+    torch.manual_seed(7)
+    if mode == "ensemble":
+        pp, qp = producers(O, A, H, q_out=5)
+        pol, qfs = pp(), [qp()]
+        hp = dict(beta_UB=4.66, delta=20.53, share_layers=True)
+    else:
+        pp, qp = producers(O, A, H)
+        pol, qfs = pp(), [qp(), qp()]
+        hp = dict(beta_UB=4.66, delta=23.53, share_layers=False)
+    det = mode == "deterministic"
+    rng = np.random.RandomState(3)
+    obs = rng.randn(40, O)
+    eps = rng.randn(40, A).astype(np.float32)
+    big = explore_batch(obs, pol, qfs, hp, deterministic=det, eps=eps)
+    for i in range(0, 40, 8):
+        small = explore_batch(obs[i:i + 8], pol, qfs, hp, deterministic=det, eps=eps[i:i + 8])
+        for a, b in zip(big, small):
+            assert max_abs(a[i:i + 8], b) <= 2e-5, (mode, i, max_abs(a[i:i + 8], b))
