@@ -261,6 +261,11 @@ struct CriticHeadParams {
     int share_layers, counts;
     float discount, reward_scale, standard_bound, std_init;
     int iters;            // sample groups (of GLUE_SPC samples) per CTA
+    // (critic, head) pairs in evaluation order, built by the host: pair i is head pair_hd[i] of source pair_src[i];
+    // goff[s] = first pair of source s
+    int n_pairs;
+    short pair_src[MAX_VALS], pair_hd[MAX_VALS];
+    int goff[MAX_HEAD_SRC];
 };
 
 // Head dot products of one sample: the loads of up to four (critic, head) pairs are issued before the first
@@ -310,22 +315,14 @@ __device__ __forceinline__ void critic_head_body(const CriticHeadParams& p, int 
     constexpr int SPC = GLUE_WARPS / G;
     __shared__ float s_vals[SPC][MAX_VALS];
     __shared__ float s_dq[SPC][MAX_VALS];
-    __shared__ int s_goff[MAX_HEAD_SRC];
-    __shared__ short s_pair_src[MAX_VALS], s_pair_hd[MAX_VALS];
-    __shared__ int s_npairs;
+    const int* s_goff = p.goff;
+    const short* s_pair_src = p.pair_src;
+    const short* s_pair_hd = p.pair_hd;
+    const int s_npairs = p.n_pairs;
     const int seed = by;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = warp / G, g = warp % G;
     const int B = p.B, H = p.H;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int s = 0; s < p.n_src; ++s) {
-            s_goff[s] = n;
-            for (int hd = 0; hd < p.src[s].n_heads; ++hd, ++n) { s_pair_src[n] = (short)s; s_pair_hd[n] = (short)hd; }
-        }
-        s_npairs = n;
-    }
-    __syncthreads();
     for (int it = 0; it < p.iters; ++it) {                 // p.iters sample groups per CTA (many-seed launches)
     if (it > 0) group_sync<G>();                           // s_vals / s_dq are rewritten
     const int b = (bx * p.iters + it) * SPC + sl;

@@ -912,6 +912,17 @@ static int finalize(OacTrainer& t) {
         } else if (s.kind == ST_CRITIC_HEAD) {
             glue_plan(s, (long long)t.cfg.batch * seeds, false);
             s.chp.iters = s.glue_iters;
+            {
+                int n = 0;
+                for (int i = 0; i < s.chp.n_src; ++i) {
+                    s.chp.goff[i] = n;
+                    for (int hd = 0; hd < s.chp.src[i].n_heads; ++hd, ++n) {
+                        if (n >= MAX_VALS) return set_error(OAC_E_UNSUPPORTED, "too many critic heads for one critic_head stage");
+                        s.chp.pair_src[n] = (short)i; s.chp.pair_hd[n] = (short)hd;
+                    }
+                }
+                s.chp.n_pairs = n;
+            }
             s.chp.as = t.as;
             if (int e = upload(t, &s.chp, 1, &s.dev)) return e;
         } else if (s.kind == ST_ADAM) {
