@@ -3,8 +3,10 @@
 # same commands.  Everything lands in gpurun_out/; tools/summarize_profiles.py turns it into profiles/*.txt.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/run_profiles.sh'
 set -u
+PHASE=${1:-all}        # bench | ncu | all  (gpurun copies back at most 64 MiB per call: the two full captures go alone)
 O=gpurun_out
-T="r01g"
+T="r01h"
+if [ "$PHASE" != "ncu" ]; then
 python bench.py > $O/${T}_bench_single.json 2> $O/${T}_bench_single.err
 python bench.py --impl reference --steps 200 --warmup 5 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err
 python bench.py --seeds-per-gpu 64 --steps 100 --warmup 5 > $O/${T}_bench_64seeds.json 2> $O/${T}_bench_64seeds.err
@@ -19,10 +21,13 @@ python tools/profile_step.py --steps 3 > $O/${T}_plain_single.log 2>&1 && \
 python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_plain_64.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_64seeds_tf32.csv \
       python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_ncu_64.log 2>&1
+python tools/bench_explore.py > $O/${T}_explore.json 2> $O/${T}_explore.err
+fi
+if [ "$PHASE" != "bench" ]; then
 # full captures: the last step's launches of each configuration
 ncu --set full --clock-control none --import-source on -k regex:"gemm_sk_kernel|critic_head_kernel|policy_head_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 38 --launch-count 19 -o $O/${T}_single_fp32 -f \
     python tools/profile_step.py --steps 3 > $O/${T}_full_single.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"gemm_ws_kernel|adam_stream_kernel|critic_head_kernel|policy_head_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 19 --launch-count 19 -o $O/${T}_64seeds_tf32 -f \
+ncu --set full --clock-control none -k regex:"gemm_ws_kernel|adam_stream_kernel|critic_head_kernel|policy_head_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 19 --launch-count 19 -o $O/${T}_64seeds_tf32 -f \
     python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_full_64.log 2>&1
 tail -2 $O/${T}_full_64.log
-python tools/bench_explore.py > $O/${T}_explore.json 2> $O/${T}_explore.err
+fi
