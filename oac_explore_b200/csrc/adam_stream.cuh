@@ -6,7 +6,7 @@
 // ~3.6 TB/s however the loads are arranged (profiles/r01c).  Here the weight-gradient GEMMs store plain gradients
 // (EPI_GRAD, 4 B per element, laid out like the parameter arena) and this kernel streams
 //     grad, param, exp_avg, exp_avg_sq [, Polyak target]  ->  param, exp_avg, exp_avg_sq [, target]
-// with 2048 threads per SM and 20 x 16 B loads in flight per thread.  The arithmetic is adam_update()'s
+// with 1536 threads per SM, one float4 of every stream per thread.  The arithmetic is adam_update()'s
 // (torch.optim.Adam 1.4 operation order, IEEE divide / square root), so the optimizer step itself is exact.
 #pragma once
 #include "gemm_simt.cuh"
@@ -15,7 +15,7 @@ namespace oac {
 
 constexpr int ADAM_MAX_SEGS = 24;
 constexpr int ADAM_THREADS = 256;
-constexpr int ADAM_UNROLL = 4;
+constexpr int ADAM_UNROLL = 1;
 
 struct AdamSeg {
     long long off;          // first float of the block in the parameter / moment arenas (multiple of 4)
@@ -42,7 +42,11 @@ __device__ __forceinline__ void adam_elem(float g, float& p, float& m, float& v,
     if (polyak) t = __fadd_rn(__fmul_rn(t, s.one_m_tau), __fmul_rn(p, s.tau));
 }
 
-__global__ void __launch_bounds__(ADAM_THREADS) adam_stream_kernel(const AdamStreamParams* __restrict__ pp) {
+// UN float4 elements per thread.  Measured at 64 seeds (767 MB per critic launch): UN = 4 (121 registers, 2 CTAs / SM)
+// 4.4 TB/s, UN = 2 (4 CTAs / SM) 5.6 TB/s, UN = 1 (6 CTAs / SM) 6.0 TB/s = 91 % of the copy peak -- occupancy, not
+// per-thread unrolling, hides the latency here; cache-streaming hints (STREAM) made no difference.
+template <int UN, bool STREAM>
+__global__ void __launch_bounds__(ADAM_THREADS, UN == 1 ? 6 : (UN == 2 ? 4 : 2)) adam_stream_kernel(const AdamStreamParams* __restrict__ pp) {
     pdl_wait();
     const AdamStreamParams& P = *pp;
     __shared__ AdamScalars s_sc[ADAM_MAX_SEGS];
@@ -59,17 +63,18 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_stream_kernel(const AdamStr
         s_start4[P.n_seg] = a;
     }
     __syncthreads();
-    float* __restrict__ par = P.as.base[AR_PARAM] + (long long)seed * P.as.stride[AR_PARAM];
-    float* __restrict__ m1 = P.as.base[AR_ADAM_M] + (long long)seed * P.as.stride[AR_ADAM_M];
-    float* __restrict__ m2 = P.as.base[AR_ADAM_V] + (long long)seed * P.as.stride[AR_ADAM_V];
-    const float* __restrict__ wrk = P.as.base[AR_WORK] + (long long)seed * P.as.stride[AR_WORK];
-
-    float4 g4[ADAM_UNROLL], p4[ADAM_UNROLL], a4[ADAM_UNROLL], v4[ADAM_UNROLL], t4[ADAM_UNROLL];
-    long long po[ADAM_UNROLL], to[ADAM_UNROLL];
-    int sg[ADAM_UNROLL];
-    const long long base = (long long)blockIdx.x * (ADAM_THREADS * ADAM_UNROLL) + threadIdx.x;
+    float* par = P.as.base[AR_PARAM] + (long long)seed * P.as.stride[AR_PARAM];
+    float* m1 = P.as.base[AR_ADAM_M] + (long long)seed * P.as.stride[AR_ADAM_M];
+    float* m2 = P.as.base[AR_ADAM_V] + (long long)seed * P.as.stride[AR_ADAM_V];
+    const float* wrk = P.as.base[AR_WORK] + (long long)seed * P.as.stride[AR_WORK];
+    auto ld4 = [](const float* p_) { return STREAM ? __ldcs(reinterpret_cast<const float4*>(p_)) : *reinterpret_cast<const float4*>(p_); };
+    auto st4 = [](float* p_, const float4& v_) { if (STREAM) __stcs(reinterpret_cast<float4*>(p_), v_); else *reinterpret_cast<float4*>(p_) = v_; };
+    float4 g4[UN], p4[UN], a4[UN], v4[UN], t4[UN];
+    long long po[UN], to[UN];
+    int sg[UN];
+    const long long base = (long long)blockIdx.x * (ADAM_THREADS * UN) + threadIdx.x;
 #pragma unroll
-    for (int u = 0; u < ADAM_UNROLL; ++u) {
+    for (int u = 0; u < UN; ++u) {
         const long long i4 = base + (long long)u * ADAM_THREADS;
         po[u] = -1; to[u] = -1; sg[u] = 0;
         if (i4 < P.total4) {
@@ -78,18 +83,18 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_stream_kernel(const AdamStr
             const AdamSeg& S = P.seg[k];
             const long long e = (i4 - s_start4[k]) << 2;
             sg[u] = k; po[u] = S.off + e;
-            g4[u] = *reinterpret_cast<const float4*>(wrk + S.grad_off + e);
-            p4[u] = *reinterpret_cast<const float4*>(par + po[u]);
-            a4[u] = *reinterpret_cast<const float4*>(m1 + po[u]);
-            v4[u] = *reinterpret_cast<const float4*>(m2 + po[u]);
+            g4[u] = ld4(wrk + S.grad_off + e);
+            p4[u] = ld4(par + po[u]);
+            a4[u] = ld4(m1 + po[u]);
+            v4[u] = ld4(m2 + po[u]);
             if (S.target_off >= 0 && s_sc[k].do_polyak) {
                 to[u] = S.target_off + e;
-                t4[u] = *reinterpret_cast<const float4*>(par + to[u]);
+                t4[u] = ld4(par + to[u]);
             }
         }
     }
 #pragma unroll
-    for (int u = 0; u < ADAM_UNROLL; ++u) {
+    for (int u = 0; u < UN; ++u) {
         if (po[u] < 0) continue;
         const AdamScalars s = s_sc[sg[u]];
         const bool pk = to[u] >= 0;
@@ -97,10 +102,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_stream_kernel(const AdamStr
         adam_elem(g4[u].y, p4[u].y, a4[u].y, v4[u].y, t4[u].y, pk, s);
         adam_elem(g4[u].z, p4[u].z, a4[u].z, v4[u].z, t4[u].z, pk, s);
         adam_elem(g4[u].w, p4[u].w, a4[u].w, v4[u].w, t4[u].w, pk, s);
-        *reinterpret_cast<float4*>(par + po[u]) = p4[u];
-        *reinterpret_cast<float4*>(m1 + po[u]) = a4[u];
-        *reinterpret_cast<float4*>(m2 + po[u]) = v4[u];
-        if (pk) *reinterpret_cast<float4*>(par + to[u]) = t4[u];
+        st4(par + po[u], p4[u]);
+        st4(m1 + po[u], a4[u]);
+        st4(m2 + po[u], v4[u]);
+        if (pk) st4(par + to[u], t4[u]);
     }
 }
 

@@ -273,7 +273,7 @@ struct CriticHeadParams {
 template <int HR, int G>
 __device__ __forceinline__ void head_dots(const CriticHeadParams& p, int seed, int b, int g, int lane, int npairs,
                                           const short* pair_src, const short* pair_hd, float* vals) {
-    constexpr int PB = 32 / HR;                       // 64 load registers either way
+    constexpr int PB = (G == 1 ? 16 : 32) / HR;       // load registers: 64 (G = 4: few warps, deep batches), 32 (G = 1: occupancy)
     const int H = p.H;
     for (int base = g; base < npairs; base += G * PB) {
         float hv[PB][HR], wv[PB][HR];
@@ -465,7 +465,7 @@ __device__ __forceinline__ void critic_head_body(const CriticHeadParams& p, int 
 }
 
 template <int G>
-__global__ void __launch_bounds__(GLUE_THREADS, 2) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
+__global__ void __launch_bounds__(GLUE_THREADS, G == 1 ? 4 : 2) critic_head_kernel(const CriticHeadParams* __restrict__ pp) {
     pdl_wait();
     critic_head_body<G>(*pp, blockIdx.x, blockIdx.y);
 }

@@ -1059,7 +1059,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
         } else if (s.kind == ST_ADAM) {
             const long long per_cta = (long long)ADAM_THREADS * ADAM_UNROLL;
             dim3 grid((unsigned)((s.asp.total4 + per_cta - 1) / per_cta), seeds, 1);
-            launch_pdl(adam_stream_kernel, grid, dim3(ADAM_THREADS), 0, st, (const AdamStreamParams*)s.dev);
+            launch_pdl(adam_stream_kernel<ADAM_UNROLL, false>, grid, dim3(ADAM_THREADS), 0, st, (const AdamStreamParams*)s.dev);
         } else if (s.kind == ST_CRITIC_HEAD) {
             const int per_cta = (GLUE_WARPS / s.glue_g) * s.glue_iters;       // iters is part of the uploaded CriticHeadParams
             dim3 grid((t.cfg.batch + per_cta - 1) / per_cta, seeds, 1);
