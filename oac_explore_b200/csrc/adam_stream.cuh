@@ -3,7 +3,7 @@
 // With one or a few seeds the Adam update is fused into the epilogue of the weight-gradient GEMM (every weight
 // and moment is touched once, no gradient buffer exists).  With many seeds that epilogue is the slowest part of
 // the step: its 256 threads per SM cannot keep more than ~64 KB of loads in flight, which caps the stage at
-// ~3.6 TB/s however the loads are arranged (profiles/r01c).  Here the weight-gradient GEMMs store plain gradients
+// ~3.6 TB/s however the loads are arranged (ncu, mid-round capture).  Here the weight-gradient GEMMs store plain gradients
 // (EPI_GRAD, 4 B per element, laid out like the parameter arena) and this kernel streams
 //     grad, param, exp_avg, exp_avg_sq [, Polyak target]  ->  param, exp_avg, exp_avg_sq [, target]
 // with 1536 threads per SM, one float4 of every stream per thread.  The arithmetic is adam_update()'s

@@ -515,7 +515,7 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
                             reinterpret_cast<uintptr_t>(pt)) & 15) == 0);
         if (vec) {
             // one 16-byte load per array instead of four dependent scalar round trips (the loads of element j+1 may not
-            // pass the stores of element j: 40 % of this kernel's stall samples sat on them, profiles/r01f)
+            // pass the stores of element j: 40 % of this kernel's stall samples sat on them, ncu source view, mid-round)
             float4 p4 = *reinterpret_cast<const float4*>(C + e0);
             float4 a4 = *reinterpret_cast<const float4*>(pm);
             float4 v4 = *reinterpret_cast<const float4*>(pv);

@@ -46,7 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 // same, but a failed probe backs off: single-lane producer / MMA loops would otherwise burn issue slots that the
-// epilogue warps of the same SM sub-partition need (18 % of the instruction stream in profiles/r01b)
+// epilogue warps of the same SM sub-partition need (18 % of the instruction stream in a mid-round ncu capture)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         if (mbar_try_wait(bar, parity)) return;

@@ -61,9 +61,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {     // p 16-byte aligned, bytes % 16 == 0
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -95,7 +92,7 @@ __device__ __forceinline__ AdamScalars make_adam_scalars_fast(const AdamHyper& h
 }
 // Adam (+Polyak) on register operands for the TF32 path.  The weight gradient g already carries ~1e-3 of tf32
 // rounding, so the IEEE-exact divide / square root of adam_update (gemm_simt.cuh: ~40 dependent instructions per
-// element, 40 % of this kernel's instruction stream in profiles/r01b) buy nothing here: MUFU sqrt / reciprocal
+// element, 40 % of this kernel's instruction stream in a mid-round ncu capture) buy nothing here: MUFU sqrt / reciprocal
 // (2 ulp) and fused multiply-adds instead.  inv_bc2 = 1 / sqrt(1 - beta2^t).
 __device__ __forceinline__ void adam_core(float g, float& p, float& m, float& v, float& tgt, bool has_tgt, const AdamScalars& s,
                                           float inv_bc2) {
@@ -238,28 +235,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
         float* __restrict__ m2 = sp.as.base[AR_ADAM_V];
         float* __restrict__ pb0 = sp.as.base[AR_PARAM];
         const int rsub = lane >> 4, c4 = (lane & 15) << 2;
-        // Adam tiles stream 16 B per element of param / moments / target through registers, which caps the bytes in
-        // flight at ~64 KB per SM (one DRAM latency per batch: 3.6 TB/s in profiles/r01c).  Each warp therefore pulls
-        // its NEXT slab towards L2 (cp.async.bulk.prefetch.L2, no registers held) before it starts on the current one,
-        // so the register loads find their lines in L2.
-        auto prefetch_slab = [&](int g, int sl) {
-            if (g >= wp.total_tiles) return;
-            int seed, j, tm, tn;
-            decode(g, seed, j, tm, tn);
-            const GemmTask& T = tasks[j];
-            if (T.epi != EPI_ADAM) return;
-            const int n0 = tn * T.bn + sl * WS_SLAB;
-            const int nlim = min(T.N, tn * T.bn + T.bn);
-            const int m = tm * WS_BM + q * 32 + lane;
-            if (n0 >= nlim || m >= T.M) return;
-            const uint32_t bytes = (uint32_t)min(WS_SLAB, (nlim - n0 + 3) & ~3) * 4u;
-            const long long eo = (long long)m * T.ldc + n0;
-            l2_prefetch(resolve(sp.as, T.C, seed) + eo, bytes);
-            l2_prefetch(m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off + eo, bytes);
-            l2_prefetch(m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off + eo, bytes);
-            if (T.target_off >= 0) l2_prefetch(pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off + eo, bytes);
-        };
-        prefetch_slab(blockIdx.x, hsel);
         int tl = 0;
         for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x, ++tl) {
             int seed, j, tm, tn;
@@ -294,15 +269,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
             const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
-            if (is_adam && !rows_live) prefetch_slab(g + gridDim.x, hsel);
             for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
                 const int c0 = sl * WS_SLAB;
-                if (is_adam) {
-                    if ((sl + 2) * WS_SLAB < nlim - n0) prefetch_slab(g, sl + 2);
-                    else prefetch_slab(g + gridDim.x, hsel);
-                }
                 // ReLU-mask epilogue: all 16 mask loads of this lane fly while the accumulator is read back and
-                // transposed (one at a time they cost a DRAM latency each: 21 us per K=1 tile in profiles/r01c)
+                // transposed (one at a time they cost a DRAM latency each: 21 us per K=1 tile before this)
                 float4 k4[16];
                 const bool mask_vec = mask != nullptr && (n0 + c0 + c4 + 3 < nlim);
                 if (mask_vec) {
