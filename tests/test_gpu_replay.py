@@ -117,3 +117,31 @@ def test_full_size_roundtrip_properties():
     assert torch.equal(d['next_observations'], rb._next_obs[it])
     assert torch.equal(d['actions'], rb._actions[it])
     assert torch.equal(d['rewards'], rb._rewards[it])
+
+
+def test_pinned_index_ring_without_host_synchronisation():
+    """The gather kernel reads its indices from a ring of pinned host slots while the host runs ahead: 2 600 batches
+    (more than two turns of the 1 024-slot ring) are issued without any synchronisation in between and every one of
+    them must still be the batch of ITS index draw."""
+    from oac_explore_b200.replay_buffer import ReplayBuffer
+    from tests.test_gpu_sac import make_trainer
+    O, A, N, B, H = 7, 2, 300, 16, 32
+    rb = ReplayBuffer(N, Box(O), Box(A))
+    g = torch.Generator(device='cuda').manual_seed(3)
+    rb._observations.normal_(generator=g)
+    rb._size = N
+    tr = make_trainer(O, A, H)
+    tr._ensure_engine(B)
+    rb.attach(tr)
+    n_batches = 2600
+    keep = torch.empty((n_batches, B, O), device='cuda')
+    np.random.seed(11)
+    for i in range(n_batches):
+        rb.random_batch(B)
+        keep[i].copy_(tr._engine.x_block(2)[:, :O])          # stream-ordered after this batch's gather
+    torch.cuda.synchronize()
+    np.random.seed(11)
+    store = rb._observations.cpu()
+    for i in range(n_batches):
+        idx = torch.from_numpy(np.random.randint(0, N, B))
+        assert torch.equal(keep[i].cpu(), store[idx]), i
