@@ -209,7 +209,10 @@ class _Single(object):
         self.tr.train(batch)                     # fused step (CUDA graph)
 
     def scalars(self):
-        return self.engine.scalars()
+        if getattr(self, '_sc', None) is None or self._sc_engine is not self.tr._engine:
+            self._sc_engine = self.tr._engine
+            self._sc = self._sc_engine.scalars().view(1, 16)
+        return self._sc
 
     api = "ReplayBuffer.random_batch(256) + SACTrainer.train(batch) + D2H scalars, sync per step"
 

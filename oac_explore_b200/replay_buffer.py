@@ -179,7 +179,7 @@ class ReplayBuffer(object):
     def gather_into(self, engine, indices_dev, batch_size, seed=0, n_seeds=1):
         st, dst, _ = self._gather_desc(engine, seed, n_seeds)
         rc = self._lib.oac_replay_gather(C.byref(st), C.c_void_p(indices_dev.data_ptr()), batch_size, C.byref(dst),
-                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                         _lib.current_stream())
         if rc:
             _lib.check(rc, "oac_replay_gather")
 
