@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define OAC_ABI_VERSION 1
+#define OAC_ABI_VERSION 2
 #define OAC_MAX_NETS 48
 
 enum { OAC_E_INVALID = -1, OAC_E_UNSUPPORTED = -2, OAC_E_NOMEM = -3 };
@@ -129,6 +129,9 @@ typedef struct OacBuffers {
     float* work;      /* [n_seeds, work_floats]  */
     float* io;        /* [n_seeds, io_floats]    */
     int32_t* counters;/* [n_seeds, n_counters]   */
+    float* host_scalars; /* optional (may be NULL): [n_seeds, 16] MAPPED PINNED HOST memory; every step also stores its
+                          * scalars (slot 0 alpha, 1 alpha loss, 2 mean log pi) there, so a caller that wants the step's
+                          * result on the host only has to synchronise the stream (no device-to-host copy call) */
 } OacBuffers;
 
 typedef struct OacTrainer OacTrainer;   /* opaque */

@@ -61,7 +61,7 @@ class OacLayout(C.Structure):
 
 class OacBuffers(C.Structure):
     _fields_ = [("params", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
-                ("work", C.c_void_p), ("io", C.c_void_p), ("counters", C.c_void_p)]
+                ("work", C.c_void_p), ("io", C.c_void_p), ("counters", C.c_void_p), ("host_scalars", C.c_void_p)]
 
 
 class OacReplayStore(C.Structure):
@@ -131,7 +131,7 @@ def lib():
     L.oac_policy_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.oac_q_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, u32, vp, vp]
     L.oac_explore.argtypes = [C.POINTER(OacExploreArgs), vp]
-    if L.oac_abi_version() != 1:
+    if L.oac_abi_version() != 2:
         raise RuntimeError("liboac_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -68,6 +68,7 @@ struct PolicyHeadParams {
     int n_opt_counters;      // counters CNT_OPT0 .. CNT_OPT0+n-1 are bumped once per step here
     int iters;               // row groups (of GLUE_SPC rows) per CTA
     int head_from_gemm;      // 1: the head layer ran as a tensor-core GEMM stage; this kernel only samples
+    float* host_scalars;     // optional mapped pinned host copy of the step's scalars, [n_seeds, SC_COUNT]
 };
 
 // Fused head layer + sampling: the [2A, H] head weights are staged in shared memory once per CTA; GLUE_G warps
@@ -214,6 +215,10 @@ __device__ __forceinline__ void policy_head_body(const PolicyHeadParams& p, int 
         } else {
             sc[SC_ALPHA] = 0.f;              // the fork's choice (trainer.py:148-149)
             sc[SC_ALPHA_LOSS] = 0.f;
+        }
+        if (p.host_scalars != nullptr) {     // zero-copy device -> host: the caller only synchronises
+            float* hs = p.host_scalars + (long long)seed * SC_COUNT;
+            hs[SC_ALPHA] = sc[SC_ALPHA]; hs[SC_ALPHA_LOSS] = sc[SC_ALPHA_LOSS]; hs[SC_MEAN_LOGPI] = sc[SC_MEAN_LOGPI];
         }
     }
 }

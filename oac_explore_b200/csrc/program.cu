@@ -179,6 +179,7 @@ struct OacTrainer {
     bool use_graph = true;
     int n_opt = 0;
     long long* tc_dbg = nullptr;
+    float* host_scalars = nullptr;   // OacBuffers::host_scalars
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
@@ -443,6 +444,7 @@ struct Builder {
         p.alpha.log_alpha = P(la.off_w0); p.alpha.adam_off = la.off_w0;
         p.alpha.lr = c.policy_lr; p.alpha.target_entropy = c.target_entropy; p.alpha.counter = alpha_counter;
         p.head_from_gemm = tensor_glue ? 1 : 0;
+        p.host_scalars = t.host_scalars;
     }
     void fill_chp(Stage& s, int mode, int n_nets) {
         CriticHeadParams& p = s.chp;
@@ -1228,6 +1230,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     if (cfg->gemm_path < OAC_GEMM_FP32 || cfg->gemm_path > OAC_GEMM_TF32X3) return set_error(OAC_E_INVALID, "gemm_path");
     OacTrainer* t = new OacTrainer();
     t->cfg = *cfg;
+    t->host_scalars = buf->host_scalars;
     if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }

@@ -50,8 +50,11 @@ class Engine(object):
         self.params, self.adam_m, self.adam_v = z(L.param_floats), z(L.adam_floats), z(L.adam_floats)
         self.work, self.io = z(L.work_floats), z(L.io_floats)
         self.counters = torch.zeros((S, L.n_counters), dtype=torch.int32, device=self.device)
+        # the step also stores its scalars (alpha, alpha loss, mean log pi) into this mapped pinned host tensor:
+        # valid after a synchronisation of the stream the step ran on
+        self.host_scalars = torch.zeros((S, 16), dtype=torch.float32).pin_memory()
         buf = OacBuffers(_lib.ptr(self.params), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
-                         _lib.ptr(self.work), _lib.ptr(self.io), _lib.ptr(self.counters))
+                         _lib.ptr(self.work), _lib.ptr(self.io), _lib.ptr(self.counters), _lib.ptr(self.host_scalars))
         h = C.c_void_p()
         _lib.check(self.lib.oac_trainer_create(C.byref(cfg), C.byref(buf), C.byref(h)), "oac_trainer_create")
         self.handle = h

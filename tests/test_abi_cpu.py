@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert set(_lib.EXPORTS) == set(names)
-    assert L.oac_abi_version() == 1
+    assert L.oac_abi_version() == 2
 
 
 def test_ctypes_structs_match_header_sizes():
@@ -33,7 +33,7 @@ def test_ctypes_structs_match_header_sizes():
     # field-by-field mirrors of the C structs (natural alignment on both sides)
     assert C.sizeof(_lib.OacNetLayout) == 6 * 4 + 7 * 8
     assert C.sizeof(_lib.OacConfig) == 16 * 4 + 12 * 4 + 8
-    assert C.sizeof(_lib.OacBuffers) == 6 * 8
+    assert C.sizeof(_lib.OacBuffers) == 7 * 8
 
 
 @pytest.mark.parametrize("algo,kw,n_nets,n_train", [
