@@ -14,6 +14,7 @@
 // 26 addmm + 29 mm + ~150 Adam + 48 Polyak launches).
 #pragma once
 #include "oac_internal.h"
+#include "tma_util.cuh"
 
 namespace oac {
 
@@ -22,6 +23,7 @@ struct StageParams {
     ArenaSet as;
     AdamHyper hyper;
     int kc;                   // K chunk staged per pass (multiple of 4; >= K when it fits)
+    const CUtensorMap* tmaps; // gemm_sk_kernel<.., .., true>: [2 * n_tasks] fp32 tensor maps of the A and B operands
 };
 
 __device__ __forceinline__ float relu(float x) { return x > 0.f ? x : 0.f; }
@@ -356,9 +358,22 @@ gemm_stage_kernel(StageParams sp) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SK_BM = 32, SK_BN = 32, SK_T = 4, SK_KS = 4, SK_THREADS = 256, SK_PLD = 33;
 
-template <bool AT, bool BT>
+// TMA = true: the whole-K operand tiles are fetched by ONE thread with cp.async.bulk.tensor (fp32 tensor maps, bounds
+// zero-filled by the TMA unit) and everybody waits on one mbarrier, instead of every thread computing addresses and
+// predicates for its cp.async chunks (a fifth of this kernel's instructions at K = 393).  K-contiguous operands land in
+// SWIZZLE_128B atoms ([k-atom of 32][32 rows][128 B], 16-byte unit u of row r at u ^ (r & 7): conflict-free LDS.128 for
+// lanes on different rows), M/N-contiguous ones as dense [k][32] rows -- the layout the cp.async path uses as well.
+__host__ __device__ inline int sk_rows_per_box(int K) { const int k4 = (K + 3) & ~3; return k4 < 256 ? k4 : 256; }
+__host__ __device__ inline int sk_tile_bytes(bool mn_major, int K) {
+    if (!mn_major) return ((K + 31) >> 5) * 4096;
+    const int rb = sk_rows_per_box(K);
+    return ((K + rb - 1) / rb) * rb * 128;
+}
+
+template <bool AT, bool BT, bool TMA = false>
 __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int by, int bz) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t s_tma_bar;
     __shared__ AdamScalars s_adam;
     __shared__ float s_bsum[8][SK_BM];
 
@@ -383,8 +398,11 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     const int kp = kpad_of(kc);
     const int a_ld = AT ? SK_BM : kp;
     const int b_ld = BT ? SK_BN : kp;
-    float* As = smem;
-    float* Bs = smem + (AT ? kc * SK_BM : SK_BM * kp);
+    // TMA: 1024-byte aligned tiles (swizzle atoms), A then B, sized by this task's K
+    float* tma_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem) + ((1024u - (smem_u32(smem) & 1023u)) & 1023u));
+    float* As = TMA ? tma_base : smem;
+    float* Bs = TMA ? tma_base + sk_tile_bytes(AT, K) / 4 : smem + (AT ? kc * SK_BM : SK_BM * kp);
+    float* red = TMA ? tma_base : smem;            // the k-groups' partial tiles reuse the operand area
 
     const bool is_adam = T.epi == EPI_ADAM;
     float acc[SK_T][SK_T];
@@ -398,21 +416,48 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     const int r0 = AT ? ty * SK_T : ty, rs = AT ? 1 : 8;
     const int c0 = BT ? tx * SK_T : tx, cs = BT ? 1 : 8;
 
-    for (int k0 = 0; k0 < K; k0 += kc) {
-        const int kn = min(kc, K - k0);
+    for (int k0 = 0; k0 < K; k0 += (TMA ? K : kc)) {
+        const int kn = TMA ? K : min(kc, K - k0);
         if (k0 > 0) __syncthreads();
         const int kn4 = (kn + 3) & ~3;            // k tails are zero-filled
-        if (!AT) stage_tile<SK_THREADS>(As, a_ld, A, lda, m0, SK_BM, M, k0, kn, K, a_vec);
-        else     stage_tile<SK_THREADS>(As, a_ld, A, lda, k0, kn4, K, m0, SK_BM, M, a_vec);
-        if (!BT) stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, n0, SK_BN, N, k0, kn, K, b_vec);
-        else     stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, k0, kn4, K, n0, SK_BN, N, b_vec);
+        if (TMA) {
+            if (tid == 0) { mbar_init(&s_tma_bar, 1); fence_mbar_init(); }
+            __syncthreads();
+            if (tid == 0) {
+                const CUtensorMap* ta = sp.tmaps + 2 * by;
+                const CUtensorMap* tb = ta + 1;
+                const uint32_t bar = smem_u32(&s_tma_bar);
+                mbar_expect_tx(bar, (uint32_t)(sk_tile_bytes(AT, K) + sk_tile_bytes(BT, K)));
+                const uint32_t sa = smem_u32(As), sb = smem_u32(Bs);
+                const int rb = sk_rows_per_box(K);
+                if (!AT) for (int a = 0; a < ((K + 31) >> 5); ++a) tma_load_3d(sa + a * 4096, ta, a * 32, m0, seed, bar);
+                else     for (int b = 0; b * rb < K; ++b) tma_load_3d(sa + b * rb * 128, ta, m0, b * rb, seed, bar);
+                if (!BT) for (int a = 0; a < ((K + 31) >> 5); ++a) tma_load_3d(sb + a * 4096, tb, a * 32, n0, seed, bar);
+                else     for (int b = 0; b * rb < K; ++b) tma_load_3d(sb + b * rb * 128, tb, n0, b * rb, seed, bar);
+            }
+        } else {
+            if (!AT) stage_tile<SK_THREADS>(As, a_ld, A, lda, m0, SK_BM, M, k0, kn, K, a_vec);
+            else     stage_tile<SK_THREADS>(As, a_ld, A, lda, k0, kn4, K, m0, SK_BM, M, a_vec);
+            if (!BT) stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, n0, SK_BN, N, k0, kn, K, b_vec);
+            else     stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, k0, kn4, K, n0, SK_BN, N, b_vec);
+        }
         if (is_adam && k0 == 0 && tid == 0) {      // the step's Adam scalars: computed while the operand loads fly
             int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
             int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
             s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
         }
-        cp_async_wait_all();
-        __syncthreads();
+        if (TMA) {
+            mbar_wait(&s_tma_bar, 0);
+            __syncthreads();                       // s_adam
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        // K-contiguous operand element (row, k) under TMA: SWIZZLE_128B atoms
+        auto kmaj = [](const float* base, int row, int k) {
+            return reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(base) + (k >> 5) * 4096 + row * 128 +
+                                                   ((((k >> 2) & 7) ^ (row & 7)) << 4));
+        };
         const int ks = ((kn4 >> 2) + SK_KS - 1) / SK_KS * 4;          // this chunk's k per group (multiple of 4)
         const int kb = kg * ks, ke = min(kb + ks, kn4);
         if (!AT && !BT) {
@@ -420,9 +465,9 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
             for (int k = kb; k < ke; k += 4) {
                 float4 a[SK_T], b[SK_T];
 #pragma unroll
-                for (int i = 0; i < SK_T; ++i) a[i] = *reinterpret_cast<const float4*>(As + (r0 + i * rs) * a_ld + k);
+                for (int i = 0; i < SK_T; ++i) a[i] = TMA ? *kmaj(As, r0 + i * rs, k) : *reinterpret_cast<const float4*>(As + (r0 + i * rs) * a_ld + k);
 #pragma unroll
-                for (int j = 0; j < SK_T; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (c0 + j * cs) * b_ld + k);
+                for (int j = 0; j < SK_T; ++j) b[j] = TMA ? *kmaj(Bs, c0 + j * cs, k) : *reinterpret_cast<const float4*>(Bs + (c0 + j * cs) * b_ld + k);
 #pragma unroll
                 for (int i = 0; i < SK_T; ++i)
 #pragma unroll
@@ -438,7 +483,7 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
             for (int k = kb; k < ke; k += 4) {
                 float4 a[SK_T];
 #pragma unroll
-                for (int i = 0; i < SK_T; ++i) a[i] = *reinterpret_cast<const float4*>(As + (r0 + i * rs) * a_ld + k);
+                for (int i = 0; i < SK_T; ++i) a[i] = TMA ? *kmaj(As, r0 + i * rs, k) : *reinterpret_cast<const float4*>(As + (r0 + i * rs) * a_ld + k);
                 float b[4][SK_T];
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) load_adjacent<SK_T>(Bs + (k + kk) * b_ld + c0, b[kk]);
@@ -480,7 +525,7 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     pdl_trigger();
     // ---- the four k-groups' partial tiles meet in shared memory (the operand tiles are dead) ----
     __syncthreads();
-    float* part = smem;                                           // [SK_KS][32][SK_PLD]
+    float* part = red;                                            // [SK_KS][32][SK_PLD]
 #pragma unroll
     for (int i = 0; i < SK_T; ++i)
 #pragma unroll
@@ -563,10 +608,10 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     }
 }
 
-template <bool AT, bool BT>
+template <bool AT, bool BT, bool TMA = false>
 __global__ void __launch_bounds__(SK_THREADS) gemm_sk_kernel(StageParams sp) {
     pdl_wait();
-    gemm_sk_body<AT, BT>(sp, blockIdx.x, blockIdx.y, blockIdx.z);
+    gemm_sk_body<AT, BT, TMA>(sp, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 }  // namespace oac

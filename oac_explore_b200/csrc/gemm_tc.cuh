@@ -25,36 +25,6 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_BM = 128;
 // k elements per ring slot are a stage parameter (kc: 32 / 64 / 128, a multiple of the 32-element atom)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return done != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // bounded spin: a lost arrival must trap, not hang the GPU
-    for (uint32_t it = 0; it < (1u << 26); ++it)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
-}
-// same, but a failed probe backs off: single-lane producer / MMA loops would otherwise burn issue slots that the
-// epilogue warps of the same SM sub-partition need (18 % of the instruction stream in a mid-round ncu capture)
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
-        if (mbar_try_wait(bar, parity)) return;
-        __nanosleep(32);
-    }
-    __trap();
-}
-
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }

@@ -141,6 +141,7 @@ struct Stage {
     int use_tc = 0, bn = 0, tmem_cols = 0, n_main = 1;     // tcgen05 path
     // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
     int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
+    int sk_tma = 0;             // latency-regime FFMA tile with TMA-staged operands (tensor maps in ws_tmaps)
     void* ws_tmaps = nullptr;
     int max_tiles = 0;
     int max_rows = 0;
@@ -183,6 +184,7 @@ struct OacTrainer {
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
+    bool allow_sk_tma = true;  // OAC_NO_SK_TMA=1: cp.async staging in the latency-regime FFMA tile
     bool allow_mega = false;   // OAC_MEGA=1: the whole latency-regime step as one cooperative kernel (mega.cuh; measured slower)
 };
 
@@ -814,6 +816,50 @@ static void glue_plan(Stage& s, long long rows_total, bool stages_weights) {
     s.glue_iters = stages_weights ? (int)std::max<long long>(1, std::min<long long>(16, want)) : 1;
 }
 
+// Latency-regime FFMA tile with TMA staging: fp32 tensor maps (no conversion) of both operands of every task, 32 x 32
+// boxes in SWIZZLE_128B for K-contiguous operands, 32-wide row boxes for M/N-contiguous ones.  Falls back silently
+// (cp.async staging) when an operand cannot be described (row stride not a multiple of 16 B, unaligned base) or the
+// whole-K tiles of a task do not fit.
+static int sk_tma_plan(OacTrainer& t, Stage& s) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return 0;
+    const int seeds = t.cfg.n_seeds;
+    size_t smem = 0;
+    for (int a = 0; a < AR_COUNT; ++a)
+        if (seeds > 1 && (t.as.stride[a] & 3)) return 0;
+    for (const GemmTask& g : s.gemm) {
+        if ((g.lda & 3) || (g.ldb & 3) || !al16(resolve(t.as, g.A, 0)) || !al16(resolve(t.as, g.B, 0))) return 0;
+        smem = std::max(smem, (size_t)sk_tile_bytes(g.a_trans != 0, g.K) + sk_tile_bytes(g.b_trans != 0, g.K));
+    }
+    smem = std::max(smem, sizeof(float) * SK_KS * SK_BM * SK_PLD) + 1024;
+    if (smem > 110 * 1024) return 0;                           // keep two CTAs per SM
+    std::vector<CUtensorMap> maps(2 * s.gemm.size());
+    for (size_t i = 0; i < s.gemm.size(); ++i) {
+        const GemmTask& g = s.gemm[i];
+        for (int op = 0; op < 2; ++op) {
+            const Ref r = op == 0 ? g.A : g.B;
+            const bool mn = op == 0 ? g.a_trans != 0 : g.b_trans != 0;
+            const int ld = op == 0 ? g.lda : g.ldb;
+            const int ext = op == 0 ? g.M : g.N;
+            const long long sstride = std::max<long long>(t.as.stride[r.arena], 4);
+            cuuint64_t dims[3], strides[2];
+            cuuint32_t box[3], es[3] = {1, 1, 1};
+            if (!mn) { dims[0] = (cuuint64_t)g.K; dims[1] = (cuuint64_t)ext; box[0] = 32; box[1] = 32; }
+            else     { dims[0] = (cuuint64_t)ext; dims[1] = (cuuint64_t)g.K; box[0] = 32; box[1] = (cuuint32_t)sk_rows_per_box(g.K); }
+            dims[2] = (cuuint64_t)seeds; box[2] = 1;
+            strides[0] = (cuuint64_t)ld * 4; strides[1] = (cuuint64_t)sstride * 4;
+            CUresult rc = enc(&maps[2 * i + op], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)resolve(t.as, r, 0), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) return 0;
+        }
+    }
+    if (int e = upload(t, maps.data(), maps.size(), &s.ws_tmaps)) return e;
+    s.sk_tma = 1;
+    s.smem = smem;
+    return 0;
+}
+
 static int finalize(OacTrainer& t) {
     const int seeds = t.cfg.n_seeds;
     for (Stage& s : t.stages) {
@@ -898,6 +944,7 @@ static int finalize(OacTrainer& t) {
             while (kc > 16 && bytes_of(kc) > budget) kc = ((kc / 2) + 3) & ~3;
             s.kc = kc; s.smem = bytes_of(kc);
             if (s.small_tiles) s.smem = std::max(s.smem, sizeof(float) * SK_KS * SK_BM * SK_PLD);   // the k-groups' partial tiles
+            if (s.small_tiles && t.allow_sk_tma) { if (int e = sk_tma_plan(t, s)) return e; }
             s.max_tiles = 0;
             for (auto& g : s.gemm) {
                 g.tiles_m = (g.M + bm - 1) / bm; g.tiles_n = (g.N + bm - 1) / bm;
@@ -1014,6 +1061,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
     {
         if (s.kind == ST_GEMM) {
             StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
+            sp.tmaps = s.sk_tma ? (const CUtensorMap*)s.ws_tmaps : nullptr;
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
             if (s.use_ws) {
                 WsParams wp; wp.sp = sp; wp.tmaps = (const CUtensorMap*)s.ws_tmaps; wp.n_tasks = (int)s.gemm.size();
@@ -1044,9 +1092,15 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             }
             const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
             switch (sel) {
-                case 0: launch_pdl(gemm_sk_kernel<false, false>, grid, dim3(SK_THREADS), s.smem, st, sp); break;
-                case 1: launch_pdl(gemm_sk_kernel<false, true>, grid, dim3(SK_THREADS), s.smem, st, sp); break;
-                case 2: launch_pdl(gemm_sk_kernel<true, true>, grid, dim3(SK_THREADS), s.smem, st, sp); break;
+                case 0: if (s.sk_tma) launch_pdl(gemm_sk_kernel<false, false, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
+                        else launch_pdl(gemm_sk_kernel<false, false>, grid, dim3(SK_THREADS), s.smem, st, sp);
+                        break;
+                case 1: if (s.sk_tma) launch_pdl(gemm_sk_kernel<false, true, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
+                        else launch_pdl(gemm_sk_kernel<false, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
+                        break;
+                case 2: if (s.sk_tma) launch_pdl(gemm_sk_kernel<true, true, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
+                        else launch_pdl(gemm_sk_kernel<true, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
+                        break;
                 case 3: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, false>, grid, dim3(256), s.smem, st, sp); break;
                 case 4: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, true>, grid, dim3(256), s.smem, st, sp); break;
                 default: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, true, true>, grid, dim3(256), s.smem, st, sp); break;
@@ -1101,7 +1155,7 @@ static int mega_plan(OacTrainer& t) {
         if (s.kind == ST_GEMM) {
             m.kind = s.a_trans ? MK_GEMM_TT : (s.b_trans ? MK_GEMM_NT : MK_GEMM_NN);
             m.gx = s.max_tiles; m.gy = (int)s.gemm.size(); m.gz = seeds;
-            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
+            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc; sp.tmaps = nullptr;
             void* d = nullptr;
             if (int e = upload(t, &sp, 1, &d)) return e;
             m.params = d;
@@ -1234,7 +1288,9 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
+    { const char* nk = getenv("OAC_NO_SK_TMA"); t->allow_sk_tma = !(nk && nk[0] == '1'); }
     { const char* nm = getenv("OAC_MEGA"); t->allow_mega = (nm && nm[0] == '1'); }      // measured slower than the graph: opt-in
+    if (t->allow_mega) t->allow_sk_tma = false;       // the single-launch kernel runs the cp.async staging of the stage bodies
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
     else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
@@ -1260,6 +1316,9 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         cudaError_t e = cudaSuccess;
         auto opt_in = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, big); };
         opt_in((const void*)gemm_sk_kernel<false, false>);
+        opt_in((const void*)gemm_sk_kernel<false, false, true>);
+        opt_in((const void*)gemm_sk_kernel<false, true, true>);
+        opt_in((const void*)gemm_sk_kernel<true, true, true>);
         opt_in((const void*)gemm_sk_kernel<false, true>);
         opt_in((const void*)gemm_sk_kernel<true, true>);
         opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>);
@@ -1438,6 +1497,9 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
     {
         const int big = 212 * 1024;
         cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute((const void*)gemm_sk_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_sk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
