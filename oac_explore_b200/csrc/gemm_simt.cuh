@@ -416,6 +416,22 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     const int r0 = AT ? ty * SK_T : ty, rs = AT ? 1 : 8;
     const int c0 = BT ? tx * SK_T : tx, cs = BT ? 1 : 8;
 
+    // epilogue mapping (thread -> one row, 4 adjacent columns), known up front so that the Adam operands can be prefetched
+    const int er = tid >> 3, ec = (tid & 7) << 2;
+    float* ep_C = nullptr; float* ep_m = nullptr; float* ep_v = nullptr; float* ep_t = nullptr;
+    bool ep_vec = false;
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = p4, v4 = p4, t4 = p4;
+    if (is_adam && m0 + er < M) {
+        const long long e0 = (long long)(m0 + er) * T.ldc + n0 + ec;
+        ep_C = resolve(sp.as, T.C, seed) + e0;
+        ep_m = sp.as.base[AR_ADAM_M] + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off + e0;
+        ep_v = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off + e0;
+        ep_t = T.target_off >= 0 ? sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off + e0 : nullptr;
+        ep_vec = (n0 + ec + 3 < N) && ((T.ldc & 3) == 0) &&
+                 (((reinterpret_cast<uintptr_t>(ep_C) | reinterpret_cast<uintptr_t>(ep_m) | reinterpret_cast<uintptr_t>(ep_v) |
+                    reinterpret_cast<uintptr_t>(ep_t)) & 15) == 0);
+    }
+
     for (int k0 = 0; k0 < K; k0 += (TMA ? K : kc)) {
         const int kn = TMA ? K : min(kc, K - k0);
         if (k0 > 0) __syncthreads();
@@ -440,6 +456,14 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
             else     stage_tile<SK_THREADS>(As, a_ld, A, lda, k0, kn4, K, m0, SK_BM, M, a_vec);
             if (!BT) stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, n0, SK_BN, N, k0, kn, K, b_vec);
             else     stage_tile<SK_THREADS>(Bs, b_ld, B, ldb, k0, kn4, K, n0, SK_BN, N, b_vec);
+        }
+        if (k0 == 0 && ep_vec) {
+            // this thread's parameter / moment / target float4s are requested now and consumed in the epilogue: their
+            // L2 round trip overlaps the operand staging and the FFMA loop
+            p4 = *reinterpret_cast<const float4*>(ep_C);
+            a4 = *reinterpret_cast<const float4*>(ep_m);
+            v4 = *reinterpret_cast<const float4*>(ep_v);
+            if (ep_t) t4 = *reinterpret_cast<const float4*>(ep_t);
         }
         if (is_adam && k0 == 0 && tid == 0) {      // the step's Adam scalars: computed while the operand loads fly
             int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
@@ -532,7 +556,6 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
         for (int j = 0; j < SK_T; ++j) part[(kg * SK_BM + r0 + i * rs) * SK_PLD + c0 + j * cs] = acc[i][j];
     __syncthreads();
     // ---- epilogue: thread -> one row, 4 adjacent columns ----
-    const int er = tid >> 3, ec = (tid & 7) << 2;
     float v[SK_T];
 #pragma unroll
     for (int j = 0; j < SK_T; ++j) {
@@ -551,33 +574,22 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
         float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
         float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
         const AdamScalars s = s_adam;
-        const long long e0 = (long long)m * ldc + n0 + ec;
-        float* pm = m1 + T.adam_off + e0;
-        float* pv = m2 + T.adam_off + e0;
-        float* pt = (T.target_off >= 0 && s.do_polyak) ? pbase + T.target_off + e0 : nullptr;
-        const bool vec = (n0 + ec + 3 < N) && ((ldc & 3) == 0) &&
-                         (((reinterpret_cast<uintptr_t>(C + e0) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv) |
-                            reinterpret_cast<uintptr_t>(pt)) & 15) == 0);
-        if (vec) {
-            // one 16-byte load per array instead of four dependent scalar round trips (the loads of element j+1 may not
-            // pass the stores of element j: 40 % of this kernel's stall samples sat on them, ncu source view, mid-round)
-            float4 p4 = *reinterpret_cast<const float4*>(C + e0);
-            float4 a4 = *reinterpret_cast<const float4*>(pm);
-            float4 v4 = *reinterpret_cast<const float4*>(pv);
-            float4 t4 = pt ? *reinterpret_cast<const float4*>(pt) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pt = s.do_polyak ? ep_t : nullptr;
+        if (ep_vec) {
+            // one 16-byte access per array (issued before the main loop) instead of four dependent scalar round trips
             adam_update(v[0], &p4.x, &a4.x, &v4.x, pt ? &t4.x : nullptr, s);
             adam_update(v[1], &p4.y, &a4.y, &v4.y, pt ? &t4.y : nullptr, s);
             adam_update(v[2], &p4.z, &a4.z, &v4.z, pt ? &t4.z : nullptr, s);
             adam_update(v[3], &p4.w, &a4.w, &v4.w, pt ? &t4.w : nullptr, s);
-            *reinterpret_cast<float4*>(C + e0) = p4;
-            *reinterpret_cast<float4*>(pm) = a4;
-            *reinterpret_cast<float4*>(pv) = v4;
+            *reinterpret_cast<float4*>(ep_C) = p4;
+            *reinterpret_cast<float4*>(ep_m) = a4;
+            *reinterpret_cast<float4*>(ep_v) = v4;
             if (pt) *reinterpret_cast<float4*>(pt) = t4;
         } else {
 #pragma unroll
             for (int j = 0; j < SK_T; ++j) {
                 if (n0 + ec + j >= N) continue;
-                adam_update(v[j], C + e0 + j, pm + j, pv + j, pt ? pt + j : nullptr, s);
+                adam_update(v[j], ep_C + j, ep_m + j, ep_v + j, pt ? pt + j : nullptr, s);
             }
         }
         if (bias_on && ec == 0) {
