@@ -165,191 +165,10 @@ __device__ __forceinline__ void load_adjacent(const float* p, float (&v)[N]) {
     }
 }
 
-// One (tile, task, seed) block of a GEMM stage.  A device function so that the same code runs as its own kernel
-// (gemm_stage_kernel) and as a phase of the single-launch step (mega.cuh); global data produced by earlier stages is
-// read with cp.async / plain loads only (no ld.global.nc), which stay coherent across the grid barriers of that kernel.
-template <int BM, int BN, int TM, int TN, bool AT, bool BT>
-__device__ __forceinline__ void gemm_stage_body(const StageParams& sp, int bx, int by, int bz) {
-    constexpr int TY = BM / TM, TX = BN / TN, NT = TX * TY;
-    extern __shared__ __align__(16) float smem[];
-    __shared__ AdamScalars s_adam;
-
-    const GemmTask& T = sp.tasks[by];
-    const int tile = bx;
-    if (tile >= T.tiles_m * T.tiles_n) return;
-    const int seed = bz;
-    const int tm = tile / T.tiles_n, tn = tile - tm * T.tiles_n;
-    const int m0 = tm * BM, n0 = tn * BN;
-    const int tid = threadIdx.x;
-    const int tx = tid % TX, ty = tid / TX;
-
-    const float* __restrict__ A = resolve(sp.as, T.A, seed);
-    const float* __restrict__ B = resolve(sp.as, T.B, seed);
-    const int M = T.M, N = T.N, K = T.K;
-    const int lda = T.lda, ldb = T.ldb;
-    const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-
-    const int kc = sp.kc;
-    const int kp = kpad_of(kc);
-    const int a_ld = AT ? BM : kp;                 // smem row stride
-    const int b_ld = BT ? BN : kp;
-    float* As = smem;
-    float* Bs = smem + (AT ? kc * BM : BM * kp);
-
-    const bool is_adam = T.epi == EPI_ADAM;
-    if (is_adam && tid == 0) {
-        int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
-        int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
-        s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
-    }
-
-    float acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    float bsum[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) bsum[i] = 0.f;
-    const bool bias_on = AT && is_adam && T.has_bias && tn == 0;
-
-    for (int k0 = 0; k0 < K; k0 += kc) {
-        const int kn = min(kc, K - k0);
-        if (k0 > 0) __syncthreads();
-        const int kn4 = (kn + 3) & ~3;            // k tails are zero-filled (rows / columns beyond K)
-        if (!AT) stage_tile<NT>(As, a_ld, A, lda, m0, BM, M, k0, kn, K, a_vec);
-        else     stage_tile<NT>(As, a_ld, A, lda, k0, kn4, K, m0, BM, M, a_vec);
-        if (!BT) stage_tile<NT>(Bs, b_ld, B, ldb, n0, BN, N, k0, kn, K, b_vec);
-        else     stage_tile<NT>(Bs, b_ld, B, ldb, k0, kn4, K, n0, BN, N, b_vec);
-        cp_async_wait_all();
-        __syncthreads();
-        if (!AT && !BT) {
-#pragma unroll 2
-            for (int k = 0; k < kn4; k += 4) {
-                float4 a[TM], b[TN];
-#pragma unroll
-                for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + i * TY) * a_ld + k);
-#pragma unroll
-                for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (tx + j * TX) * b_ld + k);
-#pragma unroll
-                for (int i = 0; i < TM; ++i)
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) {
-                        acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
-                    }
-            }
-        } else if (!AT && BT) {
-#pragma unroll 2
-            for (int k = 0; k < kn4; k += 4) {
-                float4 a[TM];
-#pragma unroll
-                for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + i * TY) * a_ld + k);
-                float b[4][TN];
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) load_adjacent<TN>(Bs + (k + kk) * b_ld + tx * TN, b[kk]);
-#pragma unroll
-                for (int i = 0; i < TM; ++i)
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) {
-                        acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
-                        acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
-                        acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
-                        acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
-                    }
-            }
-        } else {
-            // AT (both operands row = k): rows beyond kn were never staged -> loop to kn only
-#pragma unroll 4
-            for (int k = 0; k < kn; ++k) {
-                float a[TM], b[TN];
-                load_adjacent<TM>(As + k * a_ld + ty * TM, a);
-                if (BT) load_adjacent<TN>(Bs + k * b_ld + tx * TN, b);
-                else {
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) b[j] = Bs[(tx + j * TX) * b_ld + k];
-                }
-#pragma unroll
-                for (int i = 0; i < TM; ++i) {
-                    if (bias_on) bsum[i] += a[i];
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-                }
-            }
-        }
-    }
-
-    pdl_trigger();
-    // ---- epilogue ----
-    // An M/N-contiguous operand gives a thread ADJACENT rows / columns (one 8- or 16-byte shared load per k instead of
-    // TM / TN scalar ones: the transposed products are bound by shared-memory wavefronts), a K-contiguous one interleaved
-    // rows / columns (conflict-free float4 loads along k).
-    auto rowi = [&](int i) { return AT ? ty * TM + i : ty + i * TY; };
-    auto colj = [&](int j) { return BT ? tx * TN + j : tx + j * TX; };
-    float* __restrict__ C = resolve(sp.as, T.C, seed);
-    const int ldc = T.ldc;
-    const int epi = T.epi;
-    if (is_adam) {
-        float* __restrict__ m1 = sp.as.base[AR_ADAM_M] + (long long)seed * sp.as.stride[AR_ADAM_M];
-        float* __restrict__ m2 = sp.as.base[AR_ADAM_V] + (long long)seed * sp.as.stride[AR_ADAM_V];
-        float* __restrict__ pbase = sp.as.base[AR_PARAM] + (long long)seed * sp.as.stride[AR_PARAM];
-        const AdamScalars s = s_adam;
-#pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            const int m = m0 + rowi(i);
-            if (m >= M) continue;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int n = n0 + colj(j);
-                if (n >= N) continue;
-                const long long e = (long long)m * ldc + n;
-                float* tgt = T.target_off >= 0 ? pbase + T.target_off + e : nullptr;
-                adam_update(acc[i][j], C + e, m1 + T.adam_off + e, m2 + T.adam_off + e, tgt, s);
-            }
-            if (bias_on && tx == 0) {
-                float* pb = resolve(sp.as, T.bias, seed) + m;
-                float* tgt = T.target_bias_off >= 0 ? pbase + T.target_bias_off + m : nullptr;
-                if (T.train_bias) {
-                    adam_update(bsum[i], pb, m1 + T.adam_bias_off + m, m2 + T.adam_bias_off + m, tgt, s);
-                } else if (tgt != nullptr && s.do_polyak) {
-                    // a frozen bias still takes part in soft_update_from_to (it is a parameter)
-                    *tgt = __fadd_rn(__fmul_rn(*tgt, s.one_m_tau), __fmul_rn(*pb, s.tau));
-                }
-            }
-        }
-        return;
-    }
-    const float* bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
-    const float* mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int m = m0 + rowi(i);
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int n = n0 + colj(j);
-            if (n >= N) continue;
-            float v = acc[i][j];
-            if (epi == EPI_BIAS) v += bias[n];
-            else if (epi == EPI_BIAS_RELU) v = relu(v + bias[n]);
-            else if (epi == EPI_MASK) v = mask[(long long)m * T.ldmask + n] > 0.f ? v : 0.f;
-            C[(long long)m * ldc + n] = v;
-        }
-    }
-}
-
-template <int BM, int BN, int TM, int TN, bool AT, bool BT>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
-gemm_stage_kernel(StageParams sp) {
-    pdl_wait();
-    gemm_stage_body<BM, BN, TM, TN, AT, BT>(sp, blockIdx.x, blockIdx.y, blockIdx.z);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Latency-regime tile: 32 x 32 outputs per CTA, 256 threads = 4 k-groups x 64 threads, 4 x 4 outputs per thread.
+// The FFMA tile: 32 x 32 outputs per CTA, 256 threads = 4 k-groups x 64 threads, 4 x 4 outputs per thread.  A device
+// function (gemm_sk_body) so that the same code runs as its own kernel and as a phase of the single-launch step
+// (mega.cuh); data produced by earlier stages is read with cp.async / TMA / plain loads only (no ld.global.nc).
 // A single seed's stages have too few outputs to give every thread a large register tile AND fill the chip, and the
 // 2 x 2-per-thread tile this replaces was bound by shared-memory wavefronts (4 LDS.128 per 16 FFMA; 37 % of its stall
 // samples at the first FFMA after the loads, profiles/r01_gemm_simt).  Splitting K four ways inside the CTA keeps

@@ -4,7 +4,7 @@
 // chip; as separate kernels (even replayed from a CUDA graph) each stage pays ~4 us of launch, ramp and drain on top
 // of its work (profiles/r01: 6.2 us for a K = 1 stage).  Here the WHOLE step is one cooperative kernel: a persistent grid
 // of 2 CTAs per SM walks the phases of the step, every CTA taking virtual blocks of the phase's stages
-// (gemm_stage_body / policy_head_body / critic_head_body / policy_grad_body -- the same device code the stand-alone
+// (gemm_sk_body / policy_head_body / critic_head_body / policy_grad_body -- the same device code the stand-alone
 // kernels run), and phases are separated by a grid-wide barrier (release arrive + acquire spin, ~1.5 us) instead of a
 // kernel boundary.  Stages the two-lane schedule marks as independent (lane 1) share a phase with the critical-chain
 // stage they overlap, so the idle SMs of that phase do their blocks.

@@ -931,8 +931,11 @@ static int finalize(OacTrainer& t) {
                 if (int e = upload(t, s.gemm.data(), s.gemm.size(), &s.dev)) return e;
                 continue;
             }
-            s.small_tiles = (tiles64 * seeds < 2 * 148);
-            const int bm = s.small_tiles ? 32 : 64;
+            // one FFMA tile shape: 32 x 32 outputs, 4-way split-K (gemm_sk_kernel).  A 64 x 64 / 4 x 4-per-thread variant
+            // for large grids was measured slower at every seed count (64 seeds: 4.32 vs 3.26 ms per step) and is gone.
+            s.small_tiles = 1;
+            (void)tiles64;
+            const int bm = 32;
             // largest K chunk (multiple of 4) whose A+B tiles fit the shared-memory budget
             auto bytes_of = [&](int kc) {
                 size_t a = s.a_trans ? (size_t)kc * bm : (size_t)bm * kpad_of(kc);
@@ -940,7 +943,7 @@ static int finalize(OacTrainer& t) {
                 return (a + b) * sizeof(float);
             };
             int kc = (kmax + 3) & ~3;
-            const size_t budget = s.small_tiles ? 100 * 1024 : 208 * 1024;   // small tiles: keep 2 CTAs / SM
+            const size_t budget = 100 * 1024;                          // keep 2 CTAs / SM
             while (kc > 16 && bytes_of(kc) > budget) kc = ((kc / 2) + 3) & ~3;
             s.kc = kc; s.smem = bytes_of(kc);
             if (s.small_tiles) s.smem = std::max(s.smem, sizeof(float) * SK_KS * SK_BM * SK_PLD);   // the k-groups' partial tiles
@@ -1090,7 +1093,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                 OAC_CUDA(cudaGetLastError());
                 return 0;
             }
-            const int sel = (s.small_tiles ? 0 : 3) + (s.a_trans ? 2 : (s.b_trans ? 1 : 0));
+            const int sel = s.a_trans ? 2 : (s.b_trans ? 1 : 0);
             switch (sel) {
                 case 0: if (s.sk_tma) launch_pdl(gemm_sk_kernel<false, false, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
                         else launch_pdl(gemm_sk_kernel<false, false>, grid, dim3(SK_THREADS), s.smem, st, sp);
@@ -1101,9 +1104,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                 case 2: if (s.sk_tma) launch_pdl(gemm_sk_kernel<true, true, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
                         else launch_pdl(gemm_sk_kernel<true, true>, grid, dim3(SK_THREADS), s.smem, st, sp);
                         break;
-                case 3: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, false>, grid, dim3(256), s.smem, st, sp); break;
-                case 4: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, false, true>, grid, dim3(256), s.smem, st, sp); break;
-                default: launch_pdl(gemm_stage_kernel<64, 64, 4, 4, true, true>, grid, dim3(256), s.smem, st, sp); break;
+                default: break;
             }
         } else if (s.kind == ST_POLICY_HEAD) {
             PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps; p.iters = s.glue_iters;
@@ -1321,9 +1322,6 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_in((const void*)gemm_sk_kernel<true, true, true>);
         opt_in((const void*)gemm_sk_kernel<false, true>);
         opt_in((const void*)gemm_sk_kernel<true, true>);
-        opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>);
-        opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>);
-        opt_in((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>);
         opt_in((const void*)gemm_tc_kernel<false, false, false>);
         opt_in((const void*)gemm_tc_kernel<false, true, false>);
         opt_in((const void*)gemm_tc_kernel<true, true, false>);
@@ -1502,9 +1500,6 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
         cudaFuncSetAttribute((const void*)gemm_sk_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_sk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_sk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute((const void*)gemm_stage_kernel<64, 64, 4, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute((const void*)gemm_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
