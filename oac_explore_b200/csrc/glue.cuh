@@ -119,12 +119,25 @@ __device__ __forceinline__ void policy_head_body(const PolicyHeadParams& p, int 
             const float* wm = Ws + j * H;
             const float* ws = Ws + (A + j) * H;
             float sm = 0.f, ss = 0.f;
+            if (H == 256) {                                 // the common width: 8 unconditional steps
 #pragma unroll
-            for (int c = 0; c < GLUE_MAX_HR; ++c) {
-                const int k = lane + 32 * c;
-                if (k < H) { sm = fmaf(hreg[c], wm[k], sm); ss = fmaf(hreg[c], ws[k], ss); }
+                for (int c = 0; c < 8; ++c) {
+                    const int k = lane + 32 * c;
+                    sm = fmaf(hreg[c], wm[k], sm); ss = fmaf(hreg[c], ws[k], ss);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < GLUE_MAX_HR; ++c) {
+                    const int k = lane + 32 * c;
+                    if (k < H) { sm = fmaf(hreg[c], wm[k], sm); ss = fmaf(hreg[c], ws[k], ss); }
+                }
             }
-            sm = warp_sum(sm); ss = warp_sum(ss);
+            // the two reductions interleaved: one shuffle latency chain instead of two
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            }
             if (lane == 0) { outv[j] = sm + bs[j]; outv[A + j] = ss + bs[A + j]; }
         }
     }
