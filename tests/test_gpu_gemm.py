@@ -80,3 +80,14 @@ def test_ws_tcgen05_tf32_gemm(M, N, K, a_trans, b_trans):
         got, ref = run_gemm(1, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=relu and a_trans == 0, align4=True,
                             want_kernel=2)
         assert rel_err(got, ref) <= 1.5e-3, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("M,N,K", WS_SHAPES)
+@pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
+def test_simt_gemm_tma_staged_operands(M, N, K, a_trans, b_trans):
+    """16-byte aligned operands make the FFMA tile fetch its whole-K tiles with TMA (fp32 tensor maps, SWIZZLE_128B atoms
+    for K-contiguous operands, bounds zero-filled by the TMA unit); K = 1000 exceeds the shared-memory budget and takes
+    the chunked cp.async path through the same kernel."""
+    got, ref = run_gemm(0, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=(b_trans == 0 and a_trans == 0), align4=True,
+                        want_kernel=0)
+    assert rel_err(got, ref) <= 2e-6, rel_err(got, ref)

@@ -5,7 +5,7 @@
 set -u
 PHASE=${1:-all}        # bench | ncu | all  (gpurun copies back at most 64 MiB per call: the two full captures go alone)
 O=gpurun_out
-T="r01j"
+T="r01k"
 if [ "$PHASE" != "ncu" ]; then
 python bench.py > $O/${T}_bench_single.json 2> $O/${T}_bench_single.err
 python bench.py --impl reference --steps 200 --warmup 5 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err

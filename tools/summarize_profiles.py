@@ -83,7 +83,7 @@ def traffic(rep, kernel_substr):
 
 if __name__ == "__main__":
     import json
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01i"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01k"
     launch_list(tag + "_launches_single_fp32.csv", 19)
     launch_list(tag + "_launches_64seeds_tf32.csv", 19)
     full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
