@@ -201,7 +201,8 @@ struct Builder {
     bool tensor_glue;
     explicit Builder(OacTrainer& tr) : t(tr), c(tr.cfg), L(tr.lay) {
         O = c.obs_dim; A = c.act_dim; H = c.hidden; B = c.batch;
-        tensor_glue = c.gemm_path == OAC_GEMM_TF32 && (long long)c.n_seeds * c.batch >= 2048;
+        static const long long tg_rows = getenv("OAC_TENSOR_GLUE_ROWS") ? atoll(getenv("OAC_TENSOR_GLUE_ROWS")) : 2048;   // measurement aid
+        tensor_glue = c.gemm_path == OAC_GEMM_TF32 && (long long)c.n_seeds * c.batch >= tg_rows;
         split_adam = tensor_glue && tr.allow_split && tr.allow_ws;
         if (split_adam) grad = work(L.adam_floats);
     }
@@ -483,7 +484,8 @@ void Builder::build_sac() {
     const bool mode_b = c.stale_graph_mode == 1;
     // Latency regime (few seeds): a step is a chain of small kernels that leave most SMs idle, so independent work runs
     // on a second lane: the critics' forward on the DATA rows does not depend on the policy and overlaps its forward.
-    const bool two_lanes = !tensor_glue && c.n_seeds * (long long)B <= 1024 && t.allow_lanes;
+    static const long long lane_rows = getenv("OAC_LANE_ROWS") ? atoll(getenv("OAC_LANE_ROWS")) : 1024;                  // measurement aid
+    const bool two_lanes = !tensor_glue && c.n_seeds * (long long)B <= lane_rows && t.allow_lanes;
     if (two_lanes) {
         { Stage& s = add_stage(ST_GEMM, "critic_l1_data"); s.lane = 1; crit_l1_rows(s, q1, 2, ca1, B); crit_l1_rows(s, q2, 2, ca2, B); }
         { Stage& s = add_stage(ST_GEMM, "critic_l2_data"); s.lane = 1; crit_l2_rows(s, q1, ca1, B); crit_l2_rows(s, q2, ca2, B); }
