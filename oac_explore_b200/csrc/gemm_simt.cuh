@@ -256,9 +256,8 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
         if (k0 > 0) __syncthreads();
         const int kn4 = (kn + 3) & ~3;            // k tails are zero-filled
         if (TMA) {
-            if (tid == 0) { mbar_init(&s_tma_bar, 1); fence_mbar_init(); }
-            __syncthreads();
-            if (tid == 0) {
+            if (tid == 0) {                          // init, arm and issue in one go; the others meet the barrier below
+                mbar_init(&s_tma_bar, 1); fence_mbar_init();
                 const CUtensorMap* ta = sp.tmaps + 2 * by;
                 const CUtensorMap* tb = ta + 1;
                 const uint32_t bar = smem_u32(&s_tma_bar);
@@ -290,8 +289,8 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
             s_adam = make_adam_scalars(sp.hyper, T.lr, t, ts);
         }
         if (TMA) {
+            __syncthreads();                       // the mbarrier is initialised; s_adam is written
             mbar_wait(&s_tma_bar, 0);
-            __syncthreads();                       // s_adam
         } else {
             cp_async_wait_all();
             __syncthreads();
