@@ -69,7 +69,57 @@ struct PolicyHeadParams {
     int iters;               // row groups (of GLUE_SPC rows) per CTA
     int head_from_gemm;      // 1: the head layer ran as a tensor-core GEMM stage; this kernel only samples
     float* host_scalars;     // optional mapped pinned host copy of the step's scalars, [n_seeds, SC_COUNT]
+    int tail_in_own_kernel;  // 1: policy_head ends at its last store; step_tail_kernel follows on a side lane
 };
+
+// Once per seed and step, after every row's log-prob is written: bump the step counters, take the entropy-temperature
+// Adam step (trainer/trainer.py:140-149) and publish the step's scalars.  Runs in the last policy_head CTA to finish, or
+// as a one-CTA-per-seed kernel of its own on a side lane (the single-seed critical chain then ends policy_head at its
+// last store: the fence / ticket / reduction tail cost ~2 us there).
+__device__ __forceinline__ void step_tail(const PolicyHeadParams& p, int seed) {
+    __shared__ float s_red[GLUE_THREADS];
+    const int B = p.B;
+    float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
+    int32_t* cnt = p.as.counters + seed * p.as.n_counters;
+    const int step = cnt[CNT_TRAIN_STEPS];
+    float part = 0.f;
+    if (p.alpha.enabled) {
+        const PolicyHeadTask& TA = p.tasks[p.alpha.task];
+        const volatile float* lp = io + p.off_log_pi + TA.out_row0 + (long long)p.alpha.block * B;
+        for (int i = threadIdx.x; i < B; i += GLUE_THREADS) part += lp[i];
+    }
+    s_red[threadIdx.x] = part;
+    __syncthreads();
+    for (int s = GLUE_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cnt[CNT_TRAIN_STEPS] = step + 1;
+        for (int i = 0; i < p.n_opt_counters; ++i) cnt[CNT_OPT0 + i] += 1;
+        float* sc = io + p.off_scalars;
+        if (p.alpha.enabled) {
+            // alpha_loss = -(log_alpha * (log_pi + target_entropy).detach()).mean()  (trainer.py:140-146)
+            float mean_lp = s_red[0] / (float)B;
+            float* la = resolve(p.as, p.alpha.log_alpha, seed);
+            float* m1 = p.as.base[AR_ADAM_M] + (long long)seed * p.as.stride[AR_ADAM_M] + p.alpha.adam_off;
+            float* m2 = p.as.base[AR_ADAM_V] + (long long)seed * p.as.stride[AR_ADAM_V] + p.alpha.adam_off;
+            float tgt = mean_lp + p.alpha.target_entropy;
+            sc[SC_ALPHA_LOSS] = -(la[0] * tgt);
+            sc[SC_MEAN_LOGPI] = mean_lp;
+            AdamScalars s = make_adam_scalars(p.hyper, p.alpha.lr, cnt[CNT_OPT0 + p.alpha.counter], step + 1);
+            adam_update(-tgt, la, m1, m2, nullptr, s);
+            sc[SC_ALPHA] = expf(la[0]);      // POST-step alpha (trainer.py:147)
+        } else {
+            sc[SC_ALPHA] = 0.f;              // the fork's choice (trainer.py:148-149)
+            sc[SC_ALPHA_LOSS] = 0.f;
+        }
+        if (p.host_scalars != nullptr) {     // zero-copy device -> host: the caller only synchronises
+            float* hs = p.host_scalars + (long long)seed * SC_COUNT;
+            hs[SC_ALPHA] = sc[SC_ALPHA]; hs[SC_ALPHA_LOSS] = sc[SC_ALPHA_LOSS]; hs[SC_MEAN_LOGPI] = sc[SC_MEAN_LOGPI];
+        }
+    }
+}
 
 // Fused head layer + sampling: the [2A, H] head weights are staged in shared memory once per CTA; GLUE_G warps
 // share one row (each keeps the hidden row in registers and reduces every GLUE_G-th pair of dot products with
@@ -183,63 +233,32 @@ __device__ __forceinline__ void policy_head_body(const PolicyHeadParams& p, int 
     }
 
     pdl_trigger();
+    if (p.tail_in_own_kernel) return;          // step_tail_kernel runs on a side lane (multi-lane schedule)
     // ---- last CTA of this seed: bump step counters, entropy-temperature Adam step ----
     __shared__ int s_last;
-    __shared__ float s_red[GLUE_THREADS];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int total = gdx * gdy;
         int prev = atomicAdd(&cnt[CNT_TICKET0], 1);
         s_last = (prev == total - 1);
+        if (s_last) cnt[CNT_TICKET0] = 0;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    float part = 0.f;
-    if (p.alpha.enabled) {
-        const PolicyHeadTask& TA = p.tasks[p.alpha.task];
-        const volatile float* lp = io + p.off_log_pi + TA.out_row0 + (long long)p.alpha.block * B;
-        for (int i = threadIdx.x; i < B; i += GLUE_THREADS) part += lp[i];
-    }
-    s_red[threadIdx.x] = part;
-    __syncthreads();
-    for (int s = GLUE_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        cnt[CNT_TICKET0] = 0;
-        cnt[CNT_TRAIN_STEPS] = step + 1;
-        for (int i = 0; i < p.n_opt_counters; ++i) cnt[CNT_OPT0 + i] += 1;
-        float* sc = io + p.off_scalars;
-        if (p.alpha.enabled) {
-            // alpha_loss = -(log_alpha * (log_pi + target_entropy).detach()).mean()  (trainer.py:140-146)
-            float mean_lp = s_red[0] / (float)B;
-            float* la = resolve(p.as, p.alpha.log_alpha, seed);
-            float* m1 = p.as.base[AR_ADAM_M] + (long long)seed * p.as.stride[AR_ADAM_M] + p.alpha.adam_off;
-            float* m2 = p.as.base[AR_ADAM_V] + (long long)seed * p.as.stride[AR_ADAM_V] + p.alpha.adam_off;
-            float tgt = mean_lp + p.alpha.target_entropy;
-            sc[SC_ALPHA_LOSS] = -(la[0] * tgt);
-            sc[SC_MEAN_LOGPI] = mean_lp;
-            AdamScalars s = make_adam_scalars(p.hyper, p.alpha.lr, cnt[CNT_OPT0 + p.alpha.counter], step + 1);
-            adam_update(-tgt, la, m1, m2, nullptr, s);
-            sc[SC_ALPHA] = expf(la[0]);      // POST-step alpha (trainer.py:147)
-        } else {
-            sc[SC_ALPHA] = 0.f;              // the fork's choice (trainer.py:148-149)
-            sc[SC_ALPHA_LOSS] = 0.f;
-        }
-        if (p.host_scalars != nullptr) {     // zero-copy device -> host: the caller only synchronises
-            float* hs = p.host_scalars + (long long)seed * SC_COUNT;
-            hs[SC_ALPHA] = sc[SC_ALPHA]; hs[SC_ALPHA_LOSS] = sc[SC_ALPHA_LOSS]; hs[SC_MEAN_LOGPI] = sc[SC_MEAN_LOGPI];
-        }
-    }
+    step_tail(p, seed);
 }
 
 template <int G>
 __global__ void __launch_bounds__(GLUE_THREADS) policy_head_kernel(PolicyHeadParams p) {
     pdl_wait();
     policy_head_body<G>(p, p.use_external_eps, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y);
+}
+
+__global__ void __launch_bounds__(GLUE_THREADS) step_tail_kernel(PolicyHeadParams p) {     // grid = seeds
+    pdl_wait();
+    step_tail(p, blockIdx.x);
 }
 
 // =====================================================================================

@@ -121,7 +121,7 @@ static int build_layout(const OacConfig& c, OacLayout& L, NetIds& ids) {
 // ------------------------------------------------------------------------------------
 // program
 // ------------------------------------------------------------------------------------
-enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3, ST_ADAM = 4 };
+enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3, ST_ADAM = 4, ST_STEP_TAIL = 5 };
 
 struct Stage {
     int kind;
@@ -495,6 +495,13 @@ void Builder::build_sac() {
     if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
+    if (two_lanes && !t.allow_mega && !getenv("OAC_NO_TAIL_SPLIT")) {        // (env: A/B measurement aid)
+        // the step counters / entropy-temperature Adam step are needed by critic_head at the earliest: they leave the
+        // policy_head kernel (fence + ticket + reduction in its last CTA) for a one-CTA kernel on lane 2
+        t.stages.back().php.tail_in_own_kernel = 1;
+        Stage tail = t.stages.back();
+        Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = tail.ph; s.php = tail.php;
+    }
     if (two_lanes) {
         { Stage& s = add_stage(ST_GEMM, "critic_l1_pi");
           crit_l1_rows(s, q1, 1, ca1, 0); crit_l1_rows(s, q2, 1, ca2, 0); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
@@ -963,6 +970,10 @@ static int finalize(OacTrainer& t) {
             if (int e = upload(t, s.ph.data(), s.ph.size(), &s.dev)) return e;
             s.php.tasks = (const PolicyHeadTask*)s.dev;
             s.php.as = t.as; s.php.hyper = t.hyper;
+        } else if (s.kind == ST_STEP_TAIL) {
+            if (int e = upload(t, s.ph.data(), s.ph.size(), &s.dev)) return e;
+            s.php.tasks = (const PolicyHeadTask*)s.dev;
+            s.php.as = t.as; s.php.hyper = t.hyper;
         } else if (s.kind == ST_CRITIC_HEAD) {
             glue_plan(s, (long long)t.cfg.batch * seeds, false);
             s.chp.iters = s.glue_iters;
@@ -1115,6 +1126,8 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             const size_t smem = glue_smem(t, s);
             if (s.glue_g == 1) launch_pdl(policy_head_kernel<1>, grid, dim3(GLUE_THREADS), smem, st, p);
             else launch_pdl(policy_head_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
+        } else if (s.kind == ST_STEP_TAIL) {
+            launch_pdl(step_tail_kernel, dim3(seeds), dim3(GLUE_THREADS), 0, st, s.php);
         } else if (s.kind == ST_ADAM) {
             const long long per_cta = (long long)ADAM_THREADS * ADAM_UNROLL;
             dim3 grid((unsigned)((s.asp.total4 + per_cta - 1) / per_cta), seeds, 1);
