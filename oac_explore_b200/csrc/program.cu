@@ -468,6 +468,21 @@ struct Builder {
     }
 
     // X blocks: 0 [obs|a_tp] (G-OAC), 1 [obs|a_pi], 2 [obs|actions], 3 [next_obs|a_next]
+    // Latency regime (few seeds): a step is a chain of small kernels that leave most SMs idle, so independent work runs
+    // on side lanes (launch_stages).
+    bool latency_lanes() const {
+        static const long long lane_rows = getenv("OAC_LANE_ROWS") ? atoll(getenv("OAC_LANE_ROWS")) : 1024;              // measurement aid
+        return !tensor_glue && c.n_seeds * (long long)B <= lane_rows && t.allow_lanes;
+    }
+    // The step counters / entropy-temperature Adam step are needed by the first critic_head at the earliest: they leave
+    // the policy_head kernel just added (fence + ticket + reduction in its last CTA) for a one-CTA kernel on lane 2
+    // (measured per step: SAC 123.6 -> 119.4 us, P-OAC 129.6 -> 127.0, G-OAC 131.0 -> 128.9).
+    void split_step_tail() {
+        if (!latency_lanes() || t.allow_mega || getenv("OAC_NO_TAIL_SPLIT")) return;                                      // (env: A/B measurement aid)
+        t.stages.back().php.tail_in_own_kernel = 1;
+        Stage head = t.stages.back();
+        Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = head.ph; s.php = head.php;
+    }
     void build_sac();
     void build_poac();
     void build_goac();
@@ -482,10 +497,8 @@ void Builder::build_sac() {
     CritAct ta1 = alloc_crit(1, 1), ta2 = alloc_crit(1, 1);   // block 3
     PolGrad pg = alloc_polgrad();
     const bool mode_b = c.stale_graph_mode == 1;
-    // Latency regime (few seeds): a step is a chain of small kernels that leave most SMs idle, so independent work runs
-    // on a second lane: the critics' forward on the DATA rows does not depend on the policy and overlaps its forward.
-    static const long long lane_rows = getenv("OAC_LANE_ROWS") ? atoll(getenv("OAC_LANE_ROWS")) : 1024;                  // measurement aid
-    const bool two_lanes = !tensor_glue && c.n_seeds * (long long)B <= lane_rows && t.allow_lanes;
+    // second lane: the critics' forward on the DATA rows does not depend on the policy and overlaps its forward
+    const bool two_lanes = latency_lanes();
     if (two_lanes) {
         { Stage& s = add_stage(ST_GEMM, "critic_l1_data"); s.lane = 1; crit_l1_rows(s, q1, 2, ca1, B); crit_l1_rows(s, q2, 2, ca2, B); }
         { Stage& s = add_stage(ST_GEMM, "critic_l2_data"); s.lane = 1; crit_l2_rows(s, q1, ca1, B); crit_l2_rows(s, q2, ca2, B); }
@@ -495,13 +508,7 @@ void Builder::build_sac() {
     if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
-    if (two_lanes && !t.allow_mega && !getenv("OAC_NO_TAIL_SPLIT")) {        // (env: A/B measurement aid)
-        // the step counters / entropy-temperature Adam step are needed by critic_head at the earliest: they leave the
-        // policy_head kernel (fence + ticket + reduction in its last CTA) for a one-CTA kernel on lane 2
-        t.stages.back().php.tail_in_own_kernel = 1;
-        Stage tail = t.stages.back();
-        Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = tail.ph; s.php = tail.php;
-    }
+    split_step_tail();
     if (two_lanes) {
         { Stage& s = add_stage(ST_GEMM, "critic_l1_pi");
           crit_l1_rows(s, q1, 1, ca1, 0); crit_l1_rows(s, q2, 1, ca2, 0); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
@@ -581,11 +588,15 @@ void Builder::build_poac() {
     // next_obs noise FIRST here (:193 then :271) -- the host wrapper maps call order to slots
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 1); }
+    // Of the SAC program's lanes only the step tail pays here (measured, 127.0 us per step): the data-row critic forward
+    // on lane 1 (134.2 us) and the head / fc1 Adam stages on side lanes (129.0 us) cost more in forks and joins than the
+    // two critic phases of this step can hide.
+    split_step_tail();
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
       for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+sort+targets+dh2");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+sort+targets+dh2"); s.join = 3;
       memset(&s.chp, 0, sizeof(s.chp));
       for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0); s.chp.src[i].write_dh2 = 1; }
       for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.tf[i], ta[i], 0);
@@ -632,11 +643,12 @@ void Builder::build_goac() {
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1));
       s.ph.push_back(ph_task(tpol, tpa, 2 * B, 0, 0, 0, 0));
       fill_php(s, 0, 0, 0); s.php.alpha.enabled = 0; s.php.deterministic = 1; }
+    split_step_tail();                           // as in P-OAC: the only side-lane stage that pays (131.0 -> 128.9 us)
     { Stage& s = add_stage(ST_GEMM, "critic_l1");
       for (int i = 0; i < n; ++i) { crit_l1(s, t.ids.qf[i], 2, qa[i]); crit_l1(s, t.ids.tf[i], 3, ta[i]); } }
     { Stage& s = add_stage(ST_GEMM, "critic_l2");
       for (int i = 0; i < n; ++i) { crit_l2(s, t.ids.qf[i], qa[i]); crit_l2(s, t.ids.tf[i], ta[i]); } }
-    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2");
+    { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2"); s.join = 3;
       memset(&s.chp, 0, sizeof(s.chp));
       for (int i = 0; i < n; ++i) { s.chp.src[i] = head_src(t.ids.qf[i], qa[i], 0); s.chp.src[i].write_dh2 = 1; }
       for (int i = 0; i < n; ++i) s.chp.src[n + i] = head_src(t.ids.tf[i], ta[i], 0);
