@@ -768,9 +768,22 @@ static int ws_plan(OacTrainer& t, Stage& s) {
         for (auto& g : s.gemm) { const int bn = width(g, cap); n += (long long)((g.M + WS_BM - 1) / WS_BM) * ((g.N + bn - 1) / bn); }
         return n;
     };
-    // widest tiles that still give every SM work; the narrowest ones when even those cannot (single seed: latency)
+    // Tile width.  With many rounds of the persistent grid (>= 4 at the widest tile) the widest tiles that still give every
+    // SM work win: operand re-reads fall with the width.  With fewer, what counts is the number of rounds times the cost
+    // of a tile, which has a fixed part (pipeline fill, TMEM round trip, epilogue set-up: worth ~64 columns) next to the
+    // one that grows with the width (measured: 8 seeds 27.9k -> 31.4k seed-updates/s, 16 seeds 43.8k -> 48.7k, 32 seeds
+    // 60.9k -> 63.0k, 64 seeds unchanged).
     int cap = 256;
     while (cap > 32 && tiles(cap) * seeds < sm_count()) cap >>= 1;
+    if (tiles(256) * seeds < 4ll * sm_count()) {
+        double best = 1e30;
+        for (int cnd = 256; cnd >= 32; cnd >>= 1) {
+            const long long n = tiles(cnd) * seeds;
+            const long long rounds = (n + sm_count() - 1) / sm_count();
+            const double cost = rounds * (64.0 + cnd);
+            if (cost < best) { best = cost; cap = cnd; }
+        }
+    }
     // heaviest tiles first (epilogue elements dominate; an Adam element moves 8x the bytes of a stored one)
     auto tile_cost = [&](const GemmTask& g) {
         const double rows = std::min(g.M, (int)WS_BM), cols = std::min(g.N, width(g, cap));
