@@ -21,6 +21,7 @@
 #include "glue.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
+#include "gemm_fwd2.cuh"
 #include "adam_stream.cuh"
 #include "mega.cuh"
 #include "oac_error.h"
@@ -142,6 +143,8 @@ struct Stage {
     // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
     int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
     int sk_tma = 0;             // latency-regime FFMA tile with TMA-staged operands (tensor maps in ws_tmaps)
+    int fused2 = 0;             // tasks are [layer-1 ..., layer-2 ...] pairs of two dependent forward layers: one cluster launch
+    int fwd2_cluster = 0;       // (gemm_fwd2.cuh) when the plan allows it, else two plain launches
     void* ws_tmaps = nullptr;
     int max_tiles = 0;
     int max_rows = 0;
@@ -483,6 +486,10 @@ struct Builder {
         Stage head = t.stages.back();
         Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = head.ph; s.php = head.php;
     }
+    // two dependent forward layers as one cluster launch (gemm_fwd2.cuh): the FFMA latency regime only
+    bool fuse_fwd2() const {
+        return latency_lanes() && c.gemm_path == OAC_GEMM_FP32 && !t.allow_mega && !getenv("OAC_NO_FWD2");               // (env: A/B measurement aid)
+    }
     void build_sac();
     void build_poac();
     void build_goac();
@@ -499,17 +506,30 @@ void Builder::build_sac() {
     const bool mode_b = c.stale_graph_mode == 1;
     // second lane: the critics' forward on the DATA rows does not depend on the policy and overlaps its forward
     const bool two_lanes = latency_lanes();
-    if (two_lanes) {
+    // layer pairs as one cluster launch each (gemm_fwd2.cuh).  Measured per step: none 119.4 us, all three 117.3 us; any
+    // subset is between 118.7 and 123.5 us (the lanes' co-scheduling, not the sum of the parts, decides).
+    const bool fwd2 = fuse_fwd2();
+    if (two_lanes && fwd2) {
+        Stage& s = add_stage(ST_GEMM, "critic_l1+l2_data"); s.lane = 1; s.fused2 = 1;
+        crit_l1_rows(s, q1, 2, ca1, B); crit_l1_rows(s, q2, 2, ca2, B); crit_l2_rows(s, q1, ca1, B); crit_l2_rows(s, q2, ca2, B);
+    } else if (two_lanes) {
         { Stage& s = add_stage(ST_GEMM, "critic_l1_data"); s.lane = 1; crit_l1_rows(s, q1, 2, ca1, B); crit_l1_rows(s, q2, 2, ca2, B); }
         { Stage& s = add_stage(ST_GEMM, "critic_l2_data"); s.lane = 1; crit_l2_rows(s, q1, ca1, B); crit_l2_rows(s, q2, ca2, B); }
     }
+    if (fwd2) { Stage& s = add_stage(ST_GEMM, "policy_l1+l2"); s.fused2 = 1; pol_l1(s, pol, 2, pa); pol_l2(s, pol, pa); }
+    else {
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
+    }
     if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
     split_step_tail();
-    if (two_lanes) {
+    if (two_lanes && fwd2) {
+        Stage& s = add_stage(ST_GEMM, "critic_l1+l2_pi"); s.fused2 = 1;
+        crit_l1_rows(s, q1, 1, ca1, 0); crit_l1_rows(s, q2, 1, ca2, 0); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2);
+        crit_l2_rows(s, q1, ca1, 0); crit_l2_rows(s, q2, ca2, 0); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2);
+    } else if (two_lanes) {
         { Stage& s = add_stage(ST_GEMM, "critic_l1_pi");
           crit_l1_rows(s, q1, 1, ca1, 0); crit_l1_rows(s, q2, 1, ca2, 0); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
         { Stage& s = add_stage(ST_GEMM, "critic_l2_pi");
@@ -581,6 +601,7 @@ void Builder::build_poac() {
     std::vector<CritAct> qa, ta, pa_q;      // data rows (block 2), next rows (block 3), a_pi rows (block 1)
     for (int i = 0; i < n; ++i) { qa.push_back(alloc_crit(1, heads)); ta.push_back(alloc_crit(1, heads)); pa_q.push_back(alloc_crit(1, heads)); }
     PolGrad pg = alloc_polgrad();
+    // (fusing the layer pairs of this linear chain into cluster launches, gemm_fwd2.cuh, measured slower: 131.3 vs 127.0 us)
     { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
     { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
     if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
@@ -987,6 +1008,19 @@ static int finalize(OacTrainer& t) {
                 g.tiles_m = (g.M + bm - 1) / bm; g.tiles_n = (g.N + bm - 1) / bm;
                 s.max_tiles = std::max(s.max_tiles, g.tiles_m * g.tiles_n);
             }
+            if (s.fused2) {
+                // one cluster launch when every pair is (K-contiguous, bias[/relu]) x 2 with the same strip structure
+                const size_t np = s.gemm.size() / 2;
+                bool ok = s.sk_tma && !s.a_trans && !s.b_trans && s.gemm.size() % 2 == 0 && np > 0;
+                const int cl = ok ? s.gemm[0].tiles_n : 0;
+                ok = ok && cl >= 1 && cl <= 8;
+                for (size_t i = 0; ok && i < np; ++i) {
+                    const GemmTask& a = s.gemm[i]; const GemmTask& b = s.gemm[np + i];
+                    ok = a.M == b.M && a.tiles_n == cl && b.tiles_n == cl && b.K == a.N && b.A.arena == a.C.arena && b.A.off == a.C.off &&
+                         (a.epi == EPI_BIAS || a.epi == EPI_BIAS_RELU) && (b.epi == EPI_BIAS || b.epi == EPI_BIAS_RELU);
+                }
+                s.fwd2_cluster = ok ? cl : 0;
+            }
             if (int e = upload(t, s.gemm.data(), s.gemm.size(), &s.dev)) return e;
         } else if (s.kind == ST_POLICY_HEAD) {
             s.max_rows = 0;
@@ -1127,6 +1161,30 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                 } else {
                     if (x3) launch_pdl(gemm_tc_kernel<true, true, true>, grid, dim3(TC_THREADS), s.smem, st, tp);
                     else launch_pdl(gemm_tc_kernel<true, true, false>, grid, dim3(TC_THREADS), s.smem, st, tp);
+                }
+                OAC_CUDA(cudaGetLastError());
+                return 0;
+            }
+            if (s.fused2) {
+                const int np = (int)s.gemm.size() / 2;
+                grid.y = np;
+                if (s.fwd2_cluster) {                  // both layers of every 32-row strip in one cluster launch
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof(cfg));
+                    cfg.gridDim = grid; cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = s.smem; cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = s.fwd2_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    OAC_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd2_kernel, sp, np));
+                } else {                               // layer 1, then layer 2
+                    for (int l = 0; l < 2; ++l) {
+                        StageParams sl = sp;
+                        sl.tasks = sp.tasks + l * np;
+                        if (sl.tmaps) sl.tmaps = sp.tmaps + 2 * l * np;
+                        if (s.sk_tma) launch_pdl(gemm_sk_kernel<false, false, true>, grid, dim3(SK_THREADS), s.smem, st, sl);
+                        else launch_pdl(gemm_sk_kernel<false, false>, grid, dim3(SK_THREADS), s.smem, st, sl);
+                    }
                 }
                 OAC_CUDA(cudaGetLastError());
                 return 0;
@@ -1362,6 +1420,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_in((const void*)gemm_sk_kernel<true, true, true>);
         opt_in((const void*)gemm_sk_kernel<false, true>);
         opt_in((const void*)gemm_sk_kernel<true, true>);
+        opt_in((const void*)gemm_fwd2_kernel);
         opt_in((const void*)gemm_tc_kernel<false, false, false>);
         opt_in((const void*)gemm_tc_kernel<false, true, false>);
         opt_in((const void*)gemm_tc_kernel<true, true, false>);
@@ -1427,7 +1486,10 @@ extern "C" int oac_trainer_destroy(OacTrainer* t) {
 
 extern "C" int oac_trainer_launches_per_step(const OacTrainer* t) {
     if (!t) return 0;
-    return t->mega_prog ? 1 : (int)t->stages.size();
+    if (t->mega_prog) return 1;
+    int n = 0;
+    for (const Stage& s : t->stages) n += (s.fused2 && !s.fwd2_cluster) ? 2 : 1;      // a fused layer pair without its cluster: two launches
+    return n;
 }
 
 extern "C" int oac_trainer_ws_stages(const OacTrainer* t) {

@@ -261,3 +261,31 @@ def test_single_launch_step_matches_graph(monkeypatch):
         a, b = net_cpu(getattr(trainers[0], n)), net_cpu(getattr(trainers[1], n))
         for k in a:
             assert torch.equal(a[k], b[k]), (n, k)
+
+
+@pytest.mark.parametrize("H", [256, 320])
+def test_fused_forward_layers_match_separate_launches(monkeypatch, H):
+    """gemm_fwd2_kernel runs layer 1 and layer 2 of every 32-row strip in one thread-block cluster with the arithmetic of the
+    two gemm_sk_kernel launches it replaces: weights after three steps must be equal bit for bit (H = 256: clusters of 8;
+    H = 320: 10 column tiles exceed the portable cluster size, so the fused stage falls back to its two launches)."""
+    O, A, B = 376, 17, 256
+    trainers = []
+    for off in ("", "1"):
+        if off:
+            monkeypatch.setenv("OAC_NO_FWD2", off)
+        torch.manual_seed(6)
+        trainers.append(make_trainer(O, A, H))
+    monkeypatch.delenv("OAC_NO_FWD2")
+    if H == 256:
+        assert trainers[0]._engine.launches_per_step == trainers[1]._engine.launches_per_step - 3
+    for step in range(3):
+        batch = synth_batch(B, O, A, seed=50 + step)
+        eps = synth_eps(2, B, A, seed=500 + step)
+        for tr in trainers:
+            tr.inject_noise(eps[0], eps[1])
+            tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
+    torch.cuda.synchronize()
+    for n in NETS:
+        a, b = net_cpu(getattr(trainers[0], n)), net_cpu(getattr(trainers[1], n))
+        for k in a:
+            assert torch.equal(a[k], b[k]), (n, k)

@@ -83,8 +83,8 @@ def traffic(rep, kernel_substr):
 
 if __name__ == "__main__":
     import json
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01m"
-    launch_list(tag + "_launches_single_fp32.csv", 20)
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01n"
+    launch_list(tag + "_launches_single_fp32.csv", 18)
     launch_list(tag + "_launches_64seeds_tf32.csv", 19)
     full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
     full_report(tag + "_64seeds_tf32.ncu-rep", tag + "_64seeds_tf32_full.txt")
