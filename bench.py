@@ -364,7 +364,7 @@ def run_ours(args):
             all_ms = sum(p[1] for p in prof)
             tf32_peak = pk["bf16"] / 2.0          # kind::tf32 runs at half the bf16 rate
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-            kname = {0: "gemm_sk_kernel (fp32 FFMA, 4-way split-K 32x32 tiles)" if S * B <= 1024 else "gemm_stage_kernel (fp32 FFMA)",
+            kname = {0: "gemm_sk_kernel / gemm_fwd2_kernel (fp32 FFMA, 4-way split-K 32x32 tiles, TMA-staged operands)",
                      1: "gemm_ws_kernel (TMA + tcgen05 kind::tf32, warp-specialised, TMEM accumulators)",
                      2: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32 split, TMEM accumulators)"}[GEMM_PATH]
             roof = {"bound": "tensor", "kernel": kname + ", all GEMM stages of one step",

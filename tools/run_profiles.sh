@@ -11,7 +11,7 @@ python bench.py > $O/${T}_bench_single.json 2> $O/${T}_bench_single.err
 python tools/profile_step.py --steps 3 > $O/${T}_plain_single.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_single_fp32.csv \
       python tools/profile_step.py --steps 3 > $O/${T}_ncu_single.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head_kernel|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 36 --launch-count 18 -o $O/${T}_single_fp32 -f \
+ncu --set full --clock-control none --import-source on -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head_kernel|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 32 --launch-count 16 -o $O/${T}_single_fp32 -f \
     python tools/profile_step.py --steps 3 > $O/${T}_full_single.log 2>&1
 exit 0
 fi
@@ -34,7 +34,7 @@ python tools/bench_explore.py > $O/${T}_explore.json 2> $O/${T}_explore.err
 fi
 if [ "$PHASE" != "bench" ]; then
 # full captures: the last step's launches of each configuration
-ncu --set full --clock-control none --import-source on -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head_kernel|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 36 --launch-count 18 -o $O/${T}_single_fp32 -f \
+ncu --set full --clock-control none --import-source on -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head_kernel|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 32 --launch-count 16 -o $O/${T}_single_fp32 -f \
     python tools/profile_step.py --steps 3 > $O/${T}_full_single.log 2>&1
 ncu --set full --clock-control none -k regex:"gemm_ws_kernel|adam_stream_kernel|critic_head_kernel|policy_head_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 19 --launch-count 19 -o $O/${T}_64seeds_tf32 -f \
     python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_full_64.log 2>&1

@@ -84,11 +84,19 @@ def traffic(rep, kernel_substr):
 if __name__ == "__main__":
     import json
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01n"
-    launch_list(tag + "_launches_single_fp32.csv", 18)
-    launch_list(tag + "_launches_64seeds_tf32.csv", 19)
-    full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
-    full_report(tag + "_64seeds_tf32.ncu-rep", tag + "_64seeds_tf32_full.txt")
-    tr = {"1:fp32": traffic(tag + "_single_fp32.ncu-rep", "gemm_sk_kernel"),
-          "64:tf32": traffic(tag + "_64seeds_tf32.ncu-rep", "gemm_ws_kernel")}
-    json.dump(tr, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    have = lambda n: os.path.exists(os.path.join(G, n))
+    tpath = os.path.join(P, "traffic.json")
+    tr = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    # a configuration whose kernels did not change since an earlier tag keeps that tag's files (and its traffic entry)
+    if have(tag + "_launches_single_fp32.csv"):
+        launch_list(tag + "_launches_single_fp32.csv", 16)
+    if have(tag + "_launches_64seeds_tf32.csv"):
+        launch_list(tag + "_launches_64seeds_tf32.csv", 19)
+    if have(tag + "_single_fp32.ncu-rep"):
+        full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
+        tr["1:fp32"] = traffic(tag + "_single_fp32.ncu-rep", "gemm_sk_kernel")
+    if have(tag + "_64seeds_tf32.ncu-rep"):
+        full_report(tag + "_64seeds_tf32.ncu-rep", tag + "_64seeds_tf32_full.txt")
+        tr["64:tf32"] = traffic(tag + "_64seeds_tf32.ncu-rep", "gemm_ws_kernel")
+    json.dump(tr, open(tpath, "w"), indent=1)
     print(tr)
