@@ -135,7 +135,6 @@ struct Stage {
     AdamStreamParams asp;       // ST_ADAM
     // launch
     void* dev = nullptr;        // task table / params on the device
-    int small_tiles = 0;
     int a_trans = 0, b_trans = 0;   // all tasks of a GEMM stage share the operand layouts
     int kc = 0;
     size_t smem = 0;
@@ -919,15 +918,15 @@ static int finalize(OacTrainer& t) {
     const int seeds = t.cfg.n_seeds;
     for (Stage& s : t.stages) {
         if (s.kind == ST_GEMM) {
-            long long tiles64 = 0;
             int kmax = 0;
             s.a_trans = s.gemm[0].a_trans; s.b_trans = s.gemm[0].b_trans;
             for (auto& g : s.gemm) {
-                tiles64 += (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
                 kmax = std::max(kmax, g.K);
                 if (g.a_trans != s.a_trans || g.b_trans != s.b_trans || (g.a_trans && !g.b_trans))
                     return set_error(OAC_E_INVALID, "internal: mixed operand layouts in one GEMM stage");
             }
+            if (s.fused2 && t.cfg.gemm_path != OAC_GEMM_FP32)
+                return set_error(OAC_E_INVALID, "internal: fused layer pairs exist on the FFMA path only");
             if (t.cfg.gemm_path == OAC_GEMM_TF32 || t.cfg.gemm_path == OAC_GEMM_TF32X3) {
                 const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
                 if (!x3 && t.allow_ws && ws_eligible(t, s)) {
@@ -988,8 +987,6 @@ static int finalize(OacTrainer& t) {
             }
             // one FFMA tile shape: 32 x 32 outputs, 4-way split-K (gemm_sk_kernel).  A 64 x 64 / 4 x 4-per-thread variant
             // for large grids was measured slower at every seed count (64 seeds: 4.32 vs 3.26 ms per step) and is gone.
-            s.small_tiles = 1;
-            (void)tiles64;
             const int bm = 32;
             // largest K chunk (multiple of 4) whose A+B tiles fit the shared-memory budget
             auto bytes_of = [&](int kc) {
@@ -1001,8 +998,8 @@ static int finalize(OacTrainer& t) {
             const size_t budget = 100 * 1024;                          // keep 2 CTAs / SM
             while (kc > 16 && bytes_of(kc) > budget) kc = ((kc / 2) + 3) & ~3;
             s.kc = kc; s.smem = bytes_of(kc);
-            if (s.small_tiles) s.smem = std::max(s.smem, sizeof(float) * SK_KS * SK_BM * SK_PLD);   // the k-groups' partial tiles
-            if (s.small_tiles && t.allow_sk_tma) { if (int e = sk_tma_plan(t, s)) return e; }
+            s.smem = std::max(s.smem, sizeof(float) * SK_KS * SK_BM * SK_PLD);   // the k-groups' partial tiles
+            if (t.allow_sk_tma) { if (int e = sk_tma_plan(t, s)) return e; }
             s.max_tiles = 0;
             for (auto& g : s.gemm) {
                 g.tiles_m = (g.M + bm - 1) / bm; g.tiles_n = (g.N + bm - 1) / bm;
@@ -1240,7 +1237,7 @@ static int mega_plan(OacTrainer& t) {
     const int seeds = t.cfg.n_seeds;
     if (!t.allow_mega || t.cfg.gemm_path != OAC_GEMM_FP32 || (long long)seeds * t.cfg.batch > 1024) return 0;
     for (const Stage& s : t.stages) {
-        if (s.kind == ST_GEMM) { if (s.use_tc || s.use_ws || !s.small_tiles || (s.a_trans && !s.b_trans)) return 0; }
+        if (s.kind == ST_GEMM) { if (s.use_tc || s.use_ws || (s.a_trans && !s.b_trans)) return 0; }
         else if (s.kind == ST_ADAM) return 0;
         else if (s.glue_g != 4 || s.glue_iters != 1) return 0;
     }
