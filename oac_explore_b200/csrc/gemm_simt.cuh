@@ -251,6 +251,16 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
                     reinterpret_cast<uintptr_t>(ep_t)) & 15) == 0);
     }
 
+    // the ReLU mask of a dX stage (EPI_MASK) is an activation of an earlier stage: like the Adam operands, this thread's
+    // four mask values are requested before the main loop instead of costing an L2 round trip in the epilogue
+    const float* ep_mask = nullptr;
+    bool mask_vec = false;
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (T.epi == EPI_MASK && m0 + er < M) {
+        ep_mask = resolve(sp.as, T.mask, seed) + (long long)(m0 + er) * T.ldmask + n0 + ec;
+        mask_vec = (n0 + ec + 3 < N) && ((T.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep_mask) & 15) == 0);
+    }
+
     for (int k0 = 0; k0 < K; k0 += (TMA ? K : kc)) {
         const int kn = TMA ? K : min(kc, K - k0);
         if (k0 > 0) __syncthreads();
@@ -283,6 +293,7 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
             v4 = *reinterpret_cast<const float4*>(ep_v);
             if (ep_t) t4 = *reinterpret_cast<const float4*>(ep_t);
         }
+        if (k0 == 0 && mask_vec) k4 = *reinterpret_cast<const float4*>(ep_mask);
         if (is_adam && k0 == 0 && tid == 0) {      // the step's Adam scalars: computed while the operand loads fly
             int t = sp.as.counters[seed * sp.as.n_counters + T.counter];
             int ts = sp.as.counters[seed * sp.as.n_counters + CNT_TRAIN_STEPS];
@@ -426,6 +437,7 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
     }
     const float* bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
     const float* mask = (epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+    const unsigned mbits = (k4.x > 0.f ? 1u : 0u) | (k4.y > 0.f ? 2u : 0u) | (k4.z > 0.f ? 4u : 0u) | (k4.w > 0.f ? 8u : 0u);
 #pragma unroll
     for (int j = 0; j < SK_T; ++j) {
         const int n = n0 + ec + j;
@@ -433,7 +445,7 @@ __device__ __forceinline__ void gemm_sk_body(const StageParams& sp, int bx, int 
         float x = v[j];
         if (epi == EPI_BIAS) x += bias[n];
         else if (epi == EPI_BIAS_RELU) x = relu(x + bias[n]);
-        else if (epi == EPI_MASK) x = mask[(long long)m * T.ldmask + n] > 0.f ? x : 0.f;
+        else if (epi == EPI_MASK) x = (mask_vec ? ((mbits >> j) & 1u) != 0u : mask[(long long)m * T.ldmask + n] > 0.f) ? x : 0.f;
         C[(long long)m * ldc + n] = x;
     }
 }
