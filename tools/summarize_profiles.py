@@ -69,7 +69,8 @@ def traffic(rep, kernel_substr):
     best = None
     for r in rows[2:]:
         d = dict(zip(hdr, r))
-        if kernel_substr not in d.get("Kernel Name", ""):
+        subs = kernel_substr if isinstance(kernel_substr, (tuple, list)) else (kernel_substr,)
+        if not any(k in d.get("Kernel Name", "") for k in subs):
             continue
         t = float(d["gpu__time_duration.sum"].replace(",", ""))
         if best is None or t > best[0]:
@@ -94,7 +95,7 @@ if __name__ == "__main__":
         launch_list(tag + "_launches_64seeds_tf32.csv", 19)
     if have(tag + "_single_fp32.ncu-rep"):
         full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
-        tr["1:fp32"] = traffic(tag + "_single_fp32.ncu-rep", "gemm_sk_kernel")
+        tr["1:fp32"] = traffic(tag + "_single_fp32.ncu-rep", ("gemm_sk_kernel", "gemm_fwd2_kernel"))
     if have(tag + "_64seeds_tf32.ncu-rep"):
         full_report(tag + "_64seeds_tf32.ncu-rep", tag + "_64seeds_tf32_full.txt")
         tr["64:tf32"] = traffic(tag + "_64seeds_tf32.ncu-rep", "gemm_ws_kernel")
