@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define OAC_ABI_VERSION 2
+#define OAC_ABI_VERSION 3
 #define OAC_MAX_NETS 48
 
 enum { OAC_E_INVALID = -1, OAC_E_UNSUPPORTED = -2, OAC_E_NOMEM = -3 };
@@ -191,6 +191,19 @@ int oac_trainer_launches_per_step(const OacTrainer* t);
 /* Number of GEMM stages of the step that run on the warp-specialised TMA + tcgen05 kernel (tests assert the
  * tensor-core path is the one measured). */
 int oac_trainer_ws_stages(const OacTrainer* t);
+/* On-device diagnostics (trainer/trainer.py:230-279, particle_trainer_oac.py:332-362, gaussian_trainer.py:397-436): one
+ * kernel reduces the last step's per-sample outputs into the `eval_statistics` vector of every seed, out[seed * out_ld + i],
+ * in the reference's key order:
+ *   SAC   [32]      QF mean, QF std, QF1 Loss, QF2 Loss, Q Loss, Policy Loss, {Q1 Predictions, Q2 Predictions, Q Targets,
+ *                   Log Pis, Policy mu, Policy log std} x {Mean, Std, Max, Min}, Alpha, Alpha Loss
+ *   P-OAC [11 + 9P] QF mean, QF std, per particle {QFi Loss, QiPredictions x4, QiTargets x4}, Policy Loss, Policy mu x4,
+ *                   Policy log std x4
+ *   G-OAC [29]      QF mean, QF std, QF Loss, Q Predictions x4, Q Target x4, STD Loss, Q STD Predictions x4,
+ *                   Q STD Target x4, Policy Loss, Policy mu x4, Policy log std x4
+ * `out` is device memory or mapped pinned host memory (then a stream synchronisation is all the caller needs); it is
+ * also the payload of the per-seed statistics all-gather.  oac_trainer_stats_count returns the vector length. */
+int oac_trainer_stats_count(const OacTrainer* t);
+int oac_trainer_stats(OacTrainer* t, float* out, int32_t out_ld, void* stream);
 /* Measurement aid: runs `iters` steps stage by stage (no graph) with a CUDA event between
  * stages and returns the mean duration of each stage in milliseconds (ms[n_stages]) and, per
  * stage, whether it is a GEMM stage (is_gemm) and its algorithmic FLOPs per seed (flops).
@@ -230,7 +243,9 @@ typedef struct OacExploreArgs {
     int32_t mode;                /* OacExploreMode */
     int32_t deterministic;       /* L2-normalised shift, returns un-squashed mu_E (:111-196) */
     int32_t quantile_index;
-    uint32_t exp_mask;           /* critic heads passed through exp (G-OAC shared net) */
+    uint32_t exp_mask;           /* bit v set: critic OUTPUT v passes through exp (networks.py:69-75 "positive"); outputs are
+                                    numbered net-major, v = net * n_heads + head, so every critic carries its own flags
+                                    (G-OAC shared net: 0b10; separate mean / std nets: 0b10 as well) */
     float beta_UB, delta;
     int32_t n_obs;               /* independent observations (1 in the reference's rollout) */
     const float* obs;            /* [n_obs, obs_dim] */
@@ -239,6 +254,12 @@ typedef struct OacExploreArgs {
     float* action;               /* [n_obs, A]: tanh(N(mu_E, std)) or mu_E (deterministic) */
     float* mu_E;                 /* [n_obs, A] or NULL */
     float* grad;                 /* [n_obs, A] dQ_UB/d(pre-tanh mean) or NULL */
+    /* Per-seed batched exploration (path_collector.py:214-232 vectorised over the seeds of one GPU): when
+     * obs_group != NULL observation i is served by the parameter arena obs_group[i] -- `policy` and `q[]` point into arena 0
+     * and arena g starts group_stride floats further (the [n_seeds, param_floats] arena of a seed group) -- so ONE launch
+     * computes every seed's action with that seed's own policy and critics. */
+    const int32_t* obs_group;    /* [n_obs] device, or NULL: every observation uses `policy` / `q[]` as given */
+    int64_t group_stride;        /* floats */
 } OacExploreArgs;
 int oac_explore(const OacExploreArgs* args, void* stream);
 

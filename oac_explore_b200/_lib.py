@@ -17,6 +17,7 @@ NET_POLICY, NET_Q, NET_SCALAR = 0, 1, 2
 EXPLORE_TWIN, EXPLORE_ENSEMBLE, EXPLORE_QUANTILE = 0, 1, 2
 # counters (oac_internal.h)
 CNT_TRAIN_STEPS, CNT_OPT0 = 0, 1
+CNT_RNG_LO, CNT_RNG_HI = 22, 23      # per-seed 64-bit key mixed into the Philox stream of the step's rsample noise
 SC_ALPHA, SC_ALPHA_LOSS, SC_MEAN_LOGPI = 0, 1, 2
 
 
@@ -86,6 +87,7 @@ class OacExploreArgs(C.Structure):
         ("n_obs", C.c_int32), ("obs", C.c_void_p), ("eps", C.c_void_p),
         ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
         ("action", C.c_void_p), ("mu_E", C.c_void_p), ("grad", C.c_void_p),
+        ("obs_group", C.c_void_p), ("group_stride", C.c_int64),
     ]
 
 
@@ -94,7 +96,7 @@ EXPORTS = [
     "oac_last_error_string", "oac_abi_version",
     "oac_replay_gather", "oac_replay_gather_dense", "oac_replay_add",
     "oac_trainer_layout", "oac_trainer_create", "oac_trainer_destroy", "oac_trainer_step",
-    "oac_trainer_launches_per_step", "oac_trainer_ws_stages", "oac_trainer_profile", "oac_gemm_debug", "oac_gemm_debug_kernel",
+    "oac_trainer_launches_per_step", "oac_trainer_ws_stages", "oac_trainer_stats", "oac_trainer_stats_count", "oac_trainer_profile", "oac_gemm_debug", "oac_gemm_debug_kernel",
     "oac_policy_forward", "oac_q_forward", "oac_explore",
 ]
 
@@ -126,12 +128,14 @@ def lib():
     L.oac_trainer_step.argtypes = [vp, i32, vp]
     L.oac_trainer_launches_per_step.argtypes = [vp]
     L.oac_trainer_ws_stages.argtypes = [vp]
+    L.oac_trainer_stats_count.argtypes = [vp]
+    L.oac_trainer_stats.argtypes = [vp, vp, i32, vp]
     L.oac_trainer_profile.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.oac_gemm_debug.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
     L.oac_policy_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.oac_q_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, u32, vp, vp]
     L.oac_explore.argtypes = [C.POINTER(OacExploreArgs), vp]
-    if L.oac_abi_version() != 2:
+    if L.oac_abi_version() != 3:
         raise RuntimeError("liboac_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -128,6 +128,8 @@ struct ExploreParams {
     const float* obs; const float* eps;
     unsigned long long rng_seed, rng_offset;
     float *action, *mu_E, *grad;
+    const int* obs_group;          // per observation: which parameter arena (seed of a group) serves it, or NULL
+    long long group_stride;        // floats between consecutive arenas
 };
 
 // dyn smem layout (floats): x[O+A pad] | h1[H] | h2[H] | head[2A] | qh1[n_q][H] | qh2[n_q][H] |
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
     extern __shared__ __align__(16) float sm[];
     const int O = p.O, A = p.A, H = p.H;
     const int ob = blockIdx.x;
+    const long long goff = p.obs_group ? (long long)p.obs_group[ob] * p.group_stride : 0;   // this observation's weights
     float* x = sm;
     float* h1 = x + ((O + A + 3) & ~3);
     float* h2 = h1 + H;
@@ -153,11 +156,11 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
     for (int i = tid; i < O; i += EX_THREADS) x[i] = p.obs[(long long)ob * O + i];
     __syncthreads();
     // ---- policy forward (trainer/policies.py:260-283), deterministic head: a = tanh(mean) ----
-    gemv_rows(p.policy.w0, p.policy.in_ld, p.policy.b0, x, O, H, h1, true);
+    gemv_rows((p.policy.w0 + goff), p.policy.in_ld, (p.policy.b0 + goff), x, O, H, h1, true);
     __syncthreads();
-    gemv_rows(p.policy.w1, H, p.policy.b1, h1, H, H, h2, true);
+    gemv_rows((p.policy.w1 + goff), H, (p.policy.b1 + goff), h1, H, H, h2, true);
     __syncthreads();
-    gemv_rows(p.policy.w2, H, p.policy.b2, h2, H, 2 * A, head, false);
+    gemv_rows((p.policy.w2 + goff), H, (p.policy.b2 + goff), h2, H, 2 * A, head, false);
     __syncthreads();
     for (int j = tid; j < A; j += EX_THREADS) x[O + j] = tanhf(head[j]);
     __syncthreads();
@@ -165,11 +168,11 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
     int n_vals = 0;
     for (int q = 0; q < p.n_q; ++q) {
         const NetPtrs& N = p.q[q];
-        gemv_rows(N.w0, N.in_ld, N.b0, x, O + A, H, qh1 + q * H, true);
+        gemv_rows((N.w0 + goff), N.in_ld, (N.b0 + goff), x, O + A, H, qh1 + q * H, true);
         __syncthreads();
-        gemv_rows(N.w1, H, N.b1, qh1 + q * H, H, H, qh2 + q * H, true);
+        gemv_rows((N.w1 + goff), H, (N.b1 + goff), qh1 + q * H, H, H, qh2 + q * H, true);
         __syncthreads();
-        gemv_rows(N.w2, H, N.b2, qh2 + q * H, H, N.n_out, qv + n_vals, false);
+        gemv_rows((N.w2 + goff), H, (N.b2 + goff), qh2 + q * H, H, N.n_out, qv + n_vals, false);
         n_vals += N.n_out;
     }
     __syncthreads();
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
     if (tid == 0) {
         const int n_heads = p.q[0].n_out;
         for (int i = 0; i < n_vals; ++i)
-            if ((p.exp_mask >> (i % n_heads)) & 1u) qv[i] = expf(qv[i]);       // networks.py:69-75
+            if (i < 32 && ((p.exp_mask >> i) & 1u)) qv[i] = expf(qv[i]);       // networks.py:69-75
         if (p.mode == OAC_EXPLORE_TWIN) {
             // Q_UB = (Q1+Q2)/2 + beta |Q1-Q2|/2     (optimistic_exploration.py:42-46,60)
             float dlt = qv[0] - qv[n_heads];
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
             }
         }
         for (int i = 0; i < n_vals; ++i)
-            if ((p.exp_mask >> (i % n_heads)) & 1u) cf[i] *= qv[i];            // d exp(u)/du
+            if (i < 32 && ((p.exp_mask >> i) & 1u)) cf[i] *= qv[i];            // d exp(u)/du
     }
     for (int j = tid; j < A; j += EX_THREADS) da[j] = 0.f;
     __syncthreads();
@@ -215,12 +218,12 @@ __global__ void __launch_bounds__(EX_THREADS) explore_kernel(ExploreParams p) {
         const NetPtrs& N = p.q[q];
         for (int n = tid; n < H; n += EX_THREADS) {
             float s = 0.f;
-            for (int hd = 0; hd < N.n_out; ++hd) s = fmaf(cf[v0 + hd], __ldg(N.w2 + (long long)hd * H + n), s);
+            for (int hd = 0; hd < N.n_out; ++hd) s = fmaf(cf[v0 + hd], __ldg((N.w2 + goff) + (long long)hd * H + n), s);
             g2[n] = qh2[q * H + n] > 0.f ? s : 0.f;
         }
         __syncthreads();
-        gemv_cols(N.w1, H, 0, g2, H, H, qh1 + q * H, g1, part, false);
-        gemv_cols(N.w0, N.in_ld, O, g1, H, A, nullptr, da, part, true);
+        gemv_cols((N.w1 + goff), H, 0, g2, H, H, qh1 + q * H, g1, part, false);
+        gemv_cols((N.w0 + goff), N.in_ld, O, g1, H, A, nullptr, da, part, true);
         v0 += N.n_out;
     }
     // ---- shift + sample (one warp) ----
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
     const int rank = (int)cl.block_rank();
     const int O = p.O, A = p.A, H = p.H;
     const int ob = blockIdx.x / EXC_CS;
+    const long long goff = p.obs_group ? (long long)p.obs_group[ob] * p.group_stride : 0;   // this observation's weights
     float* x = sm;
     float* h1 = x + ((O + A + 3) & ~3);
     float* h2 = h1 + H;
@@ -381,18 +385,18 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
     for (int i = tid; i < O; i += EXC_THREADS) x[i] = p.obs[(long long)ob * O + i];
     cl.sync();                                 // also: every CTA of the cluster is running before the first remote store
     // ---- policy forward: hidden layers split by rows, the 2A head rows on every CTA ----
-    gemv_rows_bcast(cl, p.policy.w0, p.policy.in_ld, p.policy.b0, x, O, s0, s1, h1, true);
+    gemv_rows_bcast(cl, (p.policy.w0 + goff), p.policy.in_ld, (p.policy.b0 + goff), x, O, s0, s1, h1, true);
     cl.sync();
-    gemv_rows_bcast(cl, p.policy.w1, H, p.policy.b1, h1, H, s0, s1, h2, true);
+    gemv_rows_bcast(cl, (p.policy.w1 + goff), H, (p.policy.b1 + goff), h1, H, s0, s1, h2, true);
     cl.sync();
-    gemv_rows<EXC_WARPS>(p.policy.w2, H, p.policy.b2, h2, H, 2 * A, head, false);     // 2A short rows, redundantly per CTA
+    gemv_rows<EXC_WARPS>((p.policy.w2 + goff), H, (p.policy.b2 + goff), h2, H, 2 * A, head, false);     // 2A short rows, redundantly per CTA
     __syncthreads();
     for (int j = tid; j < A; j += EXC_THREADS) x[O + j] = tanhf(head[j]);
     __syncthreads();
     // ---- critics forward ----
-    for (int q = 0; q < p.n_q; ++q) gemv_rows_bcast(cl, p.q[q].w0, p.q[q].in_ld, p.q[q].b0, x, O + A, s0, s1, qh1 + q * H, true);
+    for (int q = 0; q < p.n_q; ++q) gemv_rows_bcast(cl, (p.q[q].w0 + goff), p.q[q].in_ld, (p.q[q].b0 + goff), x, O + A, s0, s1, qh1 + q * H, true);
     cl.sync();
-    for (int q = 0; q < p.n_q; ++q) gemv_rows_bcast(cl, p.q[q].w1, H, p.q[q].b1, qh1 + q * H, H, s0, s1, qh2 + q * H, true);
+    for (int q = 0; q < p.n_q; ++q) gemv_rows_bcast(cl, (p.q[q].w1 + goff), H, (p.q[q].b1 + goff), qh1 + q * H, H, s0, s1, qh2 + q * H, true);
     cl.sync();
     int n_vals = 0;
     {
@@ -400,11 +404,11 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
         for (int q = 0; q < p.n_q; ++q) {
             const NetPtrs& N = p.q[q];
             for (int n = warp; n < N.n_out; n += EXC_WARPS) {
-                const float* w = N.w2 + (long long)n * H;
+                const float* w = (N.w2 + goff) + (long long)n * H;
                 float acc = 0.f;
                 for (int k = lane; k < H; k += 32) acc = fmaf(__ldg(w + k), qh2[q * H + k], acc);
                 acc = warp_sum(acc);
-                if (lane == 0) qv[n_vals + n] = acc + __ldg(N.b2 + n);
+                if (lane == 0) qv[n_vals + n] = acc + __ldg((N.b2 + goff) + n);
             }
             n_vals += N.n_out;
         }
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
     if (tid == 0) {
         const int n_heads = p.q[0].n_out;
         for (int i = 0; i < n_vals; ++i)
-            if ((p.exp_mask >> (i % n_heads)) & 1u) qv[i] = expf(qv[i]);
+            if (i < 32 && ((p.exp_mask >> i) & 1u)) qv[i] = expf(qv[i]);
         if (p.mode == OAC_EXPLORE_TWIN) {
             float dlt = qv[0] - qv[n_heads];
             float sg = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
             }
         }
         for (int i = 0; i < n_vals; ++i)
-            if ((p.exp_mask >> (i % n_heads)) & 1u) cf[i] *= qv[i];
+            if (i < 32 && ((p.exp_mask >> i) & 1u)) cf[i] *= qv[i];
     }
     for (int j = tid; j < A; j += EXC_THREADS) da[j] = 0.f;
     __syncthreads();
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
             const NetPtrs& N = p.q[q];
             for (int n = tid; n < H; n += EXC_THREADS) {
                 float sacc = 0.f;
-                for (int hd = 0; hd < N.n_out; ++hd) sacc = fmaf(cf[v0 + hd], __ldg(N.w2 + (long long)hd * H + n), sacc);
+                for (int hd = 0; hd < N.n_out; ++hd) sacc = fmaf(cf[v0 + hd], __ldg((N.w2 + goff) + (long long)hd * H + n), sacc);
                 g2[q * H + n] = qh2[q * H + n] > 0.f ? sacc : 0.f;
             }
             v0 += N.n_out;
@@ -458,11 +462,11 @@ __global__ void __launch_bounds__(EXC_THREADS) explore_cluster_kernel(ExplorePar
     }
     __syncthreads();
     for (int q = 0; q < p.n_q; ++q)
-        gemv_cols_slice(cl, p.q[q].w1, H, 0, g2 + q * H, H, s0, s1, qh1 + q * H, g1 + q * H, part, true, false);
+        gemv_cols_slice(cl, (p.q[q].w1 + goff), H, 0, g2 + q * H, H, s0, s1, qh1 + q * H, g1 + q * H, part, true, false);
     cl.sync();
     if (rank == 0) {
         for (int q = 0; q < p.n_q; ++q)
-            gemv_cols_slice(cl, p.q[q].w0, p.q[q].in_ld, O, g1 + q * H, H, 0, A, nullptr, da, part, false, true);
+            gemv_cols_slice(cl, (p.q[q].w0 + goff), p.q[q].in_ld, O, g1 + q * H, H, 0, A, nullptr, da, part, false, true);
         // ---- shift + sample (one warp) ----
         if (tid < 32) {
             float num = 0.f;
@@ -609,6 +613,7 @@ extern "C" int oac_explore(const OacExploreArgs* a, void* stream) {
     p.O = O; p.A = A; p.H = H; p.obs = a->obs; p.eps = a->eps;
     p.rng_seed = a->rng_seed; p.rng_offset = a->rng_offset;
     p.action = a->action; p.mu_E = a->mu_E; p.grad = a->grad;
+    p.obs_group = a->obs_group; p.group_stride = a->group_stride;
     size_t fl = ((O + A + 3) & ~3) + 2 * H + ((2 * A + 3) & ~3) + 2 * (size_t)p.n_q * H + 128 + 2 * H +
                 ((A + 3) & ~3) + (size_t)EX_WARPS * (H > A ? H : A);
     static const bool no_cluster = getenv("OAC_NO_CLUSTER") && getenv("OAC_NO_CLUSTER")[0] == '1';

@@ -137,6 +137,8 @@ __device__ __forceinline__ void policy_head_body(const PolicyHeadParams& p, int 
     float* io = p.as.base[AR_IO] + (long long)seed * p.as.stride[AR_IO];
     int32_t* cnt = p.as.counters + seed * p.as.n_counters;
     const int step = cnt[CNT_TRAIN_STEPS];
+    // the seed's own key (the real seed id of a batched seed): noise streams follow the seed, not its slot in the group
+    const unsigned long long seed_key = ((unsigned long long)(uint32_t)cnt[CNT_RNG_HI] << 32) | (uint32_t)cnt[CNT_RNG_LO];
 
     const bool from_gemm = p.head_from_gemm != 0;           // dyn smem is then only SPC * 2A floats
     float* Ws = s_ph;
@@ -208,7 +210,7 @@ __device__ __forceinline__ void policy_head_body(const PolicyHeadParams& p, int 
                 if (use_external_eps)
                     eps = io[p.off_eps + ((long long)T.eps_slot[blk] * B + b) * A + j];
                 else
-                    eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)seed,
+                    eps = philox_normal(p.rng_seed + 0x9E3779B97F4A7C15ull * seed_key,
                                         (uint32_t)T.eps_slot[blk], (uint32_t)step, (uint32_t)b, (uint32_t)j);
                 float z = fmaf(std, eps, mean_j);
                 action = tanhf(z);

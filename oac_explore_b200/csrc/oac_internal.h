@@ -36,6 +36,8 @@ enum Counter {
     CNT_MAX_OPT = 16,
     CNT_TICKET0 = 20,      // last-CTA-done tickets for the glue kernels (reset by the owner)
     CNT_TICKET1 = 21,
+    CNT_RNG_LO = 22,       // per-seed 64-bit key (the REAL seed id of a batched seed, 0 for a single trainer) mixed into the
+    CNT_RNG_HI = 23,       // Philox key of the step's rsample noise: streams follow the seed, not its slot in the group
     CNT_TOTAL = 24
 };
 

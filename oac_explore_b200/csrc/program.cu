@@ -23,6 +23,7 @@
 #include "gemm_ws.cuh"
 #include "gemm_fwd2.cuh"
 #include "adam_stream.cuh"
+#include "stats.cuh"
 #include "mega.cuh"
 #include "oac_error.h"
 
@@ -1487,6 +1488,28 @@ extern "C" int oac_trainer_launches_per_step(const OacTrainer* t) {
     int n = 0;
     for (const Stage& s : t->stages) n += (s.fused2 && !s.fwd2_cluster) ? 2 : 1;      // a fused layer pair without its cluster: two launches
     return n;
+}
+
+static int stats_len(const OacConfig& c) {
+    return c.algo == OAC_ALGO_SAC ? 32 : (c.algo == OAC_ALGO_POAC ? 11 + 9 * c.n_particles : 29);
+}
+
+extern "C" int oac_trainer_stats_count(const OacTrainer* t) { return t ? stats_len(t->cfg) : 0; }
+
+extern "C" int oac_trainer_stats(OacTrainer* t, float* out, int32_t out_ld, void* stream) {
+    if (!t || !out) return set_error(OAC_E_INVALID, "oac_trainer_stats: null argument");
+    if (out_ld < stats_len(t->cfg)) return set_error(OAC_E_INVALID, "oac_trainer_stats: out_ld too small");
+    StatsParams p;
+    memset(&p, 0, sizeof(p));
+    const OacLayout& L = t->lay;
+    p.as = t->as; p.algo = t->cfg.algo; p.B = t->cfg.batch; p.A = t->cfg.act_dim; p.P = t->cfg.n_particles; p.nq = L.nq;
+    p.deterministic = t->cfg.deterministic; p.auto_alpha = t->cfg.auto_alpha; p.standard_bound = t->cfg.standard_bound;
+    p.off_q_pred = L.off_q_pred; p.off_q_target = L.off_q_target; p.off_q_new = L.off_q_new; p.off_log_pi = L.off_log_pi;
+    p.off_mean = L.off_mean; p.off_log_std = L.off_log_std; p.off_scalars = L.off_scalars;
+    p.out = out; p.out_ld = out_ld;
+    trainer_stats_kernel<<<t->cfg.n_seeds, STATS_THREADS, 0, (cudaStream_t)stream>>>(p);
+    OAC_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int oac_trainer_ws_stages(const OacTrainer* t) {

@@ -87,14 +87,38 @@ __global__ void __launch_bounds__(GATHER_THREADS) replay_gather_kernel(GatherArg
     }
 }
 
-// counts[idx] += 1 once per DISTINCT index (numpy fancy-index "+=", replay_buffer.py:195)
-__global__ void replay_counts_bump_kernel(float* counts, const int64_t* idx, int batch) {
+// counts[idx] += 1 once per DISTINCT index (numpy fancy-index "+=", replay_buffer.py:195).  The index array may live in
+// mapped pinned HOST memory (the single-seed path reads it in place): it is staged into shared memory with ONE coalesced
+// pass, and the earlier-duplicate scan of every sample then runs on shared memory (it used to re-read idx[] from its home
+// O(B^2) times -- up to 32k PCIe reads per batch).  Every CTA stages the prefix it needs: [0, end of its own range).
+constexpr int BUMP_THREADS = 256;
+constexpr int BUMP_MAX_SMEM_BATCH = 6144;      // 48 KB of int64
+__global__ void __launch_bounds__(BUMP_THREADS) replay_counts_bump_kernel(float* counts, const int64_t* idx, int batch) {
+    extern __shared__ long long s_idx[];
+    const int i = blockIdx.x * BUMP_THREADS + threadIdx.x;
+    const int need = min(batch, (int)(blockIdx.x + 1) * BUMP_THREADS);
+    for (int j = threadIdx.x; j < need; j += BUMP_THREADS) s_idx[j] = idx[j];
+    __syncthreads();
+    if (i >= batch) return;
+    const long long r = s_idx[i];
+    for (int j = 0; j < i; ++j)
+        if (s_idx[j] == r) return;        // an earlier occurrence owns the increment
+    counts[r] += 1.0f;
+}
+// batches too large for the shared-memory staging (never the reference's 256): the plain scan
+__global__ void replay_counts_bump_global_kernel(float* counts, const int64_t* idx, int batch) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     const long long r = idx[i];
     for (int j = 0; j < i; ++j)
-        if (idx[j] == r) return;          // an earlier occurrence owns the increment
+        if (idx[j] == r) return;
     counts[r] += 1.0f;
+}
+static inline void launch_counts_bump(float* counts, const int64_t* idx, int batch, cudaStream_t st) {
+    if (batch <= BUMP_MAX_SMEM_BATCH)
+        replay_counts_bump_kernel<<<(batch + BUMP_THREADS - 1) / BUMP_THREADS, BUMP_THREADS, sizeof(long long) * (size_t)batch, st>>>(counts, idx, batch);
+    else
+        replay_counts_bump_global_kernel<<<(batch + 127) / 128, 128, 0, st>>>(counts, idx, batch);
 }
 
 struct DenseArgs {
@@ -160,7 +184,7 @@ extern "C" int oac_replay_gather(const OacReplayStore* store, const int64_t* ind
     replay_gather_kernel<<<dim3(batch, seeds), GATHER_THREADS, 0, st>>>(a);
     OAC_CUDA(cudaGetLastError());
     if (store->counts) {
-        replay_counts_bump_kernel<<<(batch + 127) / 128, 128, 0, st>>>(store->counts, indices, batch);
+        launch_counts_bump(store->counts, indices, batch, st);
         OAC_CUDA(cudaGetLastError());
     }
     return 0;
@@ -176,7 +200,7 @@ extern "C" int oac_replay_gather_dense(const OacReplayStore* store, const int64_
     replay_gather_dense_kernel<<<batch, GATHER_THREADS, 0, st>>>(a);
     OAC_CUDA(cudaGetLastError());
     if (store->counts) {
-        replay_counts_bump_kernel<<<(batch + 127) / 128, 128, 0, st>>>(store->counts, indices, batch);
+        launch_counts_bump(store->counts, indices, batch, st);
         OAC_CUDA(cudaGetLastError());
     }
     return 0;

@@ -61,6 +61,8 @@ class Engine(object):
         self.B, self.O, self.A, self.H = cfg.batch, cfg.obs_dim, cfg.act_dim, cfg.hidden
         self.launches_per_step = self.lib.oac_trainer_launches_per_step(self.handle)
         self.ws_stages = self.lib.oac_trainer_ws_stages(self.handle)
+        self.n_stats = self.lib.oac_trainer_stats_count(self.handle)
+        self._host_stats = None
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -139,6 +141,24 @@ class Engine(object):
     def step(self, external_eps=False):
         _lib.check(self.lib.oac_trainer_step(self.handle, 1 if external_eps else 0, _lib.current_stream()),
                    "oac_trainer_step")
+
+    def stats_device(self, out=None):
+        """[n_seeds, n_stats] fp32 DEVICE tensor: the ``eval_statistics`` vector of every seed for the last step, reduced
+        by one kernel (``oac_trainer_stats``; key order in include/oac_b200.h).  The all-gather payload."""
+        if out is None:
+            out = torch.empty((self.cfg.n_seeds, self.n_stats), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.oac_trainer_stats(self.handle, _lib.ptr(out), out.stride(0), _lib.current_stream()),
+                   "oac_trainer_stats")
+        return out
+
+    def stats_host(self):
+        """The same vector as a [n_seeds, n_stats] numpy array: the kernel stores straight into mapped pinned host memory,
+        so this is one launch + one stream synchronisation (no device-to-host copy calls)."""
+        if self._host_stats is None:
+            self._host_stats = torch.zeros((self.cfg.n_seeds, self.n_stats), dtype=torch.float32).pin_memory()
+        self.stats_device(self._host_stats)
+        torch.cuda.current_stream().synchronize()
+        return self._host_stats.numpy().copy()
 
     def profile(self, iters=20):
         """Per-stage mean milliseconds (stage-by-stage launches, CUDA events): [(name, ms, is_gemm, flops)]."""

@@ -114,26 +114,19 @@ class GaussianTrainer(_EngineTrainer):
             return [qs, stds], upper_bound
         return upper_bound
 
+    STAT_KEYS = (['QF mean', 'QF std', 'QF Loss'] +
+                 [n + s for n in ('Q Predictions', 'Q Target') for s in (' Mean', ' Std', ' Max', ' Min')] + ['STD Loss'] +
+                 [n + s for n in ('Q STD Predictions', 'Q STD Target') for s in (' Mean', ' Std', ' Max', ' Min')] +
+                 ['Policy Loss'] +
+                 [n + s for n in ('Policy mu', 'Policy log std') for s in (' Mean', ' Std', ' Max', ' Min')])
+
     def _update_eval_statistics(self):
-        """Keys of :397-436."""
-        B, A = self._engine.B, self._A
-        pred = get_numpy(self._io('off_q_pred', (B, 2)))
-        tgt = get_numpy(self._io('off_q_target', (B, 2)))
-        q_new = get_numpy(self._io('off_q_new', (B, 2)))
-        mean = get_numpy(self._io('off_mean', (3 * B, A)))[2 * B:]       # the reference logs the
-        log_std = get_numpy(self._io('off_log_std', (3 * B, A)))[2 * B:]  # target policy's outputs (:361-363)
+        """Keys of :397-436, reduced on the device (``oac_trainer_stats``); ``Policy mu`` / ``Policy log std`` are the
+        target policy's outputs like in the reference (:361-363)."""
+        vec = self._engine.stats_host()[0]
         st = self.eval_statistics
-        q, s, qt, s_t = pred[:, :1], pred[:, 1:], tgt[:, :1], tgt[:, 1:]
-        st['QF mean'], st['QF std'] = np.mean(q), np.mean(s)
-        st['QF Loss'] = np.mean((q - qt) ** 2)
-        st.update(create_stats_ordered_dict('Q Predictions', q))
-        st.update(create_stats_ordered_dict('Q Target', qt))
-        st['STD Loss'] = np.mean((s - s_t) ** 2)
-        st.update(create_stats_ordered_dict('Q STD Predictions', s))
-        st.update(create_stats_ordered_dict('Q STD Target', s_t))
-        st['Policy Loss'] = np.mean(q_new[:, :1] + self.standard_bound * q_new[:, 1:])
-        st.update(create_stats_ordered_dict('Policy mu', mean))
-        st.update(create_stats_ordered_dict('Policy log std', log_std))
+        for k, v in zip(self.STAT_KEYS, vec):
+            st[k] = v
 
     @property
     def networks(self):

@@ -103,27 +103,22 @@ class ParticleTrainer(_EngineTrainer):
             return sorted_qs, out
         return out
 
+    def _stat_keys(self):
+        keys = ['QF mean', 'QF std']
+        for i in range(self.num_particles):
+            keys.append('QF' + str(i) + ' Loss')
+            keys += ['Q' + str(i) + 'Predictions' + s for s in (' Mean', ' Std', ' Max', ' Min')]
+            keys += ['Q' + str(i) + 'Targets' + s for s in (' Mean', ' Std', ' Max', ' Min')]
+        keys.append('Policy Loss')
+        keys += [n + s for n in ('Policy mu', 'Policy log std') for s in (' Mean', ' Std', ' Max', ' Min')]
+        return keys
+
     def _update_eval_statistics(self):
-        """Keys of :332-362 that derive from the step's tensors."""
-        B, A, P = self._engine.B, self._A, self.num_particles
-        qs = get_numpy(self._io('off_q_pred', (B, P))).T[:, :, None]            # sorted [P,B,1]
-        tg = get_numpy(self._io('off_q_target', (B, P))).T[:, :, None]
-        q_new = get_numpy(self._io('off_q_new', (B, P)))
-        log_pi = get_numpy(self._io('off_log_pi', (3 * B,)))[:B, None]
-        mean = get_numpy(self._io('off_mean', (3 * B, A)))[:B]
-        log_std = get_numpy(self._io('off_log_std', (3 * B, A)))[:B]
-        alpha = float(get_numpy(self._engine.scalars())[_lib.SC_ALPHA])
+        """Keys of :332-362 that derive from the step's tensors, reduced on the device (``oac_trainer_stats``)."""
+        vec = self._engine.stats_host()[0]
         st = self.eval_statistics
-        st['QF mean'] = np.mean(qs, axis=0).mean()
-        st['QF std'] = np.std(qs, axis=0).mean()
-        for i in range(P):
-            st['QF' + str(i) + ' Loss'] = np.mean((qs[i] - tg[i]) ** 2)
-            st.update(create_stats_ordered_dict('Q' + str(i) + 'Predictions', qs[i]))
-            st.update(create_stats_ordered_dict('Q' + str(i) + 'Targets', tg[i]))
-        lp = log_pi if not self.deterministic else 0.0
-        st['Policy Loss'] = np.mean(alpha * lp - q_new.min(axis=1, keepdims=True))
-        st.update(create_stats_ordered_dict('Policy mu', mean))
-        st.update(create_stats_ordered_dict('Policy log std', log_std))
+        for k, v in zip(self._stat_keys(), vec):
+            st[k] = v
 
     @property
     def networks(self):

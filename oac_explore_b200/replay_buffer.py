@@ -54,11 +54,20 @@ class ReplayBuffer(object):
         self._size = 0
         # host staging for add_sample: rows = obs | action | reward | terminal | next_obs
         self._W = 2 * O + A + 2
-        self._stage = torch.zeros((self.STAGE_ROWS, self._W), dtype=torch.float32).pin_memory()
+        # two pinned staging buffers (+ their device twins): while the copy / scatter of one is in flight the host
+        # fills the other; a buffer is only rewritten after the event recorded behind its scatter has completed
+        self._stages = [torch.zeros((self.STAGE_ROWS, self._W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._stages_dev = [torch.zeros((self.STAGE_ROWS, self._W), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._stage_events = [None, None]
+        self._stage_cur = 0
+        self._stage = self._stages[0]
         self._stage_np = self._stage.numpy()
-        self._stage_dev = torch.zeros((self.STAGE_ROWS, self._W), dtype=torch.float32, device=dev)
         self._n_staged = 0
         self._stage_top = 0
+        # ``random_batch`` with an attached trainer returns VIEWS of the trainer's batch rows (the next call overwrites
+        # them in place; the reference returns fresh arrays).  Set True when the caller keeps batches, e.g.
+        # rl_algorithm.py:163-165 ``save_sampled_data``: every returned tensor is then a private clone.
+        self.return_copies = False
         self._idx_host = None
         self._idx_dev = None
         self._trainer = None
@@ -67,11 +76,35 @@ class ReplayBuffer(object):
 
     # ---- insert path (replay_buffer.py:50-104) -------------------------------------
     def add_path(self, path):
-        for obs, action, reward, next_obs, terminal, agent_info, env_info in zip(
-                path["observations"], path["actions"], path["rewards"], path["next_observations"],
-                path["terminals"], path["agent_infos"], path["env_infos"]):
-            self.add_sample(observation=obs, action=action, reward=reward, next_observation=next_obs,
-                            terminal=terminal, agent_info=agent_info, env_info=env_info)
+        """replay_buffer.py:57-82, without the per-sample Python loop: the whole path is packed into the pinned staging
+        rows with five vectorised numpy stores ([T, 2O+A+2] fp32: obs | action | reward | terminal | next_obs) and goes to
+        the device as one copy + one scatter kernel (ring wrap and count zeroing on the device)."""
+        if hasattr(self._action_space, 'n') and not hasattr(self._action_space, 'low'):
+            raise AssertionError("discrete action spaces are not supported (replay_buffer.py:91)")
+        O, A = self._ob_dim, self._ac_dim
+        T = len(path["observations"])
+        obs = np.asarray(path["observations"], dtype=np.float64).reshape(T, O)
+        act = np.asarray(path["actions"], dtype=np.float64).reshape(T, A)
+        rew = np.asarray(path["rewards"], dtype=np.float64).reshape(T)
+        nob = np.asarray(path["next_observations"], dtype=np.float64).reshape(T, O)
+        term = np.asarray(path["terminals"]).reshape(T).astype(np.uint8)        # uint8 store (replay_buffer.py:45)
+        t = 0
+        while t < T:
+            if self._n_staged == 0:
+                self._stage_top = self._top
+            n = min(T - t, self.STAGE_ROWS - self._n_staged)
+            rows = self._stage_np[self._n_staged:self._n_staged + n]
+            rows[:, :O] = obs[t:t + n]
+            rows[:, O:O + A] = act[t:t + n]
+            rows[:, O + A] = rew[t:t + n]
+            rows[:, O + A + 1] = term[t:t + n]
+            rows[:, O + A + 2:] = nob[t:t + n]
+            self._n_staged += n
+            self._top = (self._top + n) % self._max_replay_buffer_size
+            self._size = min(self._size + n, self._max_replay_buffer_size)
+            t += n
+            if self._n_staged == self.STAGE_ROWS:
+                self._flush()
 
     def add_paths(self, paths):
         for path in paths:
@@ -104,13 +137,24 @@ class ReplayBuffer(object):
         if n == 0:
             return
         stream = torch.cuda.current_stream()
-        self._stage_dev[:n].copy_(self._stage[:n], non_blocking=True)
+        k = self._stage_cur
+        dev = self._stages_dev[k]
+        dev[:n].copy_(self._stage[:n], non_blocking=True)
         _lib.check(self._lib.oac_replay_add(
             _lib.ptr(self._observations), _lib.ptr(self._next_obs), _lib.ptr(self._actions),
             _lib.ptr(self._rewards), _lib.ptr(self._terminals), _lib.ptr(self._counts_dev),
-            self._max_replay_buffer_size, self._ob_dim, self._ac_dim, _lib.ptr(self._stage_dev), n,
+            self._max_replay_buffer_size, self._ob_dim, self._ac_dim, _lib.ptr(dev), n,
             self._stage_top, C.c_void_p(stream.cuda_stream)), "oac_replay_add")
-        stream.synchronize()          # the pinned staging rows are reused by the next add_sample
+        ev = self._stage_events[k] or torch.cuda.Event()
+        ev.record(stream)
+        self._stage_events[k] = ev
+        # switch to the other staging buffer; wait only if ITS previous flush is still in flight (no host stall otherwise)
+        k ^= 1
+        if self._stage_events[k] is not None:
+            self._stage_events[k].synchronize()
+        self._stage_cur = k
+        self._stage = self._stages[k]
+        self._stage_np = self._stage.numpy()
         self._n_staged = 0
 
     # ---- sample path (replay_buffer.py:106-115) ----------------------------------------
@@ -135,6 +179,10 @@ class ReplayBuffer(object):
     def _upload_indices(self, indices):
         n = len(indices)
         if self._idx_host is None or self._idx_host.shape[1] < n:
+            if self._idx_host is not None:
+                # queued gather kernels may still read the old pinned ring by pointer (torch's host allocator does not
+                # know about that use): drain the device before the ring is dropped
+                torch.cuda.synchronize()
             slots = self._RING_GROUPS * self._RING_GROUP_SLOTS
             self._idx_host = torch.zeros((slots, n), dtype=torch.int64).pin_memory()
             self._idx_np = self._idx_host.numpy()
@@ -208,7 +256,11 @@ class ReplayBuffer(object):
             e = tr._engine
             self.gather_into(e, idx_dev, batch_size)
             self._indices_consumed()
-            return self._resident_views(e, batch_size)
+            batch = self._resident_views(e, batch_size)
+            if self.return_copies:
+                batch = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+                batch.pop('_oac_resident')             # clones are not the trainer's rows any more: normal upload path
+            return batch
         out = self.gather_dense(idx_dev, batch_size)
         self._indices_consumed()
         return self._numpy_batch(out)

@@ -16,9 +16,11 @@ from . import _lib
 from .engine import Engine, make_config
 from .networks import get_policy_producer, get_q_producer
 
-N_STATS = 8
-STAT_NAMES = ("alpha", "alpha_loss", "log_pi_mean", "qf1_loss", "qf2_loss", "q_target_mean", "q1_pred_mean",
-              "policy_loss")
+from .trainer import SACTrainer as _SACTrainer
+
+# the per-seed statistics vector = SACTrainer's eval_statistics keys (trainer/trainer.py:243-279), reduced on the device
+STAT_NAMES = tuple(_SACTrainer.STAT_KEYS)
+N_STATS = len(STAT_NAMES)
 
 
 def partition_seeds(n_seeds_total, rank, world_size):
@@ -57,8 +59,19 @@ class SACSeedGroup(object):
                 objs[name] = net
             self.nets.append(objs)
         self._n_train_steps_total = 0
-        self._idx_host = torch.zeros((S, batch), dtype=torch.int64).pin_memory()
+        # the step's Philox noise is keyed by the REAL seed id, not the slot: seeds keep their stream wherever they are
+        # placed, and ranks holding different seeds never share one
+        ids = torch.tensor(self.seed_ids, dtype=torch.int64)
+        self.engine.counters[:, _lib.CNT_RNG_LO] = (ids & 0x7fffffff).to(torch.int32).to(self.engine.device)
+        self.engine.counters[:, _lib.CNT_RNG_HI] = (ids >> 31).to(torch.int32).to(self.engine.device)
+        # index upload: the host runs ahead of the stream (a step takes longer than drawing the next indices), so the
+        # pinned staging buffers form a ring and a slot is only rewritten after the copy that read it has completed
+        self._idx_ring = [torch.zeros((S, batch), dtype=torch.int64).pin_memory() for _ in range(self._IDX_RING)]
+        self._idx_events = [None] * self._IDX_RING
+        self._idx_slot = 0
         self._idx_dev = torch.zeros((S, batch), dtype=torch.int64, device=self.engine.device)
+
+    _IDX_RING = 4
 
     @property
     def n_seeds(self):
@@ -67,8 +80,17 @@ class SACSeedGroup(object):
     def gather(self, replay, indices):
         """indices: [S, B] int64 (host numpy or device tensor) -> one gather launch for all seeds."""
         if isinstance(indices, np.ndarray):
-            self._idx_host.numpy()[...] = indices
-            self._idx_dev.copy_(self._idx_host, non_blocking=True)
+            k = self._idx_slot
+            self._idx_slot = (k + 1) % self._IDX_RING
+            if self._idx_events[k] is not None:
+                self._idx_events[k].synchronize()          # the copy that last read this pinned slot is done
+            host = self._idx_ring[k]
+            host.numpy()[...] = indices
+            # _idx_dev itself is safe to overwrite: the copy is stream-ordered after the previous gather that read it
+            self._idx_dev.copy_(host, non_blocking=True)
+            ev = self._idx_events[k] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._idx_events[k] = ev
             indices = self._idx_dev
         replay.gather_into(self.engine, indices, self.B, seed=0, n_seeds=self.n_seeds)
 
@@ -85,22 +107,14 @@ class SACSeedGroup(object):
         self._n_train_steps_total += 1
 
     def stats(self):
-        """[S, N_STATS] fp32 device tensor (STAT_NAMES) of the last step -- the all-gather payload."""
-        e, L, B, S = self.engine, self.engine.lay, self.B, self.n_seeds
-        io = e.io
-        sc = io[:, L.off_scalars:L.off_scalars + 3]
-        qp = io[:, L.off_q_pred:L.off_q_pred + 2 * B].view(S, B, 2)
-        qt = io[:, L.off_q_target:L.off_q_target + 2 * B].view(S, B, 2)[:, :, 0]
-        qn = io[:, L.off_q_new:L.off_q_new + 2 * B].view(S, B, 2)
-        lp = io[:, L.off_log_pi:L.off_log_pi + B]
-        out = torch.empty((S, N_STATS), dtype=torch.float32, device=e.device)
-        out[:, 0:3] = sc
-        out[:, 3] = ((qp[:, :, 0] - qt) ** 2).mean(dim=1)
-        out[:, 4] = ((qp[:, :, 1] - qt) ** 2).mean(dim=1)
-        out[:, 5] = qt.mean(dim=1)
-        out[:, 6] = qp[:, :, 0].mean(dim=1)
-        out[:, 7] = (lp - torch.minimum(qn[:, :, 0], qn[:, :, 1])).mean(dim=1)
-        return out
+        """[S, N_STATS] fp32 device tensor (STAT_NAMES: the reference's ``eval_statistics`` keys) of the last step,
+        reduced by one kernel (``oac_trainer_stats``) -- the all-gather payload."""
+        return self.engine.stats_device()
+
+    def explorer(self, hyper_params, **kw):
+        """One-launch exploration for all seeds' current observations (``optimistic_exploration.GroupExplorer``)."""
+        from .optimistic_exploration import GroupExplorer
+        return GroupExplorer(self, hyper_params, **kw)
 
 
 def allgather_stats(local_stats, seed_ids, n_seeds_total, group=None):

@@ -239,34 +239,19 @@ class SACTrainer(_EngineTrainer):
             return mu_Q
         return mu_Q + beta_UB * sigma_Q
 
+    STAT_KEYS = (['QF mean', 'QF std', 'QF1 Loss', 'QF2 Loss', 'Q Loss', 'Policy Loss'] +
+                 [n + s for n in ('Q1 Predictions', 'Q2 Predictions', 'Q Targets', 'Log Pis', 'Policy mu', 'Policy log std')
+                  for s in (' Mean', ' Std', ' Max', ' Min')] + ['Alpha', 'Alpha Loss'])
+
     def _update_eval_statistics(self):
-        """Same keys and definitions as trainer/trainer.py:230-279."""
-        B, A = self._engine.B, self._A
-        q_pred = get_numpy(self._io('off_q_pred', (B, 2)))
-        q_target = get_numpy(self._io('off_q_target', (B, 2)))[:, :1]
-        q_new = get_numpy(self._io('off_q_new', (B, 2)))
-        log_pi = get_numpy(self._io('off_log_pi', (3 * B,)))[:B, None]
-        mean = get_numpy(self._io('off_mean', (3 * B, A)))[:B]
-        log_std = get_numpy(self._io('off_log_std', (3 * B, A)))[:B]
-        sc = get_numpy(self._engine.scalars())
-        q1, q2 = q_pred[:, :1], q_pred[:, 1:]
+        """Same keys, order and definitions as trainer/trainer.py:230-279, reduced on the device by ONE kernel
+        (``oac_trainer_stats``) straight into mapped host memory instead of seven device-to-host copies + numpy."""
+        vec = self._engine.stats_host()[0]
         st = self.eval_statistics
-        qf1_loss, qf2_loss = np.mean((q1 - q_target) ** 2), np.mean((q2 - q_target) ** 2)
-        stack = np.stack([q1, q2], axis=0)
-        st['QF mean'] = np.mean(stack, axis=0).mean()
-        st['QF std'] = np.std(stack, axis=0).mean()
-        st['QF1 Loss'], st['QF2 Loss'], st['Q Loss'] = qf1_loss, qf2_loss, qf1_loss + qf2_loss
-        # the logged policy loss carries no alpha (trainer/trainer.py:236)
-        st['Policy Loss'] = np.mean(log_pi - np.minimum(q_new[:, :1], q_new[:, 1:]))
-        st.update(create_stats_ordered_dict('Q1 Predictions', q1))
-        st.update(create_stats_ordered_dict('Q2 Predictions', q2))
-        st.update(create_stats_ordered_dict('Q Targets', q_target))
-        st.update(create_stats_ordered_dict('Log Pis', log_pi))
-        st.update(create_stats_ordered_dict('Policy mu', mean))
-        st.update(create_stats_ordered_dict('Policy log std', log_std))
-        if self.use_automatic_entropy_tuning:
-            st['Alpha'] = float(sc[_lib.SC_ALPHA])
-            st['Alpha Loss'] = float(sc[_lib.SC_ALPHA_LOSS])
+        for k, v in zip(self.STAT_KEYS, vec):
+            if k.startswith('Alpha') and not self.use_automatic_entropy_tuning:
+                continue
+            st[k] = v
 
     @property
     def networks(self):

@@ -39,6 +39,89 @@ TANH_EPS = 1e-6     # trainer/policies.py:127
 
 
 # --------------------------------------------------------------------------
+# TF32 arithmetic model (for the tcgen05 kind::tf32 path only)
+# --------------------------------------------------------------------------
+# The reference computes every nn.Linear product in fp32.  The CUDA GEMM_TF32 path feeds the tensor
+# cores with operands rounded to tf32 (10 mantissa bits; the TMA unit rounds to nearest on the way into
+# shared memory) and accumulates in fp32.  ``tf32_mode`` restates exactly that arithmetic on the CPU --
+# both operands of the forward product, of the input-gradient product (dY W) and of the weight-gradient
+# product (dY^T X, and the bias gradient as the column sums of the ROUNDED dY, which is what the all-ones
+# MMA computes) are rounded, products and sums stay fp32 -- so the CUDA path can be held to rel <= 1e-3 on
+# gradients and weights too, not only on values: against THIS model ReLU masks agree, against the fp32
+# oracle they flip for the few units whose pre-activation sits within the rounding error of zero.
+#   "all"   : every Linear (many-seed regime: head layers, dQ/da and the head backward are GEMM stages)
+#   "trunk" : hidden layers only; a head layer is exact fp32 forward and in its input gradient (they are
+#             fused into the glue kernels in the few-seed regime) but its WEIGHT gradient is still a GEMM stage
+_TF32 = {"mode": None}
+
+
+def round_tf32(x):
+    """fp32 -> tf32, round to nearest (ties away from zero, cvt.rna.tf32.f32), kept in an fp32 container."""
+    if x.dtype != torch.float32:
+        return x
+    i = x.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class tf32_mode(object):
+    """``with orc.tf32_mode("all"): orc.sac_step(...)`` (see the comment above)."""
+
+    def __init__(self, mode="all"):
+        assert mode in (None, "all", "trunk")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _TF32["mode"]
+        _TF32["mode"] = self.mode
+        return self
+
+    def __exit__(self, *a):
+        _TF32["mode"] = self.prev
+        return False
+
+
+class _LinearTF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, r_fwd, r_dx, r_dw):
+        ctx.save_for_backward(x, w)
+        ctx.flags = (r_dx, r_dw)
+        xr, wr = (round_tf32(x), round_tf32(w)) if r_fwd else (x, w)
+        y = xr @ wr.t()
+        return y + b if b is not None else y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        r_dx, r_dw = ctx.flags
+        gr = round_tf32(gy)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (gr @ round_tf32(w)) if r_dx else (gy @ w)
+        if ctx.needs_input_grad[1]:
+            gw = (gr.t() @ round_tf32(x)) if r_dw else (gy.t() @ x)
+        if ctx.needs_input_grad[2]:
+            gb = (gr if r_dw else gy).sum(dim=0)
+        return gx, gw, gb, None, None, None
+
+
+def linear(x, w, b, head=False):
+    """y = x W^T + b (nn.Linear).  fp32 / fp64 exact unless a ``tf32_mode`` is active."""
+    mode = _TF32["mode"]
+    if mode is None or x.dtype != torch.float32:
+        return x @ w.t() + b
+    exact = head and mode == "trunk"
+    return _LinearTF32.apply(x, w, b, not exact, not exact, True)
+
+
+def matmul_dx(g, w, head=False):
+    """grad_in = grad_out @ W (Linear backward, written out by hand in ``_q_dx_action``)."""
+    mode = _TF32["mode"]
+    if mode is None or g.dtype != torch.float32 or (head and mode == "trunk"):
+        return g @ w
+    return round_tf32(g) @ round_tf32(w)
+
+
+# --------------------------------------------------------------------------
 # replay buffer  (replay_buffer.py:8-148, 151-203)
 # --------------------------------------------------------------------------
 class ReplayBuffer(object):
@@ -184,7 +267,7 @@ def mlp_trunk(p, x):
     hs = []
     h = x
     for i in range(_n_hidden(p)):
-        h = torch.relu(h @ p['fc%d.weight' % i].t() + p['fc%d.bias' % i])
+        h = torch.relu(linear(h, p['fc%d.weight' % i], p['fc%d.bias' % i]))
         hs.append(h)
     return hs
 
@@ -193,7 +276,7 @@ def q_forward(p, obs, act, positive=None, return_hidden=False):
     """FlattenMlp.forward (networks.py:154-161 cat; :62-79 MLP; :69-75 ``positive`` -> exp)."""
     x = torch.cat([obs, act], dim=1)
     hs = mlp_trunk(p, x)
-    out = hs[-1] @ p['last_fc.weight'].t() + p['last_fc.bias']
+    out = linear(hs[-1], p['last_fc.weight'], p['last_fc.bias'], head=True)
     if positive is not None and positive is not False:
         if isinstance(positive, (list, tuple)):
             cols = [torch.exp(out[:, i]) if v else out[:, i] for i, v in enumerate(positive)]
@@ -211,8 +294,8 @@ def policy_forward(p, obs, eps=None, deterministic=False):
     TanhNormal.rsample (:179-187).  Returns the reference's 6-tuple."""
     hs = mlp_trunk(p, obs)
     h = hs[-1]
-    mean = h @ p['last_fc.weight'].t() + p['last_fc.bias']
-    log_std = h @ p['last_fc_log_std.weight'].t() + p['last_fc_log_std.bias']
+    mean = linear(h, p['last_fc.weight'], p['last_fc.bias'], head=True)
+    log_std = linear(h, p['last_fc_log_std.weight'], p['last_fc_log_std.bias'], head=True)
     log_std = torch.clamp(log_std, LOG_SIG_MIN, LOG_SIG_MAX)
     std = torch.exp(log_std)
     if deterministic:
@@ -333,10 +416,11 @@ def _q_dx_action(p, hs, dq, obs_dim):
     """dQ/d(action) chain with explicit weights ``p`` and saved activations ``hs``:
     Linear backward grad_in = grad_out @ W, ReLU backward grad * (out > 0)."""
     n = len(hs)
-    g = dq @ p['last_fc.weight']
+    g = matmul_dx(dq, p['last_fc.weight'], head=True)
     for i in range(n - 1, -1, -1):
         g = g * (hs[i] > 0).to(g.dtype)
-        g = g @ p['fc%d.weight' % i]
+        # few-seed regime: the action columns of the fc0 product are formed inside the policy_grad glue kernel (fp32)
+        g = matmul_dx(g, p['fc%d.weight' % i], head=(i == 0))
     return g[:, obs_dim:]
 
 
@@ -683,30 +767,55 @@ def goac_step(st, batch):
 # optimistic exploration  (optimistic_exploration.py:14-196)
 # --------------------------------------------------------------------------
 def explore(ob, policy, qfs, beta_UB, delta, share_layers=False, eps_sample=None,
-            deterministic=False, positive=None):
-    """get_optimistic_exploration_action (stochastic :14-109 / deterministic :111-196)
-    with ``trainer=None``.  ``ob`` is an unbatched [O] tensor.  The policy's own
-    (discarded) rsample draw at :27 is not modelled -- it only advances the RNG.
-    Dispatch quirk (:41-58): with >=2 nets only qfs[0], qfs[1] are used (twin formula);
-    a single multi-head net takes the mean / unbiased-std branch.  The deterministic
+            deterministic=False, positive=None, trainer=None, positives=None):
+    """get_optimistic_exploration_action (stochastic :14-109 / deterministic :111-196).
+    ``ob`` is an unbatched [O] tensor.  The policy's own (discarded) rsample draw at :27 is not
+    modelled -- it only advances the RNG.
+    ``trainer=None``: dispatch quirk (:41-58): with >=2 nets only qfs[0], qfs[1] are used (twin
+    formula); a single multi-head net takes the mean / unbiased-std branch.  The deterministic
     variant always takes the ensemble branch and returns un-squashed mu_E (:181).
+    ``trainer=dict(kind=...)`` restates ``Q_UB = trainer.predict(ob[None], a[None], upper_bound=True,
+    beta_UB=beta_UB)`` (:38-39 / :135-136):
+      kind='sac'      SACTrainer.predict (trainer/trainer.py:105-123): twin formula on trainer.qfs[0:2]
+      kind='particle' ParticleTrainer.predict (trainer/particle_trainer_oac.py:147-167): the
+                      ``delta_index``-th smallest particle (sort over the particle axis); beta_UB unused
+      kind='gaussian' GaussianTrainer.predict(obs, action, std=True) has no ``upper_bound`` keyword
+                      (trainer/gaussian_trainer.py:161): the reference raises TypeError, so do we.
+    ``positives``: one ``positive`` spec per critic (networks.py:69-75), e.g. [False, True] for G-OAC's
+    separate mean / std nets; ``positive`` applies one spec to every critic.
     Returns (action_or_muE, mu_E, grad)."""
     _, mu_T, _, _, std, _ = policy_forward(policy, ob[None], None, True)
     mu_T = mu_T[0].detach().clone().requires_grad_(True)
     std = std[0].detach()
     a = torch.tanh(mu_T)
-    if (not deterministic) and len(qfs) >= 2:
-        Q1 = q_forward(qfs[0], ob[None], a[None], positive=positive)
-        Q2 = q_forward(qfs[1], ob[None], a[None], positive=positive)
+    pos = positives if positives is not None else [positive] * len(qfs)
+    qf = lambda i: q_forward(qfs[i], ob[None], a[None], positive=pos[i])
+    Q_UB = None
+    if trainer is not None:
+        kind = trainer['kind']
+        if kind == 'sac':
+            Q1, Q2 = qf(0), qf(1)
+            mu_Q = (Q1 + Q2) / 2.0
+            sigma_Q = torch.abs(Q1 - Q2) / 2.0
+        elif kind == 'particle':
+            qs = torch.stack([qf(i) for i in range(len(qfs))], dim=0)
+            if trainer.get('share_layers', share_layers):
+                qs = qs.permute(2, 1, 0)
+            Q_UB = torch.sort(qs, dim=0)[0][trainer['delta_index']]
+        else:
+            raise TypeError("predict() got an unexpected keyword argument 'upper_bound'")
+    elif (not deterministic) and len(qfs) >= 2:
+        Q1, Q2 = qf(0), qf(1)
         mu_Q = (Q1 + Q2) / 2.0
         sigma_Q = torch.abs(Q1 - Q2) / 2.0
     else:
-        qs = torch.stack([q_forward(q, ob[None], a[None], positive=positive) for q in qfs], dim=0)
+        qs = torch.stack([qf(i) for i in range(len(qfs))], dim=0)
         if share_layers:
             qs = qs.permute(2, 1, 0)
         mu_Q = torch.mean(qs, dim=0)
         sigma_Q = torch.std(qs, dim=0)
-    Q_UB = mu_Q + beta_UB * sigma_Q
+    if Q_UB is None:
+        Q_UB = mu_Q + beta_UB * sigma_Q
     grad, = torch.autograd.grad(Q_UB.sum(), mu_T)
     if deterministic:
         denom = torch.sqrt(torch.sum(grad ** 2)) + 10e-6          # :160-164

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert set(_lib.EXPORTS) == set(names)
-    assert L.oac_abi_version() == 2
+    assert L.oac_abi_version() == 3
 
 
 def test_ctypes_structs_match_header_sizes():
@@ -34,6 +34,9 @@ def test_ctypes_structs_match_header_sizes():
     assert C.sizeof(_lib.OacNetLayout) == 6 * 4 + 7 * 8
     assert C.sizeof(_lib.OacConfig) == 16 * 4 + 12 * 4 + 8
     assert C.sizeof(_lib.OacBuffers) == 7 * 8
+    # OacExploreArgs: policy*, layout, q[48], layout, 8 x 32-bit (n_q .. n_obs), obs*, eps*, 2 u64, 3 out*, obs_group*, group_stride
+    lay = C.sizeof(_lib.OacNetLayout)
+    assert C.sizeof(_lib.OacExploreArgs) == 8 + lay + 48 * 8 + lay + 8 * 4 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8
 
 
 @pytest.mark.parametrize("algo,kw,n_nets,n_train", [

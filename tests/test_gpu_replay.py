@@ -145,3 +145,107 @@ def test_pinned_index_ring_without_host_synchronisation():
     for i in range(n_batches):
         idx = torch.from_numpy(np.random.randint(0, N, B))
         assert torch.equal(keep[i].cpu(), store[idx]), i
+
+
+# ---- round 2 ----
+def _path(rng, T, O, A):
+    return dict(observations=rng.randn(T, O), actions=rng.rand(T, A) * 2 - 1, rewards=rng.randn(T, 1),
+                next_observations=rng.randn(T, O), terminals=(rng.rand(T, 1) < 0.1),
+                agent_infos=[{}] * T, env_infos=[{}] * T)
+
+
+@pytest.mark.parametrize("N,lens", [(100, [30, 50, 45, 7]), (9000, [4096, 4096, 300, 5000])])
+def test_add_path_packed_equals_add_sample_loop(N, lens):
+    """add_path packs a whole path with vectorised stores + one scatter launch (replay_buffer.py:57-82 loops per sample):
+    same store, _top, _size and counts as the oracle's per-sample loop, across ring wraps, staging-buffer switches and
+    paths longer than the staging buffer."""
+    from oac_explore_b200.replay_buffer import ReplayBufferCount
+    O, A = 6, 2
+    rng = np.random.RandomState(3)
+    rb = ReplayBufferCount(N, Box(O), Box(A))
+    ob = orc.ReplayBufferCount(N, O, A)
+    for i, T in enumerate(lens):
+        p = _path(rng, T, O, A)
+        rb.add_paths([p])
+        for t in range(T):
+            ob.add_sample(p['observations'][t], p['actions'][t], p['rewards'][t], p['next_observations'][t], p['terminals'][t])
+        if i == 1:          # sample in between so some counts are non-zero before the next overwrite zeroes them
+            np.random.seed(1); rb.random_batch(16)
+            np.random.seed(1); ob.random_batch(16)
+    assert (rb._top, rb._size) == (ob._top, ob._size)
+    ss = rb.get_snapshot()
+    n = ob._size
+    assert np.array_equal(ss['_observations'][:n], ob._observations[:n].astype(np.float32))
+    assert np.array_equal(ss['_next_obs'][:n], ob._next_obs[:n].astype(np.float32))
+    assert np.array_equal(ss['_actions'][:n], ob._actions[:n].astype(np.float32))
+    assert np.array_equal(ss['_rewards'][:n], ob._rewards[:n].astype(np.float32))
+    assert np.array_equal(ss['_terminals'][:n], ob._terminals[:n])
+    assert np.array_equal(rb._counts[:n], ob._counts[:n])
+
+
+@pytest.mark.parametrize("B", [256, 2048, 7000])
+def test_counts_bump_once_per_distinct_index(B):
+    """numpy fancy ``counts[idx] += 1`` increments a duplicated index ONCE (replay_buffer.py:195): heavy duplication
+    (B draws from 50 slots), the shared-memory staging kernel (B <= 6144) and the plain-scan fallback (B = 7000)."""
+    from oac_explore_b200.replay_buffer import ReplayBufferCount
+    O, A, N = 3, 1, 50
+    rb = ReplayBufferCount(N, Box(O), Box(A))
+    ob = orc.ReplayBufferCount(N, O, A)
+    rng = np.random.RandomState(0)
+    for t in range(N):
+        s = (rng.randn(O), rng.rand(A), rng.randn(), rng.randn(O), False)
+        rb.add_sample(*s, env_info={}); ob.add_sample(*s)
+    for rep in range(3):
+        np.random.seed(rep); b1 = rb.random_batch(B)
+        np.random.seed(rep); b2 = ob.random_batch(B)
+        assert np.array_equal(b1['counts'], b2['counts'])
+    assert np.array_equal(rb._counts, ob._counts) and ob._counts.max() == 3
+
+
+def test_priority_sample_matches_reference_draw():
+    """replay_buffer.py:181-185: p ~ 1 / (count + 1), np.random.choice on the global stream."""
+    from oac_explore_b200.replay_buffer import ReplayBufferCount
+    O, A, N, B = 3, 1, 40, 8
+    rb = ReplayBufferCount(N, Box(O), Box(A), priority_sample=True)
+    ob = orc.ReplayBufferCount(N, O, A)
+    rng = np.random.RandomState(0)
+    for t in range(N):
+        s = (rng.randn(O), rng.rand(A), rng.randn(), rng.randn(O), False)
+        rb.add_sample(*s, env_info={}); ob.add_sample(*s)
+    for rep in range(4):
+        np.random.seed(rep)
+        b1 = rb.random_batch(B)
+        np.random.seed(rep)
+        probs = 1 / (ob._counts[:ob._size] + 1)
+        probs /= probs.sum()
+        idx = np.random.choice(np.arange(ob._size), size=B, p=probs[:, 0])
+        b2 = ob.gather(idx)
+        for k in b2:
+            assert np.array_equal(b1[k].astype(np.float32), b2[k].astype(np.float32)), (rep, k)
+    assert np.array_equal(rb._counts, ob._counts)
+
+
+def test_random_batch_return_copies_flag():
+    """With a trainer attached random_batch returns views of the trainer's batch rows (overwritten by the next call);
+    ``return_copies`` gives private tensors for callers that keep batches (rl_algorithm.py:163-165)."""
+    from oac_explore_b200.replay_buffer import ReplayBuffer
+    from tests.test_gpu_sac import make_trainer
+    O, A, N, B, H = 5, 2, 200, 16, 32
+    rb = ReplayBuffer(N, Box(O), Box(A))
+    g = torch.Generator(device='cuda').manual_seed(1)
+    rb._observations.normal_(generator=g)
+    rb._size = N
+    tr = make_trainer(O, A, H)
+    rb.attach(tr)
+    np.random.seed(0); v1 = rb.random_batch(B)['observations']
+    keep = v1.clone()
+    np.random.seed(1); rb.random_batch(B)
+    assert not torch.equal(v1, keep)                 # a view: the second batch replaced it
+    rb.return_copies = True
+    np.random.seed(0); c1 = rb.random_batch(B)
+    assert '_oac_resident' not in c1
+    np.random.seed(1); rb.random_batch(B)
+    assert torch.equal(c1['observations'], keep)     # a private copy: unchanged
+    c1['buffer'] = rb
+    tr.train(c1)                                     # goes through the normal upload path
+    assert tr._n_train_steps_total == 1

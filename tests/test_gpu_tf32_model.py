@@ -1,0 +1,186 @@
+"""The tcgen05 kind::tf32 path against the TF32 arithmetic model of the oracle (``orc.tf32_mode``: both operands of every
+forward, input-gradient and weight-gradient product rounded to tf32, fp32 accumulate), at the tolerance BASELINE.json's
+north_star states for TF32: norm-wise rel <= 1e-3 on Q-values, losses, GRADIENTS and UPDATED WEIGHTS.
+
+Round 1 compared the TF32 path with the fp32 oracle only and had to allow 3e-2 on gradients (a 3e-4 relative error on a
+pre-activation flips the ReLU mask of the few units that sit that close to zero).  The model removes the excuse: against
+it the masks agree, so any remaining difference is accumulation order -- and the fp32 oracle comparison of the values
+and losses (<= 1e-3) is kept next to it.  ``test_tf32_model_differs_from_fp32_like_the_kernel`` shows the model
+reproduces the ~1e-2 gradient gap to fp32 that the round-1 tests tolerated, i.e. the gap IS tf32 rounding."""
+import pytest
+import torch
+
+from oracle import oac_oracle as orc
+from tests.util import synth_batch, synth_eps, rel_err, max_abs
+from tests.gpu_util import net_cpu
+from tests.test_gpu_sac import make_trainer, NETS
+from tests.test_gpu_poac_goac import make_poac, make_goac
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north_star: "rel <= 1e-3 with TF32 tensor cores"
+O, A, B, H = 376, 17, 256, 256
+
+
+def grads_of(e, idx, seed=0):
+    """first-step gradients = exp_avg / (1 - beta1)"""
+    return {k: v.cpu() / 0.1 for k, v in e.net_views(idx, seed=seed, arena=e.adam_m).items()}
+
+
+def test_sac_single_seed_tf32_vs_model():
+    """One seed on the TF32 path (few-seed regime: head layers stay fp32 in the glue kernels -> model mode "trunk")."""
+    torch.manual_seed(0)
+    tr = make_trainer(O, A, H, gemm_path=1)
+    torch.manual_seed(0)
+    st = orc.SACState(O, A, hidden=(H, H))          # tf32 model
+    torch.manual_seed(0)
+    st32 = orc.SACState(O, A, hidden=(H, H))        # fp32 oracle (values / losses)
+    for s in range(3):
+        batch = synth_batch(B, O, A, seed=10 + s)
+        eps = synth_eps(2, B, A, seed=100 + s)
+        with orc.tf32_mode("trunk"):
+            out = orc.sac_step(st, batch, eps[0], eps[1])
+        out32 = orc.sac_step(st32, batch, eps[0], eps[1])
+        tr.inject_noise(eps[0], eps[1])
+        tr._need_to_update_eval_statistics = True
+        tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
+        e = tr._engine
+        qp = e.io_view(e.lay.off_q_pred, (B, 2)).cpu()
+        for ref, tol in ((out, TOL), (out32, TOL)):
+            assert rel_err(qp[:, 0], ref['q1_pred'][:, 0]) <= tol
+            assert rel_err(qp[:, 1], ref['q2_pred'][:, 0]) <= tol
+            assert rel_err(e.io_view(e.lay.off_q_target, (B, 2)).cpu()[:, 0], ref['q_target'][:, 0]) <= tol
+            assert rel_err(e.io_view(e.lay.off_log_pi, (3 * B,)).cpu()[:B], ref['log_pi'][:, 0]) <= tol
+            assert abs(tr.eval_statistics['QF1 Loss'] - float(ref['qf1_loss'])) <= tol * abs(float(ref['qf1_loss']))
+            assert abs(tr.eval_statistics['QF2 Loss'] - float(ref['qf2_loss'])) <= tol * abs(float(ref['qf2_loss']))
+        if s == 0:
+            for idx, gname in ((0, 'grad_policy'), (1, 'grad_qf1'), (2, 'grad_qf2')):
+                for k, got in grads_of(e, idx).items():
+                    assert rel_err(got, out[gname][k]) <= TOL, (gname, k, rel_err(got, out[gname][k]))
+    for n in NETS:
+        ours = net_cpu(getattr(tr, n))
+        for k, v in getattr(st, n).items():
+            assert rel_err(ours[k], v) <= TOL, (n, k, rel_err(ours[k], v))
+
+
+def test_tf32_model_differs_from_fp32_like_the_kernel():
+    """The ~1e-2 gradient gap between the TF32 path and the fp32 oracle is tf32 rounding, not a kernel defect: the CPU
+    model shows the same gap to fp32 (> 3e-3 on the first layer's gradient) while the kernel sits within 1e-3 of the model."""
+    torch.manual_seed(0)
+    tr = make_trainer(O, A, H, gemm_path=1)
+    torch.manual_seed(0)
+    st = orc.SACState(O, A, hidden=(H, H))
+    torch.manual_seed(0)
+    st32 = orc.SACState(O, A, hidden=(H, H))
+    batch = synth_batch(B, O, A, seed=10)
+    eps = synth_eps(2, B, A, seed=100)
+    with orc.tf32_mode("trunk"):
+        out = orc.sac_step(st, batch, eps[0], eps[1])
+    out32 = orc.sac_step(st32, batch, eps[0], eps[1])
+    tr.inject_noise(eps[0], eps[1])
+    tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
+    got = grads_of(tr._engine, 1)['fc0.weight']
+    model_vs_fp32 = rel_err(out['grad_qf1']['fc0.weight'], out32['grad_qf1']['fc0.weight'])
+    kernel_vs_model = rel_err(got, out['grad_qf1']['fc0.weight'])
+    kernel_vs_fp32 = rel_err(got, out32['grad_qf1']['fc0.weight'])
+    assert model_vs_fp32 > 3e-3 and kernel_vs_fp32 > 3e-3
+    assert kernel_vs_model <= TOL and kernel_vs_model < 0.2 * model_vs_fp32
+
+
+def test_group_of_64_seeds_tf32_vs_oracle():
+    """BASELINE config 5 as benchmarked: 64 seeds in one SACSeedGroup on the warp-specialised TMA + tcgen05 program
+    (>= 13 gemm_ws stages).  A sample of 8 seeds is compared with the ORACLE (not with the repo's own fp32 singles):
+    the tf32 model at <= 1e-3 on values, losses, gradients and weights, the fp32 oracle at <= 1e-3 on values / losses."""
+    from oac_explore_b200.seed_group import SACSeedGroup
+    S = 64
+    ids = list(range(S))
+    grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=1)
+    e = grp.engine
+    assert e.ws_stages >= 13, e.ws_stages
+    sample = [0, 7, 13, 21, 34, 42, 55, 63]
+    states, states32 = {}, {}
+    for sid in sample:
+        torch.manual_seed(sid)
+        states[sid] = orc.SACState(O, A, hidden=(H, H))
+        torch.manual_seed(sid)
+        states32[sid] = orc.SACState(O, A, hidden=(H, H))
+    for step in range(2):
+        outs, outs32 = {}, {}
+        for slot, sid in enumerate(ids):
+            batch = synth_batch(B, O, A, seed=1000 * sid + step)
+            eps = synth_eps(2, B, A, seed=77 * sid + step)
+            grp.load_batch(slot, batch)
+            grp.inject_noise(slot, eps[0], eps[1])
+            if sid in states:
+                with orc.tf32_mode("all"):
+                    outs[sid] = orc.sac_step(states[sid], batch, eps[0], eps[1])
+                outs32[sid] = orc.sac_step(states32[sid], batch, eps[0], eps[1])
+        grp.step(external_eps=True)
+        torch.cuda.synchronize()
+        stats = grp.stats().cpu()
+        for sid in sample:
+            slot = sid
+            qp = e.io_view(e.lay.off_q_pred, (B, 2), seed=slot).cpu()
+            qt = e.io_view(e.lay.off_q_target, (B, 2), seed=slot).cpu()[:, 0]
+            lp = e.io_view(e.lay.off_log_pi, (3 * B,), seed=slot).cpu()[:B]
+            for ref in (outs[sid], outs32[sid]):
+                assert rel_err(qp[:, 0], ref['q1_pred'][:, 0]) <= TOL, (sid, step)
+                assert rel_err(qp[:, 1], ref['q2_pred'][:, 0]) <= TOL, (sid, step)
+                assert rel_err(qt, ref['q_target'][:, 0]) <= TOL, (sid, step)
+                assert rel_err(lp, ref['log_pi'][:, 0]) <= TOL, (sid, step)
+                assert abs(float(stats[slot, 2]) - float(ref['qf1_loss'])) <= TOL * abs(float(ref['qf1_loss']))
+                assert abs(float(stats[slot, 3]) - float(ref['qf2_loss'])) <= TOL * abs(float(ref['qf2_loss']))
+            if step == 0:
+                for idx, gname in ((0, 'grad_policy'), (1, 'grad_qf1'), (2, 'grad_qf2')):
+                    for k, got in grads_of(e, idx, seed=slot).items():
+                        r = rel_err(got, outs[sid][gname][k])
+                        assert r <= TOL, (sid, gname, k, r)
+    for sid in sample:
+        for n in NETS:
+            ours = net_cpu(grp.nets[sid][n])
+            for k, v in getattr(states[sid], n).items():
+                assert rel_err(ours[k], v) <= TOL, (sid, n, k, rel_err(ours[k], v))
+
+
+@pytest.mark.parametrize("share", [True, False])
+def test_poac_goac_tensor_path_vs_model(share):
+    """P-OAC / G-OAC in the many-row regime (every product a GEMM stage -> model mode "all"): gradients <= 1e-3."""
+    o, a, b, h, P = 24, 4, 2048, 64, 5
+    torch.manual_seed(1)
+    tr = make_poac(o, a, h, P, share, False)
+    tr.gemm_path = 1
+    tr._make_engine(b)
+    assert tr._engine.ws_stages >= 12
+    torch.manual_seed(1)
+    st = orc.ParticleState(o, a, hidden=(h, h), n_estimators=P, share_layers=share, q_min=0., q_max=500.)
+    batch = synth_batch(b, o, a, seed=20)
+    eps = synth_eps(2, b, a, seed=200)
+    with orc.tf32_mode("all"):
+        ref = orc.poac_step(st, batch, eps[0], eps[1])
+    tr.inject_noise(eps_obs=eps[1], eps_next=eps[0])
+    tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
+    e = tr._engine
+    assert rel_err(e.io_view(e.lay.off_q_target, (b, P)).cpu().t(), ref['q_target'][:, :, 0]) <= TOL
+    for k, got in grads_of(e, 0).items():
+        assert rel_err(got, ref['grad_policy'][k]) <= TOL, ('poac policy', k, rel_err(got, ref['grad_policy'][k]))
+    for i in range(len(st.qfs)):
+        for k, got in grads_of(e, 1 + i).items():
+            gref = ref['grad_qf'][i][k]
+            assert rel_err(got, gref) <= TOL, ('poac qf', i, k, rel_err(got, gref))
+
+    torch.manual_seed(2)
+    tg = make_goac(o, a, h, share, False)
+    tg.gemm_path = 1
+    tg._make_engine(b)
+    torch.manual_seed(2)
+    sg = orc.GaussianState(o, a, hidden=(h, h), share_layers=share, q_min=0., q_max=500.)
+    batch = synth_batch(b, o, a, seed=30)
+    with orc.tf32_mode("all"):
+        og = orc.goac_step(sg, batch)
+    tg.train_from_torch({k: v.cuda() for k, v in batch.items()})
+    e = tg._engine
+    for idx, gname in ((0, 'grad_policy'), (1, 'grad_target_policy'), (2, 'grad_q')):
+        for k, got in grads_of(e, idx).items():
+            if og[gname][k] is None:
+                continue
+            assert rel_err(got, og[gname][k]) <= TOL, (gname, k, rel_err(got, og[gname][k]))
