@@ -49,9 +49,15 @@ TANH_EPS = 1e-6     # trainer/policies.py:127
 # MMA computes) are rounded, products and sums stay fp32 -- so the CUDA path can be held to rel <= 1e-3 on
 # gradients and weights too, not only on values: against THIS model ReLU masks agree, against the fp32
 # oracle they flip for the few units whose pre-activation sits within the rounding error of zero.
-#   "all"   : every Linear (many-seed regime: head layers, dQ/da and the head backward are GEMM stages)
-#   "trunk" : hidden layers only; a head layer is exact fp32 forward and in its input gradient (they are
-#             fused into the glue kernels in the few-seed regime) but its WEIGHT gradient is still a GEMM stage
+# Which products are GEMM stages (rounded) and which are fused into the fp32 "glue" kernels (exact) depends on the regime
+# the program builder picks (oac_explore_b200/csrc/program.cu); hidden layers are GEMM stages in every regime:
+#   "trunk" : few seeds (< 2048 batch rows per launch).  Head layers (critic AND policy) are exact in the forward and in
+#             their input gradient, and so is the action-column product dh1 W0[:, O:O+A] of the policy loss; a head's
+#             WEIGHT gradient is a GEMM stage.
+#   "many"  : many seeds (the batched-seed program).  The policy head, its backward, dQ/da and -- SAC mode A -- the
+#             policy-loss product dq W3 are GEMM stages too; the critic head's forward and its Q-loss input gradient stay
+#             in the critic_head glue kernel (exact).
+#   "all"   : every Linear rounded (the idealised model; no kernel regime is exactly this).
 _TF32 = {"mode": None}
 
 
@@ -67,7 +73,7 @@ class tf32_mode(object):
     """``with orc.tf32_mode("all"): orc.sac_step(...)`` (see the comment above)."""
 
     def __init__(self, mode="all"):
-        assert mode in (None, "all", "trunk")
+        assert mode in (None, "all", "trunk", "many")
         self.mode = mode
 
     def __enter__(self):
@@ -104,19 +110,21 @@ class _LinearTF32(torch.autograd.Function):
         return gx, gw, gb, None, None, None
 
 
-def linear(x, w, b, head=False):
-    """y = x W^T + b (nn.Linear).  fp32 / fp64 exact unless a ``tf32_mode`` is active."""
+def linear(x, w, b, head=None):
+    """y = x W^T + b (nn.Linear).  fp32 / fp64 exact unless a ``tf32_mode`` is active.  head: None (hidden layer),
+    'q' (critic output layer) or 'pi' (policy output layers)."""
     mode = _TF32["mode"]
     if mode is None or x.dtype != torch.float32:
         return x @ w.t() + b
-    exact = head and mode == "trunk"
+    exact = (head is not None and mode == "trunk") or (head == 'q' and mode == "many")
     return _LinearTF32.apply(x, w, b, not exact, not exact, True)
 
 
-def matmul_dx(g, w, head=False):
-    """grad_in = grad_out @ W (Linear backward, written out by hand in ``_q_dx_action``)."""
+def matmul_dx(g, w, exact_modes=()):
+    """grad_in = grad_out @ W (Linear backward, written out by hand in ``_q_dx_action``); exact fp32 in the tf32 regimes
+    listed in ``exact_modes`` (the product is fused into a glue kernel there)."""
     mode = _TF32["mode"]
-    if mode is None or g.dtype != torch.float32 or (head and mode == "trunk"):
+    if mode is None or g.dtype != torch.float32 or mode in exact_modes:
         return g @ w
     return round_tf32(g) @ round_tf32(w)
 
@@ -276,7 +284,7 @@ def q_forward(p, obs, act, positive=None, return_hidden=False):
     """FlattenMlp.forward (networks.py:154-161 cat; :62-79 MLP; :69-75 ``positive`` -> exp)."""
     x = torch.cat([obs, act], dim=1)
     hs = mlp_trunk(p, x)
-    out = linear(hs[-1], p['last_fc.weight'], p['last_fc.bias'], head=True)
+    out = linear(hs[-1], p['last_fc.weight'], p['last_fc.bias'], head='q')
     if positive is not None and positive is not False:
         if isinstance(positive, (list, tuple)):
             cols = [torch.exp(out[:, i]) if v else out[:, i] for i, v in enumerate(positive)]
@@ -294,8 +302,8 @@ def policy_forward(p, obs, eps=None, deterministic=False):
     TanhNormal.rsample (:179-187).  Returns the reference's 6-tuple."""
     hs = mlp_trunk(p, obs)
     h = hs[-1]
-    mean = linear(h, p['last_fc.weight'], p['last_fc.bias'], head=True)
-    log_std = linear(h, p['last_fc_log_std.weight'], p['last_fc_log_std.bias'], head=True)
+    mean = linear(h, p['last_fc.weight'], p['last_fc.bias'], head='pi')
+    log_std = linear(h, p['last_fc_log_std.weight'], p['last_fc_log_std.bias'], head='pi')
     log_std = torch.clamp(log_std, LOG_SIG_MIN, LOG_SIG_MAX)
     std = torch.exp(log_std)
     if deterministic:
@@ -412,15 +420,16 @@ class SACState(object):
                 dst[k].copy_(torch.as_tensor(np.asarray(sd[k])).to(dst[k].dtype).reshape(dst[k].shape))
 
 
-def _q_dx_action(p, hs, dq, obs_dim):
+def _q_dx_action(p, hs, dq, obs_dim, mode_b=False):
     """dQ/d(action) chain with explicit weights ``p`` and saved activations ``hs``:
-    Linear backward grad_in = grad_out @ W, ReLU backward grad * (out > 0)."""
+    Linear backward grad_in = grad_out @ W, ReLU backward grad * (out > 0).  (tf32 regimes: the head product is a GEMM
+    stage of the many-seed program in mode A only -- in mode B the critic_head kernel forms it; the action columns of the
+    fc0 product are formed inside the policy_grad kernel in the few-seed regime.)"""
     n = len(hs)
-    g = matmul_dx(dq, p['last_fc.weight'], head=True)
+    g = matmul_dx(dq, p['last_fc.weight'], exact_modes=("trunk", "many") if mode_b else ("trunk",))
     for i in range(n - 1, -1, -1):
         g = g * (hs[i] > 0).to(g.dtype)
-        # few-seed regime: the action columns of the fc0 product are formed inside the policy_grad glue kernel (fp32)
-        g = matmul_dx(g, p['fc%d.weight' % i], head=(i == 0))
+        g = matmul_dx(g, p['fc%d.weight' % i], exact_modes=("trunk",) if i == 0 else ())
     return g[:, obs_dim:]
 
 
@@ -477,8 +486,8 @@ def sac_step(st, batch, eps_pi, eps_next, mode="A", deterministic=False):
     w1, w2 = (st.qf1, st.qf2) if mode == "A" else ({k: v.detach() for k, v in qf1.items()},
                                                     {k: v.detach() for k, v in qf2.items()})
     with torch.no_grad():
-        g_a = _q_dx_action(w1, hs1, dq * sel1, st.obs_dim) + \
-              _q_dx_action(w2, hs2, dq * (1 - sel1), st.obs_dim)
+        g_a = _q_dx_action(w1, hs1, dq * sel1, st.obs_dim, mode == "B") + \
+              _q_dx_action(w2, hs2, dq * (1 - sel1), st.obs_dim, mode == "B")
     surrogate = (alpha.detach() * log_pi).mean() + (a_pi * g_a).sum()
     g_pi = _grads(surrogate, pol)
     st.opt_policy.step(g_pi)

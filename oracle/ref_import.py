@@ -30,10 +30,26 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("OAC_REFERENCE_ROOT", "/root/reference")
+# the byte-compiled copy of the same modules (oracle/build_ref.py): what travels to the GPU box
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "trainer", "trainer.py"))
+
+
+def compiled_available():
+    from oracle import build_ref
+    return build_ref.available()
+
+
+def import_root():
+    """Where the reference is imported from: its sources when present, else oracle/_ref (compiled from them)."""
+    if reference_available():
+        return REFERENCE_ROOT
+    if compiled_available():
+        return COMPILED_ROOT
+    return None
 
 
 def _install_shims():
@@ -117,6 +133,28 @@ def _install_shims():
         sys.modules["gtimer"] = gt
 
 
+class _CompiledFinder(object):
+    """sys.meta_path finder for the byte-compiled reference modules under oracle/_ref (``<path>.bin`` = .pyc bytes)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        rel = fullname.replace(".", os.sep)
+        pkg = os.path.join(self.root, rel, "__init__.bin")
+        mod = os.path.join(self.root, rel + ".bin")
+        if os.path.isfile(pkg):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, pkg)
+            return importlib.util.spec_from_file_location(fullname, pkg, loader=loader,
+                                                          submodule_search_locations=[os.path.dirname(pkg)])
+        if os.path.isfile(mod):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, mod)
+            return importlib.util.spec_from_file_location(fullname, mod, loader=loader)
+        return None
+
+
 _REF = None
 
 
@@ -125,12 +163,18 @@ def load_reference():
     global _REF
     if _REF is not None:
         return _REF
-    if not reference_available():
-        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    root = import_root()
+    if root is None:
+        raise RuntimeError("reference not present at %s and oracle/_ref not built" % REFERENCE_ROOT)
     _install_shims()
     # The reference uses top-level module names (``trainer``, ``utils``, ...),
     # so its root has to lead sys.path while it is imported.
-    sys.path.insert(0, REFERENCE_ROOT)
+    compiled = root == COMPILED_ROOT
+    if compiled:
+        finder = _CompiledFinder(root)
+        sys.meta_path.insert(0, finder)      # stays installed: the reference also imports lazily inside functions
+    else:
+        sys.path.insert(0, root)
     try:
         import importlib
         ns = types.SimpleNamespace()
@@ -145,7 +189,9 @@ def load_reference():
         ns.optimistic_exploration = importlib.import_module("optimistic_exploration")
         ns.gym = sys.modules["gym"]
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        if not compiled:
+            sys.path.remove(root)
+    ns.root = root
     ns.ptu.set_gpu_mode(False)
     _REF = ns
     return ns

@@ -116,6 +116,9 @@ def test_riverswim_real_data_through_the_drop_in_api():
     for n in NETS:
         ours = net_cpu(getattr(tr, n))
         for k in ours:
-            gu.assert_digest_close(ours[k], g['final/%s/%s' % (n, k)], 5e-6, n + '/' + k)
+            # digests are coarse (a sum over the tensor): 2e-5 of the tensor's L2 mass after 20 steps; the element-wise
+            # check on the stored full tensors below is the sharp one
+            gu.assert_digest_close(ours[k], g['final/%s/%s' % (n, k)], 2e-5, n + '/' + k)
         assert max_abs(ours['last_fc.weight'], g['final_full/%s/last_fc.weight' % n]) <= 5e-6
+        assert max_abs(ours['fc1.bias'], g['final_full/%s/fc1.bias' % n]) <= 2e-5      # values ~0.1: 2e-4 relative, << 2*lr
     assert max_abs(tr.log_alpha.cpu(), g['final/log_alpha']) <= 2e-6
