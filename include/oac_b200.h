@@ -69,13 +69,16 @@ typedef struct OacConfig {
                                     the policy-loss dX), 1 = "B" pre-step weights */
     int32_t target_update_period;
     int32_t gemm_path;           /* OacGemmPath */
-    int32_t reserved0;
+    int32_t std_soft_update;     /* P-OAC: targets = p * next + (1 - p) * (current - mean(current) + mean(next))
+                                    over the particle axis (trainer/particle_trainer_oac.py:210-219) */
     float discount, reward_scale, soft_target_tau;
     float policy_lr, qf_lr, std_lr;
     float target_entropy;
     float standard_bound;        /* G-OAC: norm.ppf(delta) */
     float std_init;              /* G-OAC: (q_max-q_min)/sqrt(12) */
     float adam_beta1, adam_beta2, adam_eps;
+    float std_soft_update_prob;  /* P-OAC std_soft_update: p */
+    float reserved2;
     uint64_t rng_seed;           /* device Philox stream when eps == NULL */
 } OacConfig;
 

@@ -27,11 +27,12 @@ class OacConfig(C.Structure):
         ("batch", C.c_int32), ("n_seeds", C.c_int32), ("n_particles", C.c_int32),
         ("share_layers", C.c_int32), ("deterministic", C.c_int32), ("auto_alpha", C.c_int32),
         ("counts", C.c_int32), ("train_bias", C.c_int32), ("stale_graph_mode", C.c_int32),
-        ("target_update_period", C.c_int32), ("gemm_path", C.c_int32), ("reserved0", C.c_int32),
+        ("target_update_period", C.c_int32), ("gemm_path", C.c_int32), ("std_soft_update", C.c_int32),
         ("discount", C.c_float), ("reward_scale", C.c_float), ("soft_target_tau", C.c_float),
         ("policy_lr", C.c_float), ("qf_lr", C.c_float), ("std_lr", C.c_float),
         ("target_entropy", C.c_float), ("standard_bound", C.c_float), ("std_init", C.c_float),
         ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
+        ("std_soft_update_prob", C.c_float), ("reserved2", C.c_float),
         ("rng_seed", C.c_uint64),
     ]
 

@@ -299,6 +299,8 @@ struct CriticHeadParams {
     int n_nets;           // P-OAC / G-OAC: critic nets per group (1 shared, P or 2 separate)
     int share_layers, counts;
     float discount, reward_scale, standard_bound, std_init;
+    int std_soft_update;  // P-OAC (:210-219)
+    float std_soft_prob;
     int iters;            // sample groups (of GLUE_SPC samples) per CTA
     // (critic, head) pairs in evaluation order, built by the host: pair i is head pair_hd[i] of source pair_src[i];
     // goff[s] = first pair of source s
@@ -429,6 +431,10 @@ __device__ __forceinline__ void critic_head_body(const CriticHeadParams& p, int 
         for (int i = 0; i < P; ++i) {
             T[i] = p.reward_scale * r + nd * st[i];
             mean_sq += sq[i]; mean_T += T[i];
+        }
+        if (p.std_soft_update) {      // :210-219: keep the current spread, move the mean (never together with counts, :97)
+            const float msq = mean_sq / (float)P, mT = mean_T / (float)P;
+            for (int i = 0; i < P; ++i) T[i] = p.std_soft_prob * T[i] + (1.f - p.std_soft_prob) * (sq[i] - msq + mT);
         }
         if (p.counts) {      // :220-224
             mean_sq /= (float)P; mean_T /= (float)P;

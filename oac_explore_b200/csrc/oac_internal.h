@@ -75,7 +75,7 @@ struct GemmTask {
     int train_bias;           // 0: bias frozen
     int tiles_m, tiles_n;     // filled by the builder for the chosen tile shape
     int bn;                   // warp-specialised tcgen05 path: this task's tile width
-    int tile0;                // ... and its first tile in the per-seed work list
+    int tile0;                // ... and its first tile in the per-seed work list 
 };
 
 struct AdamHyper {

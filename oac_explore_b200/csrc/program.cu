@@ -19,12 +19,12 @@
 #include <cstring>
 
 #include "glue.cuh"
+#include "glue_many.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
 #include "gemm_fwd2.cuh"
 #include "adam_stream.cuh"
 #include "stats.cuh"
-#include "mega.cuh"
 #include "oac_error.h"
 
 namespace oac {
@@ -71,6 +71,8 @@ static int validate(const OacConfig& c) {
     if (c.algo == OAC_ALGO_POAC && (c.n_particles < 2 || c.n_particles > 16))
         return set_error(OAC_E_UNSUPPORTED, "P-OAC needs 2 <= n_particles <= 16");
     if (c.algo < 0 || c.algo > OAC_ALGO_GOAC) return set_error(OAC_E_INVALID, "unknown algo");
+    if (c.std_soft_update && (c.algo != OAC_ALGO_POAC || c.counts))
+        return set_error(OAC_E_INVALID, "std_soft_update is a P-OAC option and excludes counts (particle_trainer_oac.py:97)");
     return 0;
 }
 
@@ -123,7 +125,7 @@ static int build_layout(const OacConfig& c, OacLayout& L, NetIds& ids) {
 // ------------------------------------------------------------------------------------
 // program
 // ------------------------------------------------------------------------------------
-enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3, ST_ADAM = 4, ST_STEP_TAIL = 5 };
+enum StageKind { ST_GEMM = 0, ST_POLICY_HEAD = 1, ST_CRITIC_HEAD = 2, ST_POLICY_GRAD = 3, ST_ADAM = 4, ST_STEP_TAIL = 5, ST_RANK1 = 6 };
 
 struct Stage {
     int kind;
@@ -134,6 +136,8 @@ struct Stage {
     std::vector<PolicyGradTask> pg;
     PolicyGradParams pgp;
     AdamStreamParams asp;       // ST_ADAM
+    std::vector<Rank1Task> r1;  // ST_RANK1
+    int many = 0;               // glue stage runs its many-seed specialisation (glue_many.cuh)
     // launch
     void* dev = nullptr;        // task table / params on the device
     int a_trans = 0, b_trans = 0;   // all tasks of a GEMM stage share the operand layouts
@@ -171,13 +175,6 @@ struct OacTrainer {
     std::vector<void*> dev_allocs;
     long long work_cursor = 0;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
-    // single-launch step (mega.cuh)
-    void* mega_prog = nullptr;              // device MegaProgram
-    int mega_grid = 0, mega_phases = 0;
-    unsigned long long* mega_dbg = nullptr;
-    std::vector<std::string> mega_names;
-    int mega_dbg_calls = 0;
-    size_t mega_smem = 0;
     cudaStream_t side[2] = {nullptr, nullptr};            // lanes 1, 2
     cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     bool use_graph = true;
@@ -188,7 +185,6 @@ struct OacTrainer {
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
     bool allow_sk_tma = true;  // OAC_NO_SK_TMA=1: cp.async staging in the latency-regime FFMA tile
-    bool allow_mega = false;   // OAC_MEGA=1: the whole latency-regime step as one cooperative kernel (mega.cuh; measured slower)
 };
 
 namespace oac {
@@ -365,6 +361,18 @@ struct Builder {
         dx(s, Ref{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)}, pad4(n.n_out), B, n.n_out, P(n.off_w2), H, H,
            Ref{a.dh2.arena, a.dh2.off + ro}, H, Ref{a.h2.arena, a.h2.off + ro}, H, true);
     }
+    // the same product as an elementwise pass (many-seed regime: K = n_heads is no GEMM)
+    void crit_dh2_rank1(Stage& s, int ni, const CritAct& a, int row0) {
+        const OacNetLayout& n = net(ni);
+        long long ro = (long long)row0 * H;
+        Rank1Task r; memset(&r, 0, sizeof(r));
+        r.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)}; r.dq_ld = pad4(n.n_out);
+        r.w3 = P(n.off_w2); r.n_heads = n.n_out;
+        r.mask = Ref{a.h2.arena, a.h2.off + ro}; r.ldmask = H;
+        r.out = Ref{a.dh2.arena, a.dh2.off + ro}; r.ldo = H;
+        r.rows = B; r.cols = H;
+        s.r1.push_back(r);
+    }
     void crit_dh1(Stage& s, int ni, const CritAct& a, int row0) {
         const OacNetLayout& n = net(ni);
         long long ro = (long long)row0 * H;
@@ -462,6 +470,7 @@ struct Builder {
         p.share_layers = c.share_layers; p.counts = c.counts;
         p.discount = c.discount; p.reward_scale = c.reward_scale;
         p.standard_bound = c.standard_bound; p.std_init = c.std_init;
+        p.std_soft_update = c.std_soft_update; p.std_soft_prob = c.std_soft_update_prob;
     }
     void fill_pgp(Stage& s) {
         PolicyGradParams& p = s.pgp;
@@ -481,14 +490,14 @@ struct Builder {
     // the policy_head kernel just added (fence + ticket + reduction in its last CTA) for a one-CTA kernel on lane 2
     // (measured per step: SAC 123.6 -> 119.4 us, P-OAC 129.6 -> 127.0, G-OAC 131.0 -> 128.9).
     void split_step_tail() {
-        if (!latency_lanes() || t.allow_mega || getenv("OAC_NO_TAIL_SPLIT")) return;                                      // (env: A/B measurement aid)
+        if (!latency_lanes() || getenv("OAC_NO_TAIL_SPLIT")) return;                                      // (env: A/B measurement aid)
         t.stages.back().php.tail_in_own_kernel = 1;
         Stage head = t.stages.back();
         Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = head.ph; s.php = head.php;
     }
     // two dependent forward layers as one cluster launch (gemm_fwd2.cuh): the FFMA latency regime only
     bool fuse_fwd2() const {
-        return latency_lanes() && c.gemm_path == OAC_GEMM_FP32 && !t.allow_mega && !getenv("OAC_NO_FWD2");               // (env: A/B measurement aid)
+        return latency_lanes() && c.gemm_path == OAC_GEMM_FP32 && !getenv("OAC_NO_FWD2");               // (env: A/B measurement aid)
     }
     void build_sac();
     void build_poac();
@@ -582,7 +591,9 @@ void Builder::build_sac() {
     flush_adam("critic_adam_apply");
     }
     if (!mode_b) {
-        if (!two_lanes) { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
+        if (!two_lanes && tensor_glue && (H & 3) == 0) {
+            Stage& s = add_stage(ST_RANK1, "pi_dh2"); crit_dh2_rank1(s, q1, ca1, 0); crit_dh2_rank1(s, q2, ca2, 0);
+        } else if (!two_lanes) { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
         { Stage& s = add_stage(ST_GEMM, "pi_dh1"); s.join = 2; crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
         policy_grad_stage();
     }
@@ -1024,6 +1035,7 @@ static int finalize(OacTrainer& t) {
             s.max_rows = 0;
             for (auto& p : s.ph) s.max_rows = std::max(s.max_rows, p.rows);
             glue_plan(s, (long long)s.max_rows * s.ph.size() * seeds, !s.php.head_from_gemm);
+            s.many = s.php.head_from_gemm && s.glue_g == 1 && !getenv("OAC_NO_GLUE_MANY");      // (env: A/B measurement aid)
             if (int e = upload(t, s.ph.data(), s.ph.size(), &s.dev)) return e;
             s.php.tasks = (const PolicyHeadTask*)s.dev;
             s.php.as = t.as; s.php.hyper = t.hyper;
@@ -1046,12 +1058,21 @@ static int finalize(OacTrainer& t) {
                 s.chp.n_pairs = n;
             }
             s.chp.as = t.as;
+            {
+                bool ok = s.chp.mode == CM_SAC && t.cfg.hidden == 256 && s.glue_g == 1 && s.chp.n_src == 6 && !getenv("OAC_NO_GLUE_MANY");
+                for (int i = 0; i < s.chp.n_src && ok; ++i) ok = s.chp.src[i].n_heads == 1;
+                for (int a = 0; a < AR_COUNT && ok; ++a) ok = (t.as.stride[a] & 3) == 0 && al16(t.as.base[a]);
+                s.many = ok;
+            }
             if (int e = upload(t, &s.chp, 1, &s.dev)) return e;
+        } else if (s.kind == ST_RANK1) {
+            if (int e = upload(t, s.r1.data(), s.r1.size(), &s.dev)) return e;
         } else if (s.kind == ST_ADAM) {
             s.asp.as = t.as; s.asp.hyper = t.hyper;
             if (int e = upload(t, &s.asp, 1, &s.dev)) return e;
         } else if (s.kind == ST_POLICY_GRAD) {
             glue_plan(s, (long long)t.cfg.batch * s.pg.size() * seeds, !s.pgp.da_from_gemm);
+            s.many = s.pgp.da_from_gemm && s.glue_g == 1 && !getenv("OAC_NO_GLUE_MANY");
             if (int e = upload(t, s.pg.data(), s.pg.size(), &s.dev)) return e;
             s.pgp.tasks = (const PolicyGradTask*)s.dev;
             s.pgp.as = t.as;
@@ -1200,6 +1221,22 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                         break;
                 default: break;
             }
+        } else if (s.kind == ST_RANK1) {
+            int cells = 0;
+            for (auto& r : s.r1) cells = std::max(cells, ((r.rows + RANK1_ROWS - 1) / RANK1_ROWS) * (r.cols >> 2));
+            dim3 grid((cells + RANK1_THREADS - 1) / RANK1_THREADS, (unsigned)s.r1.size(), seeds);
+            launch_pdl(rank1_mask_kernel, grid, dim3(RANK1_THREADS), 0, st, (const Rank1Task*)s.dev, t.as);
+        } else if (s.kind == ST_POLICY_HEAD && s.many) {
+            PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps; p.iters = 1;
+            dim3 grid((s.max_rows + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.ph.size(), seeds);
+            launch_pdl(policy_head_many_kernel, grid, dim3(GLUE_THREADS), 0, st, p, use_external_eps);
+        } else if (s.kind == ST_CRITIC_HEAD && s.many) {
+            dim3 grid((t.cfg.batch + GLUE_WARPS - 1) / GLUE_WARPS, seeds, 1);
+            launch_pdl(critic_head_sac256_kernel, grid, dim3(GLUE_THREADS), 0, st, (const CriticHeadParams*)s.dev);
+        } else if (s.kind == ST_POLICY_GRAD && s.many) {
+            PolicyGradParams p = s.pgp; p.iters = 1; p.wa_sources = 1;
+            dim3 grid((t.cfg.batch + GLUE_WARPS - 1) / GLUE_WARPS, (unsigned)s.pg.size(), seeds);
+            launch_pdl(policy_grad_many_kernel, grid, dim3(GLUE_THREADS), 0, st, p);
         } else if (s.kind == ST_POLICY_HEAD) {
             PolicyHeadParams p = s.php; p.use_external_eps = use_external_eps; p.iters = s.glue_iters;
             const int spc = GLUE_WARPS / s.glue_g, per_cta = spc * s.glue_iters;
@@ -1227,128 +1264,6 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             else launch_pdl(policy_grad_kernel<4>, grid, dim3(GLUE_THREADS), smem, st, p);
         }
         OAC_CUDA(cudaGetLastError());
-    }
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------
-// single-launch step: phases, device program, cooperative grid size
-// ------------------------------------------------------------------------------------
-static int mega_plan(OacTrainer& t) {
-    const int seeds = t.cfg.n_seeds;
-    if (!t.allow_mega || t.cfg.gemm_path != OAC_GEMM_FP32 || (long long)seeds * t.cfg.batch > 1024) return 0;
-    for (const Stage& s : t.stages) {
-        if (s.kind == ST_GEMM) { if (s.use_tc || s.use_ws || (s.a_trans && !s.b_trans)) return 0; }
-        else if (s.kind == ST_ADAM) return 0;
-        else if (s.glue_g != 4 || s.glue_iters != 1) return 0;
-    }
-    MegaProgram mp;
-    memset(&mp, 0, sizeof(mp));
-    size_t smem = 0;
-    std::vector<const Stage*> pending;                  // lane-1 stages waiting for a critical-chain stage to share a phase with
-    auto add_to = [&](MegaPhase& P, const Stage& s) -> int {
-        MegaStage& m = P.st[P.n++];
-        const int spc = GLUE_WARPS / s.glue_g;
-        if (s.kind == ST_GEMM) {
-            m.kind = s.a_trans ? MK_GEMM_TT : (s.b_trans ? MK_GEMM_NT : MK_GEMM_NN);
-            m.gx = s.max_tiles; m.gy = (int)s.gemm.size(); m.gz = seeds;
-            StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc; sp.tmaps = nullptr;
-            void* d = nullptr;
-            if (int e = upload(t, &sp, 1, &d)) return e;
-            m.params = d;
-            smem = std::max(smem, s.smem);
-        } else if (s.kind == ST_POLICY_HEAD) {
-            m.kind = MK_POLICY_HEAD;
-            m.gx = (s.max_rows + spc - 1) / spc; m.gy = (int)s.ph.size(); m.gz = seeds;
-            PolicyHeadParams p = s.php; p.iters = 1; p.use_external_eps = 0;
-            void* d = nullptr;
-            if (int e = upload(t, &p, 1, &d)) return e;
-            m.params = d;
-            smem = std::max(smem, glue_smem(t, s));
-        } else if (s.kind == ST_CRITIC_HEAD) {
-            m.kind = MK_CRITIC_HEAD;
-            m.gx = (t.cfg.batch + spc - 1) / spc; m.gy = seeds; m.gz = 1;
-            m.params = s.dev;
-        } else {
-            m.kind = MK_POLICY_GRAD;
-            m.gx = (t.cfg.batch + spc - 1) / spc; m.gy = (int)s.pg.size(); m.gz = seeds;
-            PolicyGradParams p = s.pgp; p.iters = 1; p.wa_sources = pg_wa_sources(t, s);
-            void* d = nullptr;
-            if (int e = upload(t, &p, 1, &d)) return e;
-            m.params = d;
-            smem = std::max(smem, glue_smem(t, s));
-        }
-        m.nvb = m.gx * m.gy * m.gz;
-        P.total_vb += m.nvb;
-        return 0;
-    };
-    auto new_phase = [&]() -> MegaPhase* { return mp.n_phases < MEGA_MAX_PHASES ? &mp.ph[mp.n_phases++] : nullptr; };
-    auto flush_pending = [&]() -> int {                 // a join: what is still pending runs as phases of its own, in order
-        for (const Stage* ps : pending) {
-            MegaPhase* P = new_phase();
-            if (!P) return -1;
-            if (int e = add_to(*P, *ps)) return e;
-        }
-        pending.clear();
-        return 0;
-    };
-    for (const Stage& s : t.stages) {
-        if (s.lane >= 1) { pending.push_back(&s); continue; }
-        if (s.join) { if (flush_pending()) return 0; }
-        MegaPhase* P = new_phase();
-        if (!P) return 0;
-        if (int e = add_to(*P, s)) return e;
-        if (!pending.empty()) {                         // the oldest independent stage shares this phase
-            const Stage* ps = pending.front();
-            pending.erase(pending.begin());
-            if (int e = add_to(*P, *ps)) return e;
-        }
-    }
-    if (flush_pending()) return 0;
-    // persistent grid: every CTA resident at once (cooperative launch), 2 per SM when registers / shared memory allow
-    cudaError_t ce = cudaFuncSetAttribute((const void*)step_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_mega_kernel, MEGA_THREADS, smem);
-    int dev = 0, coop = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (ce != cudaSuccess || per_sm < 1 || !coop) { cudaGetLastError(); return 0; }
-    unsigned* bar = nullptr;
-    OAC_CUDA(cudaMalloc(&bar, sizeof(unsigned)));
-    t.dev_allocs.push_back(bar);
-    OAC_CUDA(cudaMemset(bar, 0, sizeof(unsigned)));
-    mp.barrier = bar;
-    if (getenv("OAC_MEGA_DEBUG") && getenv("OAC_MEGA_DEBUG")[0] == '1') {
-        OAC_CUDA(cudaMalloc(&mp.dbg, sizeof(unsigned long long) * (2 * MEGA_MAX_PHASES + 1)));
-        t.dev_allocs.push_back(mp.dbg);
-        t.mega_dbg = mp.dbg;
-        int i = 0;
-        for (int ph = 0; ph < mp.n_phases; ++ph) {
-            std::string nm;
-            for (int k = 0; k < mp.ph[ph].n; ++k) nm += std::string(k ? " | " : "") + std::to_string(mp.ph[ph].st[k].nvb) + " vb kind " + std::to_string(mp.ph[ph].st[k].kind);
-            t.mega_names.push_back(nm);
-            ++i;
-        }
-    }
-    if (int e = upload(t, &mp, 1, &t.mega_prog)) return e;
-    t.mega_grid = std::min(per_sm, 2) * sm_count();
-    t.mega_phases = mp.n_phases;
-    t.mega_smem = smem;
-    return 0;
-}
-
-static int launch_mega(OacTrainer& t, int use_external_eps, cudaStream_t st) {
-    const MegaProgram* prog = (const MegaProgram*)t.mega_prog;
-    void* args[2] = {(void*)&prog, (void*)&use_external_eps};
-    OAC_CUDA(cudaLaunchCooperativeKernel((const void*)step_mega_kernel, dim3(t.mega_grid), dim3(MEGA_THREADS), args, t.mega_smem, st));
-    if (t.mega_dbg && ++t.mega_dbg_calls == 200) {           // measurement aid: one warm step, phase by phase
-        cudaStreamSynchronize(st);
-        std::vector<unsigned long long> h(2 * MEGA_MAX_PHASES + 1);
-        cudaMemcpy(h.data(), t.mega_dbg, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
-        for (int ph = 0; ph < t.mega_phases; ++ph)
-            fprintf(stderr, "[mega] phase %2d: work %6.2f us, barrier wait %6.2f us   (%s)\n", ph, (h[2 * ph + 1] - h[2 * ph]) * 1e-3,
-                    (h[2 * ph + 2] - h[2 * ph + 1]) * 1e-3, t.mega_names[ph].c_str());
-        fprintf(stderr, "[mega] total %.2f us, grid %d, smem %zu\n", (h[2 * t.mega_phases] - h[0]) * 1e-3, t.mega_grid, t.mega_smem);
     }
     return 0;
 }
@@ -1386,8 +1301,6 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
     { const char* nk = getenv("OAC_NO_SK_TMA"); t->allow_sk_tma = !(nk && nk[0] == '1'); }
-    { const char* nm = getenv("OAC_MEGA"); t->allow_mega = (nm && nm[0] == '1'); }      // measured slower than the graph: opt-in
-    if (t->allow_mega) t->allow_sk_tma = false;       // the single-launch kernel runs the cp.async staging of the stage bodies
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
     else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
@@ -1451,7 +1364,6 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         fe = finalize(*t);
     }
     if (fe) { oac_trainer_destroy(t); return fe; }
-    if (int e = mega_plan(*t)) { oac_trainer_destroy(t); return e; }
     { const char* np_ = getenv("OAC_PDL"); g_use_pdl = (np_ && np_[0] == '1'); }
     const char* ng = getenv("OAC_NO_GRAPH");
     t->use_graph = !(ng && ng[0] == '1');
@@ -1484,7 +1396,6 @@ extern "C" int oac_trainer_destroy(OacTrainer* t) {
 
 extern "C" int oac_trainer_launches_per_step(const OacTrainer* t) {
     if (!t) return 0;
-    if (t->mega_prog) return 1;
     int n = 0;
     for (const Stage& s : t->stages) n += (s.fused2 && !s.fwd2_cluster) ? 2 : 1;      // a fused layer pair without its cluster: two launches
     return n;
@@ -1522,7 +1433,6 @@ extern "C" int oac_trainer_step(OacTrainer* t, int32_t use_external_eps, void* s
     if (!t) return set_error(OAC_E_INVALID, "null trainer");
     cudaStream_t st = (cudaStream_t)stream;
     const int gi = use_external_eps ? 1 : 0;
-    if (t->mega_prog) return launch_mega(*t, gi, st);          // the whole step is one cooperative kernel
     if (!t->use_graph) return launch_stages(*t, gi, st);
     if (!t->graph[gi]) {
         // capture on a private stream so the caller's stream state is untouched

@@ -20,7 +20,8 @@ def make_config(algo, obs_dim, act_dim, hidden, batch, n_seeds=1, n_particles=0,
                 deterministic=False, auto_alpha=True, counts=False, train_bias=True, stale_graph_mode="A",
                 target_update_period=1, gemm_path=_lib.GEMM_FP32, discount=0.99, reward_scale=1.0,
                 soft_target_tau=1e-2, policy_lr=1e-3, qf_lr=1e-3, std_lr=3e-5, target_entropy=None,
-                standard_bound=0.0, std_init=0.0, betas=(0.9, 0.999), adam_eps=1e-8, rng_seed=0):
+                standard_bound=0.0, std_init=0.0, betas=(0.9, 0.999), adam_eps=1e-8, rng_seed=0,
+                std_soft_update=False, std_soft_update_prob=0.0):
     c = OacConfig()
     c.algo, c.obs_dim, c.act_dim, c.hidden, c.batch, c.n_seeds = algo, obs_dim, act_dim, hidden, batch, n_seeds
     c.n_particles, c.share_layers, c.deterministic = n_particles, int(share_layers), int(deterministic)
@@ -33,6 +34,7 @@ def make_config(algo, obs_dim, act_dim, hidden, batch, n_seeds=1, n_particles=0,
     c.standard_bound, c.std_init = standard_bound, std_init
     c.adam_beta1, c.adam_beta2, c.adam_eps = betas[0], betas[1], adam_eps
     c.rng_seed = rng_seed
+    c.std_soft_update, c.std_soft_update_prob = int(bool(std_soft_update)), float(std_soft_update_prob)
     return c
 
 

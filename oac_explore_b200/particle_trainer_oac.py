@@ -28,10 +28,11 @@ class ParticleTrainer(_EngineTrainer):
         self.gemm_path = gemm_path
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("the fused step implements torch.optim.Adam")
-        if ensemble or global_opt or std_soft_update or mean_update or mellow_max:
-            raise NotImplementedError("ensemble / global_opt / std_soft_update / mean_update variants are "
+        if ensemble or global_opt or mean_update or mellow_max:
+            raise NotImplementedError("ensemble / global_opt / mean_update variants are "
                                       "outside the P-OAC hot path (SURVEY.md section 8f rank 4)")
         assert not counts or not std_soft_update                     # :97
+        self.std_soft_update, self.std_soft_update_prob = std_soft_update, std_soft_update_prob
         self.use_automatic_entropy_tuning = use_automatic_entropy_tuning
         self.target_entropy = None
         if use_automatic_entropy_tuning:
@@ -82,7 +83,8 @@ class ParticleTrainer(_EngineTrainer):
                     target_update_period=self.target_update_period, discount=self.discount,
                     reward_scale=self.reward_scale, soft_target_tau=self.soft_target_tau,
                     policy_lr=self.policy_lr, qf_lr=self.qf_lr, target_entropy=self.target_entropy,
-                    rng_seed=self._rng_seed, gemm_path=self.gemm_path)
+                    rng_seed=self._rng_seed, gemm_path=self.gemm_path, std_soft_update=self.std_soft_update,
+                    std_soft_update_prob=self.std_soft_update_prob)
 
     def _net_objects(self):
         # layout order: policy, qf[0..n), log_alpha | tf[0..n)

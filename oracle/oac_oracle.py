@@ -54,9 +54,8 @@ TANH_EPS = 1e-6     # trainer/policies.py:127
 #   "trunk" : few seeds (< 2048 batch rows per launch).  Head layers (critic AND policy) are exact in the forward and in
 #             their input gradient, and so is the action-column product dh1 W0[:, O:O+A] of the policy loss; a head's
 #             WEIGHT gradient is a GEMM stage.
-#   "many"  : many seeds (the batched-seed program).  The policy head, its backward, dQ/da and -- SAC mode A -- the
-#             policy-loss product dq W3 are GEMM stages too; the critic head's forward and its Q-loss input gradient stay
-#             in the critic_head glue kernel (exact).
+#   "many"  : many seeds (the batched-seed program).  The policy head, its backward and dQ/da are GEMM stages too; the
+#             critic head's forward and its input gradients (dq W3: critic_head / rank1_mask kernels) stay exact fp32.
 #   "all"   : every Linear rounded (the idealised model; no kernel regime is exactly this).
 _TF32 = {"mode": None}
 
@@ -520,8 +519,9 @@ class ParticleState(object):
                  policy_lr=3e-4, qf_lr=3e-4, discount=0.99, reward_scale=1.0, soft_target_tau=5e-3,
                  target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None,
                  delta=0.95, q_min=0.0, q_max=100.0, counts=False, deterministic=False,
-                 dtype=torch.float32):
+                 dtype=torch.float32, std_soft_update=False, std_soft_update_prob=0.0):
         self.obs_dim, self.act_dim = obs_dim, act_dim
+        self.std_soft_update, self.std_soft_update_prob = std_soft_update, std_soft_update_prob
         self.policy = init_policy(obs_dim, act_dim, hidden)
         q_out = n_estimators if share_layers else 1
         for _ in range(4):  # the SAC twin nets, created and dropped (trainer/trainer.py:68-71)
@@ -582,6 +582,10 @@ def poac_step(st, batch, eps_next, eps_pi):
         tqs = _particles(st.tfs, next_obs, a_next, st.share_layers)
         tq_sorted, _ = torch.sort(tqs, dim=0)                       # :202
         q_target = st.reward_scale * rewards + (1. - terminals) * st.discount * tq_sorted  # :207-208
+        if st.std_soft_update:                                      # :210-219
+            cur = sorted_qs.detach()
+            q_target = st.std_soft_update_prob * q_target + \
+                (1 - st.std_soft_update_prob) * (cur - cur.mean(dim=0) + q_target.mean(dim=0))
         if st.counts:                                               # :220-224
             factor = (batch['counts'] == 0).to(obs.dtype)
             sq = sorted_qs.detach()

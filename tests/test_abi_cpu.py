@@ -32,7 +32,7 @@ def test_ctypes_structs_match_header_sizes():
     from oac_explore_b200 import _lib
     # field-by-field mirrors of the C structs (natural alignment on both sides)
     assert C.sizeof(_lib.OacNetLayout) == 6 * 4 + 7 * 8
-    assert C.sizeof(_lib.OacConfig) == 16 * 4 + 12 * 4 + 8
+    assert C.sizeof(_lib.OacConfig) == 16 * 4 + 14 * 4 + 8
     assert C.sizeof(_lib.OacBuffers) == 7 * 8
     # OacExploreArgs: policy*, layout, q[48], layout, 8 x 32-bit (n_q .. n_obs), obs*, eps*, 2 u64, 3 out*, obs_group*, group_stride
     lay = C.sizeof(_lib.OacNetLayout)

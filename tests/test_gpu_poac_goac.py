@@ -131,3 +131,34 @@ def test_goac_humanoid_vs_oracle(share, counts):
         ours = net_cpu(getattr(tr, n))
         for k, v in getattr(st, n).items():
             close(ours[k], v, (n, k), atol=6e-6 if 'policy' in n else 1e-4)
+
+
+@pytest.mark.parametrize("share", [True, False])
+def test_poac_std_soft_update_vs_oracle(share):
+    """std_soft_update (trainer/particle_trainer_oac.py:210-219): the oracle's restatement is pinned on the
+    live reference (tests/test_oracle_vs_reference.py::test_poac_std_soft_update); here the CUDA step against it."""
+    from oac_explore_b200.particle_trainer_oac import ParticleTrainer
+    O, A, B, H, P = 376, 17, 256, 256, 10
+    pp, qp = producers(O, A, H, q_out=P if share else 1)
+    torch.manual_seed(6)
+    tr = ParticleTrainer(pp, qp, n_estimators=P, action_space=Box(A), share_layers=share, deterministic=False,
+                         use_automatic_entropy_tuning=True, std_soft_update=True, std_soft_update_prob=0.3, **KW)
+    torch.manual_seed(6)
+    st = orc.ParticleState(O, A, n_estimators=P, share_layers=share, q_min=0., q_max=500., policy_lr=3e-4, qf_lr=3e-4,
+                           soft_target_tau=5e-3, std_soft_update=True, std_soft_update_prob=0.3)
+    for s in range(3):
+        batch = synth_batch(B, O, A, seed=40 + s)
+        eps = synth_eps(2, B, A, seed=400 + s)
+        o = None
+        o = orc.poac_step(st, batch, eps[0], eps[1])
+        tr.inject_noise(eps_obs=eps[1], eps_next=eps[0])
+        tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
+        e = tr._engine
+        assert rel_err(e.io_view(e.lay.off_q_target, (B, P)).cpu().t(), o['q_target'][:, :, 0]) <= 1e-5
+    for i in range(len(st.qfs)):
+        ours = net_cpu(tr.qfs[i])
+        for k, v in st.qfs[i].items():
+            close(ours[k], v, ('qf', i, k), atol=6e-5)          # head biases ~500: 1e-7 relative
+    ours = net_cpu(tr.policy)
+    for k, v in st.policy.items():
+        close(ours[k], v, ('policy', k))

@@ -239,30 +239,6 @@ def test_snapshot_roundtrip_and_batch_resize():
             assert rel_err(ours[k], v) <= 1e-5 or max_abs(ours[k], v) <= 6e-6
 
 
-def test_single_launch_step_matches_graph(monkeypatch):
-    """OAC_MEGA=1 runs the whole step as one cooperative kernel (mega.cuh) that calls the same stage bodies between grid
-    barriers: weights after three steps must equal the CUDA-graph path bit for bit."""
-    O, A, B, H = 376, 17, 256, 256
-    trainers = []
-    for mega in ("0", "1"):
-        monkeypatch.setenv("OAC_MEGA", mega)
-        torch.manual_seed(5)
-        trainers.append(make_trainer(O, A, H))
-    monkeypatch.delenv("OAC_MEGA")
-    assert trainers[0]._engine.launches_per_step > 1 and trainers[1]._engine.launches_per_step == 1
-    for step in range(3):
-        batch = synth_batch(B, O, A, seed=40 + step)
-        eps = synth_eps(2, B, A, seed=400 + step)
-        for tr in trainers:
-            tr.inject_noise(eps[0], eps[1])
-            tr.train_from_torch({k: v.cuda() for k, v in batch.items()})
-    torch.cuda.synchronize()
-    for n in NETS:
-        a, b = net_cpu(getattr(trainers[0], n)), net_cpu(getattr(trainers[1], n))
-        for k in a:
-            assert torch.equal(a[k], b[k]), (n, k)
-
-
 @pytest.mark.parametrize("H", [256, 320])
 def test_fused_forward_layers_match_separate_launches(monkeypatch, H):
     """gemm_fwd2_kernel runs layer 1 and layer 2 of every 32-row strip in one thread-block cluster with the arithmetic of the

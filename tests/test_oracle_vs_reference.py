@@ -124,6 +124,33 @@ def test_poac_step(share_layers, counts):
 
 
 @pytest.mark.parametrize("share_layers", [True, False])
+def test_poac_std_soft_update(share_layers):
+    """trainer/particle_trainer_oac.py:210-219: targets keep the current particle spread and move the mean."""
+    O, A, B, P = 23, 5, 64, 6
+    ref = ri.load_reference()
+    _, ac_space = ri.make_spaces(O, A)
+    pp, qp = ri.make_producers(O, A, q_out=P if share_layers else 1)
+    kw = dict(policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3, use_automatic_entropy_tuning=True,
+              delta=0.95, q_min=0.0, q_max=500.0, std_soft_update=True, std_soft_update_prob=0.3)
+    torch.manual_seed(1)
+    tr = ref.particle_trainer_oac.ParticleTrainer(pp, qp, n_estimators=P, action_space=ac_space,
+                                                  share_layers=share_layers, deterministic=False, **kw)
+    ri.mode_a(tr)
+    torch.manual_seed(1)
+    st = orc.ParticleState(O, A, n_estimators=P, share_layers=share_layers, **kw)
+    for s in range(4):
+        batch = synth_batch(B, O, A, seed=20 + s)
+        eps = synth_eps(2, B, A, seed=200 + s)
+        with ri.injected_noise(eps):
+            tr.train_from_torch(dict(batch))
+        orc.poac_step(st, batch, eps[0], eps[1])
+    _cmp_net(st.policy, tr.policy, 2e-6, "policy")
+    for i in range(len(st.qfs)):
+        _cmp_net(st.qfs[i], tr.qfs[i], 5e-5, "qf%d" % i)
+        _cmp_net(st.tfs[i], tr.tfs[i], 5e-5, "tf%d" % i)
+
+
+@pytest.mark.parametrize("share_layers", [True, False])
 @pytest.mark.parametrize("counts", [False, True])
 def test_goac_step(share_layers, counts):
     O, A, B = 23, 5, 64

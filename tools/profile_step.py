@@ -28,7 +28,7 @@ import bench
 from oac_explore_b200.replay_buffer import ReplayBuffer
 
 bench.N_REPLAY = args.replay
-bench.GEMM_PATH = bench.GEMM_PATHS[args.gemm_path]
+GP = bench.GEMM_PATHS[args.gemm_path]
 dev = torch.device("cuda", 0)
 rb = ReplayBuffer(args.replay, bench.Box(bench.O), bench.Box(bench.A))
 g = torch.Generator(device=dev).manual_seed(0)
@@ -39,12 +39,12 @@ np.random.seed(0)
 S = args.seeds
 idx = torch.from_numpy(np.random.randint(0, args.replay, (args.steps, S, bench.B))).to(dev)
 if S == 1:
-    tr = bench.build_trainer(args.algo, 0)
+    tr = bench.build_trainer(args.algo, 0, GP)
     rb.attach(tr)
     engine = tr._engine
 else:
     from oac_explore_b200.seed_group import SACSeedGroup
-    grp = SACSeedGroup(list(range(S)), bench.O, bench.A, hidden=bench.H, batch=bench.B, gemm_path=bench.GEMM_PATH, **bench.HP)
+    grp = SACSeedGroup(list(range(S)), bench.O, bench.A, hidden=bench.H, batch=bench.B, gemm_path=GP, **bench.HP)
     engine = grp.engine
 torch.cuda.synchronize()
 for i in range(args.steps):
