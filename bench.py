@@ -425,6 +425,35 @@ def variants_brief(rb, dev, steps=20, warm=5):
     out["explore"] = {"workload": "get_optimistic_exploration_action (twin-Q, beta_UB=4.66, delta=23.53), host observation in -> "
                                   "host action out, wall clock per call", "calls": steps, **ex}
     rb.attach(None)
+    del w
+    # per-seed batched exploration: ONE launch serves the current observation of every seed of a 64-seed group
+    # with that seed's own policy and critics; host observations in -> host actions out
+    from oac_explore_b200.seed_group import SACSeedGroup
+    S = 64
+    grp = SACSeedGroup(list(range(S)), O, A, hidden=H, batch=B, gemm_path=GEMM_PATHS["tf32"], **HP)
+    exg = grp.explorer(hp)
+    obs = rng.randn(S, O)
+    for _ in range(5):
+        exg.actions(obs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        exg.actions(obs)
+    dt = (time.perf_counter() - t0) / steps
+    # double buffered: the second half of the environments is submitted before the first half is collected
+    half = S // 2
+    sl = np.arange(S)
+    for _ in range(3):
+        a_ = exg.submit(obs[:half], slots=sl[:half]); b_ = exg.submit(obs[half:], slots=sl[half:]); exg.collect(a_); exg.collect(b_)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        a_ = exg.submit(obs[:half], slots=sl[:half]); b_ = exg.submit(obs[half:], slots=sl[half:]); exg.collect(a_); exg.collect(b_)
+    dt2 = (time.perf_counter() - t0) / steps
+    out["explore_group"] = {"workload": "GroupExplorer: one oac_explore launch for the 64 seeds of a SACSeedGroup, every observation "
+                                        "evaluated with its own seed's policy and critics (path_collector.py:214-232 vectorised over seeds)",
+                            "seeds": S, "us_per_call": dt * 1e6, "actions_per_s": S / dt,
+                            "double_buffered_us_per_64": dt2 * 1e6, "calls": steps}
+    del grp, exg
+    torch.cuda.empty_cache()
     return out
 
 

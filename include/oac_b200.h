@@ -220,7 +220,8 @@ int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_stages, float*
 int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_trans, int32_t M, int32_t N, int32_t K,
                    const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
                    const float* bias, int32_t relu, void* stream);
-/* Which kernel the last oac_gemm_debug call ran: 0 SIMT, 1 per-tile tcgen05, 2 warp-specialised TMA + tcgen05. */
+/* Which kernel the last oac_gemm_debug call ran: 0 SIMT, 1 per-tile tcgen05, 2 warp-specialised TMA + tcgen05,
+ * 3 its CTA-pair variant (tcgen05.mma.cta_group::2). */
 int oac_gemm_debug_kernel(void);
 
 /* ---- inference ---- */

@@ -22,6 +22,7 @@
 #include "glue_many.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
+#include "gemm_ws2.cuh"
 #include "gemm_fwd2.cuh"
 #include "adam_stream.cuh"
 #include "stats.cuh"
@@ -146,6 +147,7 @@ struct Stage {
     int use_tc = 0, bn = 0, tmem_cols = 0, n_main = 1;     // tcgen05 path
     // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
     int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
+    int ws_pair = 0;            // CTA-pair kernel (gemm_ws2.cuh: tcgen05.mma.cta_group::2, 256-row tiles)
     int sk_tma = 0;             // latency-regime FFMA tile with TMA-staged operands (tensor maps in ws_tmaps)
     int fused2 = 0;             // tasks are [layer-1 ..., layer-2 ...] pairs of two dependent forward layers: one cluster launch
     int fwd2_cluster = 0;       // (gemm_fwd2.cuh) when the plan allows it, else two plain launches
@@ -182,6 +184,7 @@ struct OacTrainer {
     long long* tc_dbg = nullptr;
     float* host_scalars = nullptr;   // OacBuffers::host_scalars
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
+    bool allow_ws2 = true;     // OAC_NO_WS2=1: single-CTA tiles only, no CTA pairs (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
     bool allow_sk_tma = true;  // OAC_NO_SK_TMA=1: cp.async staging in the latency-regime FFMA tile
@@ -786,18 +789,43 @@ static bool ws_eligible(const OacTrainer& t, const Stage& s) {
     return tensor_map_encoder() != nullptr;
 }
 
+// L2 promotion of the operand maps (measurement aid: OAC_WS_L2PROMO=64|128|256, default 128)
+static CUtensorMapL2promotion ws_l2_promotion() {
+    const char* e = getenv("OAC_WS_L2PROMO");
+    const int v = e ? atoi(e) : 128;
+    return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
 static int ws_plan(OacTrainer& t, Stage& s) {
     const int seeds = t.cfg.n_seeds;
-    const int gran = s.b_trans ? 32 : 16;                      // MN-major B tiles come in 32-column TMA boxes
+    // CTA pairs (gemm_ws2.cuh) when every task is made of whole 256-row tiles: each CTA then loads half of the B tile
+    // Measured (64 seeds, B200): the first-layer forward stages gain 13 % (critic_l1 90 -> 77 us: K = 393, the weight matrix is
+    // two thirds of a tile's operand bytes), K = 256 stages and the MN-major products gain nothing, and with few seeds the pair
+    // costs time (one round of tiles either way, half as many tiles in flight: 8 seeds 0.222 -> 0.235 ms per step).  So: K-major
+    // stages with K >= 320 and at least two rounds of work.  OAC_WS2_ALL=1 lifts the restriction (tests, A/B runs).
+    const bool ws2_all = getenv("OAC_WS2_ALL") && getenv("OAC_WS2_ALL")[0] == '1';
+    bool pair = t.allow_ws2;
+    {
+        int kmax = 0;
+        long long tiles256 = 0;
+        for (auto& g : s.gemm) {
+            pair = pair && (g.M % (2 * WS_BM) == 0) && g.epi != EPI_ADAM;
+            kmax = std::max(kmax, g.K);
+            tiles256 += (long long)(g.M / (2 * WS_BM)) * ((g.N + 255) / 256);
+        }
+        if (!ws2_all) pair = pair && !s.a_trans && !s.b_trans && kmax >= 320 && tiles256 * seeds >= 2ll * (sm_count() / 2);
+    }
+    const int BM = pair ? 2 * WS_BM : WS_BM;
+    const int n_units = pair ? sm_count() / 2 : sm_count();    // CTAs or CTA pairs working at once
+    const int gran = (s.b_trans ? 32 : 16) * (pair ? 2 : 1);   // MN-major B tiles come in 32-column TMA boxes (per CTA)
     auto width = [&](const GemmTask& g, int cap) {             // tile width for a column cap: even split, rounded up
-        const int lim = ((g.epi == EPI_ADAM || g.epi == EPI_GRAD) && g.has_bias) ? std::min(cap, (int)WS_BN_MAX_BIAS) : cap;
+        const int lim = ((g.epi == EPI_ADAM || g.epi == EPI_GRAD) && g.has_bias) ? std::min(cap, pair ? 192 : (int)WS_BN_MAX_BIAS) : cap;   // room for the bias MMA's columns
         const int tn = (g.N + lim - 1) / lim;
         int bn = (((g.N + tn - 1) / tn) + gran - 1) / gran * gran;
         return std::max(bn, gran);
     };
     auto tiles = [&](int cap) {
         long long n = 0;
-        for (auto& g : s.gemm) { const int bn = width(g, cap); n += (long long)((g.M + WS_BM - 1) / WS_BM) * ((g.N + bn - 1) / bn); }
+        for (auto& g : s.gemm) { const int bn = width(g, cap); n += (long long)((g.M + BM - 1) / BM) * ((g.N + bn - 1) / bn); }
         return n;
     };
     // Tile width.  With many rounds of the persistent grid (>= 4 at the widest tile) the widest tiles that still give every
@@ -806,36 +834,39 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     // one that grows with the width (measured: 8 seeds 27.9k -> 31.4k seed-updates/s, 16 seeds 43.8k -> 48.7k, 32 seeds
     // 60.9k -> 63.0k, 64 seeds unchanged).
     int cap = 256;
-    while (cap > 32 && tiles(cap) * seeds < sm_count()) cap >>= 1;
-    if (tiles(256) * seeds < 4ll * sm_count()) {
+    const int cap_min = pair ? 64 : 32;
+    while (cap > cap_min && tiles(cap) * seeds < n_units) cap >>= 1;
+    if (tiles(256) * seeds < 4ll * n_units) {
         double best = 1e30;
-        for (int cnd = 256; cnd >= 32; cnd >>= 1) {
+        for (int cnd = 256; cnd >= cap_min; cnd >>= 1) {
             const long long n = tiles(cnd) * seeds;
-            const long long rounds = (n + sm_count() - 1) / sm_count();
+            const long long rounds = (n + n_units - 1) / n_units;
             const double cost = rounds * (64.0 + cnd);
             if (cost < best) { best = cost; cap = cnd; }
         }
     }
     // heaviest tiles first (epilogue elements dominate; an Adam element moves 8x the bytes of a stored one)
     auto tile_cost = [&](const GemmTask& g) {
-        const double rows = std::min(g.M, (int)WS_BM), cols = std::min(g.N, width(g, cap));
+        const double rows = std::min(g.M, BM), cols = std::min(g.N, width(g, cap));
         return rows * cols * (g.epi == EPI_ADAM ? 8.0 : (g.epi == EPI_MASK ? 2.0 : 1.0)) + 0.05 * WS_BM * cols * g.K / 32.0;
     };
     std::stable_sort(s.gemm.begin(), s.gemm.end(), [&](const GemmTask& a, const GemmTask& b) { return tile_cost(a) > tile_cost(b); });
     int t0 = 0, bn_max = 0;
     for (auto& g : s.gemm) {
         g.bn = width(g, cap);
-        g.tiles_m = (g.M + WS_BM - 1) / WS_BM; g.tiles_n = (g.N + g.bn - 1) / g.bn;
+        g.tiles_m = (g.M + BM - 1) / BM; g.tiles_n = (g.N + g.bn - 1) / g.bn;
         g.tile0 = t0; t0 += g.tiles_m * g.tiles_n;
         bn_max = std::max(bn_max, g.bn);
     }
     s.ws_tiles_per_seed = t0;
-    s.ws_slot_bytes = (int)WS_A_BYTES + bn_max * (WS_KC * 4);
+    s.ws_pair = pair ? 1 : 0;
+    s.ws_slot_bytes = (int)WS_A_BYTES + (pair ? bn_max / 2 : bn_max) * (WS_KC * 4);
     const int budget = 224 * 1024 - 1024 - (int)WS_ONES_BYTES - (int)WS_SLAB_BYTES;
     s.ws_slots = std::min((int)WS_MAX_SLOTS, budget / s.ws_slot_bytes);
     if (s.ws_slots < 2) return set_error(OAC_E_INVALID, "internal: ws ring does not fit");
     s.smem = (size_t)s.ws_slots * s.ws_slot_bytes + WS_ONES_BYTES + WS_SLAB_BYTES + 1024;
-    s.ws_grid = (int)std::min<long long>((long long)t0 * seeds, sm_count());
+    s.ws_grid = pair ? 2 * (int)std::min<long long>((long long)t0 * seeds, n_units)
+                     : (int)std::min<long long>((long long)t0 * seeds, sm_count());
     // tensor maps
     TensorMapEncodeFn enc = tensor_map_encoder();
     std::vector<CUtensorMap> maps(2 * s.gemm.size());
@@ -849,7 +880,7 @@ static int ws_plan(OacTrainer& t, Stage& s) {
             const long long sstride = std::max<long long>(t.as.stride[r.arena], 4);
             cuuint64_t dims[3], strides[2];
             cuuint32_t box[3], es[3] = {1, 1, 1};
-            if (!mn) { dims[0] = (cuuint64_t)g.K; dims[1] = (cuuint64_t)ext; box[0] = WS_KC; box[1] = op == 0 ? WS_BM : (cuuint32_t)g.bn; }
+            if (!mn) { dims[0] = (cuuint64_t)g.K; dims[1] = (cuuint64_t)ext; box[0] = WS_KC; box[1] = op == 0 ? WS_BM : (cuuint32_t)(pair ? g.bn / 2 : g.bn); }
             else     { dims[0] = (cuuint64_t)ext; dims[1] = (cuuint64_t)g.K; box[0] = 32; box[1] = WS_KC; }
             dims[2] = (cuuint64_t)seeds; box[2] = 1;
             strides[0] = (cuuint64_t)ld * 4; strides[1] = (cuuint64_t)sstride * 4;
@@ -857,7 +888,7 @@ static int ws_plan(OacTrainer& t, Stage& s) {
             CUresult rc = enc(&maps[2 * i + op], CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, (void*)resolve(t.as, r, 0), dims, strides,
                               box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (rc != CUDA_SUCCESS) {
                 char msg[160];
                 snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) for stage %s task %d operand %d", (int)rc, s.name, (int)i, op);
@@ -1035,7 +1066,7 @@ static int finalize(OacTrainer& t) {
             s.max_rows = 0;
             for (auto& p : s.ph) s.max_rows = std::max(s.max_rows, p.rows);
             glue_plan(s, (long long)s.max_rows * s.ph.size() * seeds, !s.php.head_from_gemm);
-            s.many = s.php.head_from_gemm && s.glue_g == 1 && !getenv("OAC_NO_GLUE_MANY");      // (env: A/B measurement aid)
+            s.many = s.php.head_from_gemm && !getenv("OAC_NO_GLUE_MANY");      // (env: A/B measurement aid)
             if (int e = upload(t, s.ph.data(), s.ph.size(), &s.dev)) return e;
             s.php.tasks = (const PolicyHeadTask*)s.dev;
             s.php.as = t.as; s.php.hyper = t.hyper;
@@ -1059,7 +1090,8 @@ static int finalize(OacTrainer& t) {
             }
             s.chp.as = t.as;
             {
-                bool ok = s.chp.mode == CM_SAC && t.cfg.hidden == 256 && s.glue_g == 1 && s.chp.n_src == 6 && !getenv("OAC_NO_GLUE_MANY");
+                bool ok = s.chp.mode == CM_SAC && t.cfg.hidden == 256 && t.cfg.gemm_path == OAC_GEMM_TF32 && (long long)seeds * t.cfg.batch >= 2048 &&
+                          s.chp.n_src == 6 && !getenv("OAC_NO_GLUE_MANY");
                 for (int i = 0; i < s.chp.n_src && ok; ++i) ok = s.chp.src[i].n_heads == 1;
                 for (int a = 0; a < AR_COUNT && ok; ++a) ok = (t.as.stride[a] & 3) == 0 && al16(t.as.base[a]);
                 s.many = ok;
@@ -1072,7 +1104,7 @@ static int finalize(OacTrainer& t) {
             if (int e = upload(t, &s.asp, 1, &s.dev)) return e;
         } else if (s.kind == ST_POLICY_GRAD) {
             glue_plan(s, (long long)t.cfg.batch * s.pg.size() * seeds, !s.pgp.da_from_gemm);
-            s.many = s.pgp.da_from_gemm && s.glue_g == 1 && !getenv("OAC_NO_GLUE_MANY");
+            s.many = s.pgp.da_from_gemm && !getenv("OAC_NO_GLUE_MANY");
             if (int e = upload(t, s.pg.data(), s.pg.size(), &s.dev)) return e;
             s.pgp.tasks = (const PolicyGradTask*)s.dev;
             s.pgp.as = t.as;
@@ -1162,6 +1194,19 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                 wp.tiles_per_seed = s.ws_tiles_per_seed; wp.n_seeds = seeds; wp.total_tiles = s.ws_tiles_per_seed * seeds;
                 wp.n_slots = s.ws_slots; wp.slot_bytes = s.ws_slot_bytes;
                 const dim3 wg(s.ws_grid), wb(WS_THREADS);
+                if (s.ws_pair) {
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof(cfg));
+                    cfg.gridDim = wg; cfg.blockDim = wb; cfg.dynamicSmemBytes = s.smem; cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    if (!s.a_trans && !s.b_trans) OAC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false, false>, wp));
+                    else if (!s.a_trans) OAC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false, true>, wp));
+                    else OAC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true, true>, wp));
+                    return 0;
+                }
                 if (!s.a_trans && !s.b_trans) launch_pdl(gemm_ws_kernel<false, false>, wg, wb, s.smem, st, wp);
                 else if (!s.a_trans) launch_pdl(gemm_ws_kernel<false, true>, wg, wb, s.smem, st, wp);
                 else launch_pdl(gemm_ws_kernel<true, true>, wg, wb, s.smem, st, wp);
@@ -1300,6 +1345,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     if (int e = build_layout(*cfg, t->lay, t->ids)) { delete t; return e; }
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
+    { const char* n2 = getenv("OAC_NO_WS2"); t->allow_ws2 = !(n2 && n2[0] == '1'); }
     { const char* nk = getenv("OAC_NO_SK_TMA"); t->allow_sk_tma = !(nk && nk[0] == '1'); }
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
@@ -1343,6 +1389,9 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_ws((const void*)gemm_ws_kernel<false, false>);
         opt_ws((const void*)gemm_ws_kernel<false, true>);
         opt_ws((const void*)gemm_ws_kernel<true, true>);
+        opt_ws((const void*)gemm_ws2_kernel<false, false>);
+        opt_ws((const void*)gemm_ws2_kernel<false, true>);
+        opt_ws((const void*)gemm_ws2_kernel<true, true>);
         opt_in((const void*)policy_head_kernel<1>);
         opt_in((const void*)policy_head_kernel<4>);
         opt_in((const void*)policy_grad_kernel<1>);
@@ -1499,7 +1548,7 @@ extern "C" int oac_trainer_profile(OacTrainer* t, int32_t iters, int32_t max_sta
 }
 
 static int g_debug_kernel = -1;
-// Which kernel the last oac_gemm_debug call ran: 0 SIMT, 1 per-tile tcgen05, 2 warp-specialised TMA + tcgen05.
+// Which kernel the last oac_gemm_debug call ran: 0 SIMT, 1 per-tile tcgen05, 2 warp-specialised TMA + tcgen05, 3 its CTA-pair variant.
 extern "C" int oac_gemm_debug_kernel(void) { return g_debug_kernel; }
 
 // Test / measurement aid: one GEMM  C[M,N] = epi(sum_k A(m,k) B(n,k))  through either stage kernel.
@@ -1541,13 +1590,16 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     }
     { const char* nw = getenv("OAC_NO_WS"); t.allow_ws = !(nw && nw[0] == '1'); }
     int rc = finalize(t);
     const char* dbg_env = getenv("OAC_TC_DEBUG");
     const int dbg_n = 64;
     if (dbg_env && dbg_env[0] == '1') { cudaMalloc(&t.tc_dbg, sizeof(long long) * 8 * dbg_n * 8); cudaMemset(t.tc_dbg, 0, sizeof(long long) * 8 * dbg_n * 8); }
-    g_debug_kernel = rc ? -1 : (s.use_ws ? 2 : (s.use_tc ? 1 : 0));
+    g_debug_kernel = rc ? -1 : (s.use_ws ? (s.ws_pair ? 3 : 2) : (s.use_tc ? 1 : 0));
     if (!rc) rc = launch_stages(t, 0, (cudaStream_t)stream);
     if (!rc && t.tc_dbg) rc = launch_stages(t, 0, (cudaStream_t)stream);      // second (warm) run is the one reported
     cudaStreamSynchronize((cudaStream_t)stream);

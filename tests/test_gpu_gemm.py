@@ -71,6 +71,20 @@ def test_tcgen05_3xtf32_gemm(M, N, K, a_trans, b_trans):
 WS_SHAPES = SHAPES + [(1024, 256, 393), (384, 512, 264), (256, 393, 1000), (640, 224, 96)]
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (512, 256, 376), (256, 256, 393), (256, 34, 256), (256, 1, 256),
+                                   (256, 393, 256), (1024, 256, 393), (256, 393, 1000), (768, 192, 40)])
+@pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
+def test_ws2_cta_pair_gemm(M, N, K, a_trans, b_trans, monkeypatch):
+    """CTA-pair kernel (gemm_ws2.cuh: tcgen05.mma.cta_group::2, 256-row tiles, each CTA loads half of the B tile) on every
+    operand layout: OAC_WS2_ALL=1 lifts the planner's restriction to the stages where pairs pay, so shapes made of whole
+    256-row tiles run on it, including ragged N / K, N = 1 and more K chunks than ring slots."""
+    monkeypatch.setenv("OAC_WS2_ALL", "1")
+    for relu in (False, True):
+        got, ref = run_gemm(1, a_trans, b_trans, M, N, K, bias=(a_trans == 0), relu=relu and a_trans == 0, align4=True,
+                            want_kernel=3)
+        assert rel_err(got, ref) <= 1.5e-3, rel_err(got, ref)
+
+
 @pytest.mark.parametrize("M,N,K", WS_SHAPES)
 @pytest.mark.parametrize("a_trans,b_trans", LAYOUTS)
 def test_ws_tcgen05_tf32_gemm(M, N, K, a_trans, b_trans):
