@@ -19,7 +19,8 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "dram__bytes_read.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__inst_executed.sum"]
+        "smsp__inst_executed.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__cluster_size"]
 
 
 def launch_list(name, per_step):
@@ -98,6 +99,11 @@ if __name__ == "__main__":
         tr["1:fp32"] = traffic(tag + "_single_fp32.ncu-rep", ("gemm_sk_kernel", "gemm_fwd2_kernel"))
     if have(tag + "_64seeds_tf32.ncu-rep"):
         full_report(tag + "_64seeds_tf32.ncu-rep", tag + "_64seeds_tf32_full.txt")
-        tr["64:tf32"] = traffic(tag + "_64seeds_tf32.ncu-rep", "gemm_ws_kernel")
+        tr["64:tf32"] = traffic(tag + "_64seeds_tf32.ncu-rep", ("gemm_ws_kernel", "gemm_ws2_kernel"))
+    # round-2 extras: the generic glue kernels before their many-seed rewrite, and the GEMM stages alone
+    if have("r02c_glue64.ncu-rep"):
+        full_report("r02c_glue64.ncu-rep", "r02_glue64_before.txt")
+    if have("r02e_gemm64.ncu-rep"):
+        full_report("r02e_gemm64.ncu-rep", "r02_gemm64_full.txt")
     json.dump(tr, open(tpath, "w"), indent=1)
     print(tr)
