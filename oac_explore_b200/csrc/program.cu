@@ -23,6 +23,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
 #include "gemm_ws2.cuh"
+#include "gemm_chain.cuh"
 #include "gemm_fwd2.cuh"
 #include "adam_stream.cuh"
 #include "stats.cuh"
@@ -30,6 +31,8 @@
 
 namespace oac {
 
+static int sm_count();
+constexpr int OAC_E_CHAIN_UNAVAILABLE = -101;     // internal: finalize() asks for a rebuild without strip-fused forward chains
 constexpr int OAC_E_SPLIT_UNAVAILABLE = -100;      // internal: finalize() asks for a rebuild without gradient-store stages
 static inline int pad4(int x) { return (x + 3) & ~3; }
 static inline long long pad4ll(long long x) { return (x + 3) & ~3ll; }
@@ -148,6 +151,8 @@ struct Stage {
     // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
     int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
     int ws_pair = 0;            // CTA-pair kernel (gemm_ws2.cuh: tcgen05.mma.cta_group::2, 256-row tiles)
+    int chain = 0;              // > 0: strip-fused forward chain of this many layers (gemm_chain.cuh); tasks are layer-major
+    int chain_strips0[WS_MAX_TASKS + 1];
     int sk_tma = 0;             // latency-regime FFMA tile with TMA-staged operands (tensor maps in ws_tmaps)
     int fused2 = 0;             // tasks are [layer-1 ..., layer-2 ...] pairs of two dependent forward layers: one cluster launch
     int fwd2_cluster = 0;       // (gemm_fwd2.cuh) when the plan allows it, else two plain launches
@@ -185,6 +190,7 @@ struct OacTrainer {
     float* host_scalars = nullptr;   // OacBuffers::host_scalars
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_ws2 = true;     // OAC_NO_WS2=1: single-CTA tiles only, no CTA pairs (A/B measurement aid)
+    bool allow_chain = true;   // OAC_NO_CHAIN=1: one launch per forward layer instead of strip-fused chains (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
     bool allow_sk_tma = true;  // OAC_NO_SK_TMA=1: cp.async staging in the latency-regime FFMA tile
@@ -499,6 +505,29 @@ struct Builder {
         Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = head.ph; s.php = head.php;
     }
     // two dependent forward layers as one cluster launch (gemm_fwd2.cuh): the FFMA latency regime only
+    // many-seed tensor-core regime: l1 -> l2 (-> head) of a 128-row strip in one launch, activations handed on in TMEM
+    bool fuse_chain() const { return tensor_glue && t.allow_chain && t.allow_ws && H == 256 && (B % 128) == 0; }
+    // builds the forward stages of a group of nets: `layers` = 2 (critics) or 3 (policies: trunk + head GEMM)
+    template <typename F1, typename F2, typename F3>
+    void forward_stages(const char* n1, const char* n2, const char* n3, const char* nchain, int layers, F1 l1, F2 l2, F3 l3) {
+        if (fuse_chain()) {
+            // Measured (B200): a chain pays when its strips fit ONE round of the persistent grid (8 seeds: policy 33.3 -> 27.1 us,
+            // critics 31.3 -> 26.9 us: two tile life cycles and two launches gone); with several rounds the unfused stages
+            // overlap every epilogue with the next tile's mainloop and win (64 seeds: 0.796 vs 0.814 ms per step).
+            Stage probe; l1(probe);
+            long long strips = 0;
+            for (auto& g : probe.gemm) strips += (g.M + 127) / 128;
+            const bool all = getenv("OAC_CHAIN_ALL") && getenv("OAC_CHAIN_ALL")[0] == '1';       // (tests, A/B runs)
+            if (all || strips * c.n_seeds <= sm_count()) {
+                Stage& s = add_stage(ST_GEMM, nchain); s.chain = layers;
+                l1(s); l2(s); if (layers == 3) l3(s);
+                return;
+            }
+        }
+        { Stage& s = add_stage(ST_GEMM, n1); l1(s); }
+        { Stage& s = add_stage(ST_GEMM, n2); l2(s); }
+        if (layers == 3 && tensor_glue) { Stage& s = add_stage(ST_GEMM, n3); l3(s); }
+    }
     bool fuse_fwd2() const {
         return latency_lanes() && c.gemm_path == OAC_GEMM_FP32 && !getenv("OAC_NO_FWD2");               // (env: A/B measurement aid)
     }
@@ -529,11 +558,8 @@ void Builder::build_sac() {
         { Stage& s = add_stage(ST_GEMM, "critic_l2_data"); s.lane = 1; crit_l2_rows(s, q1, ca1, B); crit_l2_rows(s, q2, ca2, B); }
     }
     if (fwd2) { Stage& s = add_stage(ST_GEMM, "policy_l1+l2"); s.fused2 = 1; pol_l1(s, pol, 2, pa); pol_l2(s, pol, pa); }
-    else {
-    { Stage& s = add_stage(ST_GEMM, "policy_l1"); pol_l1(s, pol, 2, pa); }
-    { Stage& s = add_stage(ST_GEMM, "policy_l2"); pol_l2(s, pol, pa); }
-    }
-    if (tensor_glue) { Stage& s = add_stage(ST_GEMM, "policy_l3"); pol_l3(s, pol, pa); }
+    else forward_stages("policy_l1", "policy_l2", "policy_l3", "policy_l1>l2>l3", 3,
+                        [&](Stage& s) { pol_l1(s, pol, 2, pa); }, [&](Stage& s) { pol_l2(s, pol, pa); }, [&](Stage& s) { pol_l3(s, pol, pa); });
     { Stage& s = add_stage(ST_POLICY_HEAD, "policy_head+sample+alpha");
       s.ph.push_back(ph_task(pol, pa, 0, 1, 3, 0, 1)); fill_php(s, 0, 0, 3); }
     split_step_tail();
@@ -547,10 +573,10 @@ void Builder::build_sac() {
         { Stage& s = add_stage(ST_GEMM, "critic_l2_pi");
           crit_l2_rows(s, q1, ca1, 0); crit_l2_rows(s, q2, ca2, 0); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
     } else {
-    { Stage& s = add_stage(ST_GEMM, "critic_l1");
-      crit_l1(s, q1, 1, ca1); crit_l1(s, q2, 1, ca2); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); }
-    { Stage& s = add_stage(ST_GEMM, "critic_l2");
-      crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); }
+        forward_stages("critic_l1", "critic_l2", "", "critic_l1>l2", 2,
+                       [&](Stage& s) { crit_l1(s, q1, 1, ca1); crit_l1(s, q2, 1, ca2); crit_l1(s, t1, 3, ta1); crit_l1(s, t2, 3, ta2); },
+                       [&](Stage& s) { crit_l2(s, q1, ca1); crit_l2(s, q2, ca2); crit_l2(s, t1, ta1); crit_l2(s, t2, ta2); },
+                       [&](Stage&) {});
     }
     { Stage& s = add_stage(ST_CRITIC_HEAD, "critic_head+targets+dh2"); s.join = 3;
       memset(&s.chp, 0, sizeof(s.chp));
@@ -902,6 +928,64 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     return 0;
 }
 
+// Strip-fused forward chain (gemm_chain.cuh): tasks are [layer][chain]; every chain's layers share M, hidden layers are H = 256
+// wide (one 256-column tile = the whole A operand of the next layer), a head layer is rounded up to 16 columns.
+static int chain_plan(OacTrainer& t, Stage& s) {
+    const int seeds = t.cfg.n_seeds;
+    const int NL = s.chain, NC = (int)s.gemm.size() / NL;
+    if (NL < 2 || NL > CH_MAX_LAYERS || NC < 1 || NC * NL != (int)s.gemm.size() || NC > WS_MAX_TASKS || !ws_eligible(t, s))
+        return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: shape");
+    int strips = 0;
+    for (int c = 0; c < NC; ++c) {
+        const GemmTask& g0 = s.gemm[c];
+        for (int l = 0; l < NL; ++l) {
+            GemmTask& g = s.gemm[l * NC + c];
+            const bool last = l == NL - 1;
+            if (g.a_trans || g.b_trans || g.M != g0.M || (g.M % WS_BM) != 0) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: layout");
+            if (l > 0) {      // reads the previous layer's output in full
+                const GemmTask& pv = s.gemm[(l - 1) * NC + c];
+                if (g.K != pv.N || g.A.arena != pv.C.arena || g.A.off != pv.C.off || g.K != 256) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: link");
+            }
+            if (!last && (g.N != 256 || g.epi != EPI_BIAS_RELU)) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: hidden layer");
+            if (g.epi != EPI_BIAS_RELU && g.epi != EPI_BIAS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: epilogue");
+            if (g.N > 256) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: width");
+            g.bn = last ? std::max(16, (g.N + 15) / 16 * 16) : 256;
+            g.tiles_m = g.M / WS_BM; g.tiles_n = 1; g.tile0 = strips;
+        }
+        s.chain_strips0[c] = strips;
+        strips += g0.M / WS_BM;
+    }
+    s.chain_strips0[NC] = strips;
+    s.ws_tiles_per_seed = strips;
+    s.ws_slot_bytes = (int)WS_A_BYTES + 256 * (WS_KC * 4);
+    const int budget = 224 * 1024 - 1024 - (int)WS_SLAB_BYTES;
+    s.ws_slots = std::min((int)WS_MAX_SLOTS, budget / s.ws_slot_bytes);
+    if (s.ws_slots < 2) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: ring");
+    s.smem = (size_t)s.ws_slots * s.ws_slot_bytes + WS_SLAB_BYTES + 1024;
+    s.ws_grid = (int)std::min<long long>((long long)strips * seeds, sm_count());
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    std::vector<CUtensorMap> maps(2 * s.gemm.size());
+    for (size_t i = 0; i < s.gemm.size(); ++i) {
+        const GemmTask& g = s.gemm[i];
+        for (int op = 0; op < 2; ++op) {
+            const Ref r = op == 0 ? g.A : g.B;
+            const int ld = op == 0 ? g.lda : g.ldb;
+            const int ext = op == 0 ? g.M : g.N;
+            const long long sstride = std::max<long long>(t.as.stride[r.arena], 4);
+            cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)ext, (cuuint64_t)seeds};
+            cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)sstride * 4};
+            cuuint32_t box[3] = {WS_KC, op == 0 ? (cuuint32_t)WS_BM : (cuuint32_t)g.bn, 1}, es[3] = {1, 1, 1};
+            CUresult rc = enc(&maps[2 * i + op], CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, (void*)resolve(t.as, r, 0), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: tensor map");
+        }
+    }
+    if (int e = upload(t, maps.data(), maps.size(), &s.ws_tmaps)) return e;
+    if (int e = upload(t, s.gemm.data(), s.gemm.size(), &s.dev)) return e;
+    s.use_ws = 1;
+    return 0;
+}
+
 // Glue kernels: G warps per row (4: a single seed's few hundred rows still fill the chip; 1: self-contained warps
 // for the many-seed launches) and, since every CTA stages head / action-column weights once, several row groups
 // per CTA when there are enough rows to keep ~4 CTAs on every SM anyway.
@@ -970,6 +1054,11 @@ static int finalize(OacTrainer& t) {
             }
             if (s.fused2 && t.cfg.gemm_path != OAC_GEMM_FP32)
                 return set_error(OAC_E_INVALID, "internal: fused layer pairs exist on the FFMA path only");
+            if (s.chain) {
+                if (t.cfg.gemm_path != OAC_GEMM_TF32) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: gemm path");
+                if (int e = chain_plan(t, s)) return e;
+                continue;
+            }
             if (t.cfg.gemm_path == OAC_GEMM_TF32 || t.cfg.gemm_path == OAC_GEMM_TF32X3) {
                 const bool x3 = t.cfg.gemm_path == OAC_GEMM_TF32X3;
                 if (!x3 && t.allow_ws && ws_eligible(t, s)) {
@@ -1189,6 +1278,15 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
             StageParams sp; sp.tasks = (const GemmTask*)s.dev; sp.as = t.as; sp.hyper = t.hyper; sp.kc = s.kc;
             sp.tmaps = s.sk_tma ? (const CUtensorMap*)s.ws_tmaps : nullptr;
             dim3 grid(s.max_tiles, (unsigned)s.gemm.size(), seeds);
+            if (s.chain) {
+                ChainParams cp; cp.sp = sp; cp.sp.tmaps = nullptr; cp.tmaps = (const CUtensorMap*)s.ws_tmaps;
+                cp.n_layers = s.chain; cp.n_chains = (int)s.gemm.size() / s.chain;
+                for (int i = 0; i <= WS_MAX_TASKS; ++i) cp.strips0[i] = i <= cp.n_chains ? s.chain_strips0[i] : 0;
+                cp.n_seeds = seeds; cp.total_items = s.ws_tiles_per_seed * seeds; cp.n_slots = s.ws_slots; cp.slot_bytes = s.ws_slot_bytes;
+                launch_pdl(gemm_chain_kernel, dim3(s.ws_grid), dim3(WS_THREADS), s.smem, st, cp);
+                OAC_CUDA(cudaGetLastError());
+                return 0;
+            }
             if (s.use_ws) {
                 WsParams wp; wp.sp = sp; wp.tmaps = (const CUtensorMap*)s.ws_tmaps; wp.n_tasks = (int)s.gemm.size();
                 wp.tiles_per_seed = s.ws_tiles_per_seed; wp.n_seeds = seeds; wp.total_tiles = s.ws_tiles_per_seed * seeds;
@@ -1346,6 +1444,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     { const char* nw = getenv("OAC_NO_WS"); t->allow_ws = !(nw && nw[0] == '1'); }
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
     { const char* n2 = getenv("OAC_NO_WS2"); t->allow_ws2 = !(n2 && n2[0] == '1'); }
+    { const char* nc = getenv("OAC_NO_CHAIN"); t->allow_chain = !(nc && nc[0] == '1'); }
     { const char* nk = getenv("OAC_NO_SK_TMA"); t->allow_sk_tma = !(nk && nk[0] == '1'); }
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
@@ -1392,6 +1491,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_ws((const void*)gemm_ws2_kernel<false, false>);
         opt_ws((const void*)gemm_ws2_kernel<false, true>);
         opt_ws((const void*)gemm_ws2_kernel<true, true>);
+        opt_ws((const void*)gemm_chain_kernel);
         opt_in((const void*)policy_head_kernel<1>);
         opt_in((const void*)policy_head_kernel<4>);
         opt_in((const void*)policy_grad_kernel<1>);
@@ -1399,6 +1499,18 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     int fe = finalize(*t);
+    if (fe == OAC_E_CHAIN_UNAVAILABLE) {
+        // a forward chain cannot be fused (tensor maps unavailable / misaligned buffers / shapes): one launch per layer
+        for (void* p : t->dev_allocs) cudaFree(p);
+        t->dev_allocs.clear(); t->stages.clear(); t->work_cursor = 0;
+        t->allow_chain = false;
+        Builder b2(*t);
+        if (cfg->algo == OAC_ALGO_SAC) b2.build_sac();
+        else if (cfg->algo == OAC_ALGO_POAC) b2.build_poac();
+        else b2.build_goac();
+        if (t->work_cursor > t->lay.work_floats) { oac_trainer_destroy(t); return set_error(OAC_E_INVALID, "internal: work arena"); }
+        fe = finalize(*t);
+    }
     if (fe == OAC_E_SPLIT_UNAVAILABLE) {
         // no TMA path for a gradient-store stage (tensor maps unavailable / misaligned buffers): rebuild the program
         // with the fused Adam epilogues
@@ -1474,7 +1586,7 @@ extern "C" int oac_trainer_stats(OacTrainer* t, float* out, int32_t out_ld, void
 
 extern "C" int oac_trainer_ws_stages(const OacTrainer* t) {
     int n = 0;
-    if (t) for (const Stage& s : t->stages) n += s.use_ws;
+    if (t) for (const Stage& s : t->stages) n += s.chain ? s.chain : s.use_ws;
     return n;
 }
 

@@ -56,6 +56,9 @@ TANH_EPS = 1e-6     # trainer/policies.py:127
 #             WEIGHT gradient is a GEMM stage.
 #   "many"  : many seeds (the batched-seed program).  The policy head, its backward and dQ/da are GEMM stages too; the
 #             critic head's forward and its input gradients (dq W3: critic_head / rank1_mask kernels) stay exact fp32.
+#   "chain" : "many" where the forward layers of a 128-row strip run as one strip-fused launch (gemm_chain.cuh, small
+#             seed groups): the hidden activations are stored tf32-ROUNDED, so the critic head's fp32 dot product sees
+#             rounded h2 rows (every other consumer rounds them itself or only tests their sign).
 #   "all"   : every Linear rounded (the idealised model; no kernel regime is exactly this).
 _TF32 = {"mode": None}
 
@@ -72,7 +75,7 @@ class tf32_mode(object):
     """``with orc.tf32_mode("all"): orc.sac_step(...)`` (see the comment above)."""
 
     def __init__(self, mode="all"):
-        assert mode in (None, "all", "trunk", "many")
+        assert mode in (None, "all", "trunk", "many", "chain")
         self.mode = mode
 
     def __enter__(self):
@@ -90,7 +93,10 @@ class _LinearTF32(torch.autograd.Function):
     def forward(ctx, x, w, b, r_fwd, r_dx, r_dw):
         ctx.save_for_backward(x, w)
         ctx.flags = (r_dx, r_dw)
-        xr, wr = (round_tf32(x), round_tf32(w)) if r_fwd else (x, w)
+        if r_fwd == "x":                        # the input arrives rounded (stored so), the weights are used exactly
+            xr, wr = round_tf32(x), w
+        else:
+            xr, wr = (round_tf32(x), round_tf32(w)) if r_fwd else (x, w)
         y = xr @ wr.t()
         return y + b if b is not None else y
 
@@ -115,15 +121,16 @@ def linear(x, w, b, head=None):
     mode = _TF32["mode"]
     if mode is None or x.dtype != torch.float32:
         return x @ w.t() + b
-    exact = (head is not None and mode == "trunk") or (head == 'q' and mode == "many")
-    return _LinearTF32.apply(x, w, b, not exact, not exact, True)
+    exact = (head is not None and mode == "trunk") or (head == 'q' and mode in ("many", "chain"))
+    r_fwd = "x" if (head == 'q' and mode == "chain") else (not exact)
+    return _LinearTF32.apply(x, w, b, r_fwd, not exact, True)
 
 
 def matmul_dx(g, w, exact_modes=()):
     """grad_in = grad_out @ W (Linear backward, written out by hand in ``_q_dx_action``); exact fp32 in the tf32 regimes
     listed in ``exact_modes`` (the product is fused into a glue kernel there)."""
     mode = _TF32["mode"]
-    if mode is None or g.dtype != torch.float32 or mode in exact_modes:
+    if mode is None or g.dtype != torch.float32 or mode in exact_modes or (mode == "chain" and "many" in exact_modes):
         return g @ w
     return round_tf32(g) @ round_tf32(w)
 

@@ -237,3 +237,55 @@ def test_poac_goac_tensor_path_vs_model(share):
             if og[gname][k] is None:
                 continue
             assert rel_err(got, og[gname][k]) <= TOL, (gname, k, rel_err(got, og[gname][k]))
+
+
+def test_strip_fused_forward_chain_vs_model_and_unfused(monkeypatch):
+    """Small seed groups run the forward layers of every 128-row strip as ONE launch (gemm_chain.cuh): h1 / h2 go from
+    layer to layer through tensor memory (accumulator converted in place -> tcgen05.mma with A in TMEM).  8 seeds: the
+    chained program against the oracle's tf32 model (mode "chain": hidden activations are stored tf32-rounded) and against
+    the unfused program (OAC_NO_CHAIN=1) on the same inputs."""
+    from oac_explore_b200.seed_group import SACSeedGroup
+    S = 8
+    ids = list(range(S))
+    grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=1)
+    monkeypatch.setenv("OAC_NO_CHAIN", "1")
+    ref_grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=1)
+    monkeypatch.delenv("OAC_NO_CHAIN")
+    # 3 launches fewer: policy l1 > l2 > l3 and critic l1 > l2 are one launch each
+    assert grp.engine.launches_per_step == ref_grp.engine.launches_per_step - 3, (grp.engine.launches_per_step, ref_grp.engine.launches_per_step)
+    states, outs = {}, {}
+    for sid in (0, 5):
+        torch.manual_seed(sid)
+        states[sid] = orc.SACState(O, A, hidden=(H, H))
+    for step in range(2):
+        for slot, sid in enumerate(ids):
+            batch = synth_batch(B, O, A, seed=3000 * sid + step)
+            eps = synth_eps(2, B, A, seed=91 * sid + step)
+            for g_ in (grp, ref_grp):
+                g_.load_batch(slot, batch)
+                g_.inject_noise(slot, eps[0], eps[1])
+            if sid in states:
+                with orc.tf32_mode("chain"):
+                    outs[sid] = orc.sac_step(states[sid], batch, eps[0], eps[1])
+        grp.step(external_eps=True)
+        ref_grp.step(external_eps=True)
+        torch.cuda.synchronize()
+        e, er = grp.engine, ref_grp.engine
+        for slot in range(S):
+            for off, shape in ((e.lay.off_q_pred, (B, 2)), (e.lay.off_q_target, (B, 2)), (e.lay.off_log_pi, (3 * B,))):
+                assert rel_err(e.io_view(off, shape, seed=slot).cpu(), er.io_view(off, shape, seed=slot).cpu()) <= TOL
+        for sid, o in outs.items():
+            qp = e.io_view(e.lay.off_q_pred, (B, 2), seed=sid).cpu()
+            assert rel_err(qp[:, 0], o['q1_pred'][:, 0]) <= TOL and rel_err(qp[:, 1], o['q2_pred'][:, 0]) <= TOL
+            assert rel_err(e.io_view(e.lay.off_q_target, (B, 2), seed=sid).cpu()[:, 0], o['q_target'][:, 0]) <= TOL
+            if step == 0:
+                batch = synth_batch(B, O, A, seed=3000 * sid)
+                xq = torch.cat([batch['observations'], batch['actions']], dim=1)
+                check_net_grads(grads_of(e, 0, seed=sid), o['grad_policy'], batch['observations'], (sid, 'policy'))
+                check_net_grads(grads_of(e, 1, seed=sid), o['grad_qf1'], xq, (sid, 'qf1'))
+                check_net_grads(grads_of(e, 2, seed=sid), o['grad_qf2'], xq, (sid, 'qf2'))
+    for sid in states:
+        for n in NETS:
+            ours = net_cpu(grp.nets[sid][n])
+            for k, v in getattr(states[sid], n).items():
+                check_weights(ours[k], v, 2, (sid, n, k))
