@@ -117,6 +117,123 @@ class SACSeedGroup(object):
         return GroupExplorer(self, hyper_params, **kw)
 
 
+class _AlgoSeedGroup(object):
+    """Shared plumbing of the P-OAC / G-OAC seed groups: S independent trainers of one algorithm in one engine (every
+    stage launched once over seeds x networks), per-seed weights / Adam state / counters / noise keys.  Subclasses build
+    the per-seed network objects in the reference's construction (= torch RNG) order."""
+
+    def __init__(self, cfg, seed_ids, obs_dim, act_dim, batch):
+        self.seed_ids = list(seed_ids)
+        if len(self.seed_ids) < 1:
+            raise ValueError("empty seed group")
+        self.engine = Engine(cfg)
+        self.O, self.A, self.B = obs_dim, act_dim, batch
+        ids = torch.tensor(self.seed_ids, dtype=torch.int64)
+        self.engine.counters[:, _lib.CNT_RNG_LO] = (ids & 0x7fffffff).to(torch.int32).to(self.engine.device)
+        self.engine.counters[:, _lib.CNT_RNG_HI] = (ids >> 31).to(torch.int32).to(self.engine.device)
+        self.nets = []
+        self._n_train_steps_total = 0
+        self._uses_counts = bool(cfg.counts)
+        self._with_tp = cfg.algo == _lib.ALGO_GOAC
+
+    n_seeds = property(lambda self: len(self.seed_ids))
+
+    def _bind(self, net, idx, s):
+        net._bind(self.engine.net_views(idx, seed=s), self.engine.params[s], self.engine.net_layout(idx))
+        return net
+
+    def load_batch(self, seed_slot, batch):
+        f = lambda t: t.to(self.engine.device, torch.float32)
+        self.engine.load_batch(f(batch['observations']), f(batch['actions']), f(batch['rewards']), f(batch['terminals']),
+                               f(batch['next_observations']),
+                               f(batch['counts']) if (self._uses_counts and 'counts' in batch) else None,
+                               seed=seed_slot, with_tp=self._with_tp)
+
+    def inject_noise(self, seed_slot, eps_obs, eps_next):
+        self.engine.set_eps(eps_obs.to(self.engine.device), eps_next.to(self.engine.device), seed=seed_slot)
+
+    def step(self, external_eps=False):
+        self.engine.step(external_eps=external_eps)
+        self._n_train_steps_total += 1
+
+    def stats(self):
+        """[S, n_stats] device tensor: every seed's ``eval_statistics`` vector (key order: include/oac_b200.h)."""
+        return self.engine.stats_device()
+
+
+class ParticleSeedGroup(_AlgoSeedGroup):
+    """S independent ``ParticleTrainer`` (P-OAC) instances in one engine (trainer/particle_trainer_oac.py:13-113; BASELINE
+    config 3 batched over seeds).  ``nets[s]`` = dict(policy, qfs=[...], tfs=[...])."""
+
+    def __init__(self, seed_ids, obs_dim, act_dim, hidden=256, batch=256, n_estimators=10, share_layers=True,
+                 gemm_path=_lib.GEMM_FP32, discount=0.99, reward_scale=1.0, policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3,
+                 target_update_period=1, use_automatic_entropy_tuning=True, target_entropy=None, deterministic=False,
+                 q_min=0.0, q_max=100.0, counts=False, train_bias=True, std_soft_update=False, std_soft_update_prob=0.0,
+                 rng_seed=0):
+        S = len(list(seed_ids))
+        cfg = make_config(_lib.ALGO_POAC, obs_dim, act_dim, hidden, batch, n_seeds=S, n_particles=n_estimators,
+                          share_layers=share_layers, deterministic=deterministic, auto_alpha=use_automatic_entropy_tuning,
+                          counts=counts, train_bias=train_bias, target_update_period=target_update_period, gemm_path=gemm_path,
+                          discount=discount, reward_scale=reward_scale, soft_target_tau=soft_target_tau, policy_lr=policy_lr,
+                          qf_lr=qf_lr, target_entropy=target_entropy, rng_seed=rng_seed, std_soft_update=std_soft_update,
+                          std_soft_update_prob=std_soft_update_prob)
+        super().__init__(cfg, seed_ids, obs_dim, act_dim, batch)
+        n = 1 if share_layers else n_estimators
+        pp = get_policy_producer(obs_dim, act_dim, [hidden, hidden])
+        qp = get_q_producer(obs_dim, act_dim, [hidden, hidden], output_size=n_estimators if share_layers else 1)
+        init = np.linspace(q_min, q_max, n_estimators)                       # :75
+        for s, sid in enumerate(self.seed_ids):
+            torch.manual_seed(sid)
+            policy = self._bind(pp(), 0, s)                                  # SACTrainer.__init__ part (:46-58): policy + 4 dropped critics
+            for _ in range(4):
+                qp()
+            qfs, tfs = [], []
+            for i in range(n):                                               # :99-113: (qf, tf) pairs
+                b = init if share_layers else init[i]
+                qfs.append(self._bind(qp(bias=b, train_bias=train_bias), 1 + i, s))
+                tfs.append(self._bind(qp(bias=b, train_bias=train_bias), 2 + n + i, s))
+            self.nets.append(dict(policy=policy, qfs=qfs, tfs=tfs))
+
+
+class GaussianSeedGroup(_AlgoSeedGroup):
+    """S independent ``GaussianTrainer`` (G-OAC) instances in one engine (trainer/gaussian_trainer.py:14-160; BASELINE
+    config 4 batched over seeds).  ``nets[s]`` = dict(policy, target_policy, qfs=[q(, std)], tfs=[q_target(, std_target)])."""
+
+    def __init__(self, seed_ids, obs_dim, act_dim, hidden=256, batch=256, share_layers=True, gemm_path=_lib.GEMM_FP32,
+                 discount=0.99, reward_scale=1.0, policy_lr=3e-4, qf_lr=3e-4, std_lr=3e-5, soft_target_tau=5e-3,
+                 target_update_period=1, delta=0.95, q_min=0.0, q_max=100.0, counts=False, train_bias=True, rng_seed=0):
+        from .gaussian_trainer import norm_ppf
+        S = len(list(seed_ids))
+        mean, std = (q_max + q_min) / 2, (q_max - q_min) / np.sqrt(12)       # :70-72
+        cfg = make_config(_lib.ALGO_GOAC, obs_dim, act_dim, hidden, batch, n_seeds=S, share_layers=share_layers,
+                          deterministic=True, auto_alpha=False, counts=counts, train_bias=train_bias,
+                          target_update_period=target_update_period, gemm_path=gemm_path, discount=discount,
+                          reward_scale=reward_scale, soft_target_tau=soft_target_tau, policy_lr=policy_lr, qf_lr=qf_lr,
+                          std_lr=std_lr, standard_bound=norm_ppf(delta), std_init=float(std), rng_seed=rng_seed)
+        super().__init__(cfg, seed_ids, obs_dim, act_dim, batch)
+        pp = get_policy_producer(obs_dim, act_dim, [hidden, hidden])
+        qp = get_q_producer(obs_dim, act_dim, [hidden, hidden], output_size=2 if share_layers else 1)
+        n = 1 if share_layers else 2
+        for s, sid in enumerate(self.seed_ids):
+            torch.manual_seed(sid)
+            policy = self._bind(pp(), 0, s)
+            for _ in range(4):
+                qp()
+            if share_layers:                                                 # :92-99
+                b = np.array([mean, np.log(std)])
+                q = self._bind(qp(bias=b, positive=[False, True], train_bias=train_bias), 2, s)
+                qt = self._bind(qp(bias=b, positive=[False, True], train_bias=train_bias), 3 + n, s)
+                qfs, tfs = [q], [qt]
+            else:                                                            # :100-112
+                q = self._bind(qp(bias=mean), 2, s)
+                qt = self._bind(qp(bias=mean), 3 + n, s)
+                sd = self._bind(qp(bias=np.log(std), positive=True, train_bias=train_bias), 3, s)
+                sdt = self._bind(qp(bias=np.log(std), positive=True, train_bias=train_bias), 4 + n, s)
+                qfs, tfs = [q, sd], [qt, sdt]
+            target_policy = self._bind(pp(), 1, s)                           # :143
+            self.nets.append(dict(policy=policy, target_policy=target_policy, qfs=qfs, tfs=tfs))
+
+
 def allgather_stats(local_stats, seed_ids, n_seeds_total, group=None):
     """Collects every rank's [S_local, n] statistics into one [n_seeds_total, n] tensor ordered by seed id.
     The only collective of the design; runs once per reporting interval, never inside a step."""

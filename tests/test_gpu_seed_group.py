@@ -62,3 +62,47 @@ def test_group_gather_shared_store():
     grp.step()
     torch.cuda.synchronize()
     assert torch.isfinite(grp.stats()).all()
+
+
+@pytest.mark.parametrize("share", [True, False])
+def test_particle_and_gaussian_groups_equal_singles(share):
+    """P-OAC and G-OAC seeds batched in one engine (ParticleSeedGroup / GaussianSeedGroup) == the same seeds trained one by
+    one through ParticleTrainer / GaussianTrainer, bit for bit (fp32 path), including the per-seed statistics vectors."""
+    from oac_explore_b200.seed_group import ParticleSeedGroup, GaussianSeedGroup
+    from tests.test_gpu_poac_goac import make_poac, make_goac
+    O, A, B, H, P = 23, 5, 64, 64, 4
+    ids = [2, 9, 5]
+    kw = dict(policy_lr=3e-4, qf_lr=3e-4, soft_target_tau=5e-3, q_min=0.0, q_max=500.0)
+    pg = ParticleSeedGroup(ids, O, A, hidden=H, batch=B, n_estimators=P, share_layers=share, **kw)
+    gg = GaussianSeedGroup(ids, O, A, hidden=H, batch=B, share_layers=share, std_lr=3e-5, **kw)
+    ps, gs = [], []
+    for sid in ids:
+        torch.manual_seed(sid)
+        ps.append(make_poac(O, A, H, P, share, False))
+        torch.manual_seed(sid)
+        gs.append(make_goac(O, A, H, share, False))
+    for step in range(2):
+        for slot, sid in enumerate(ids):
+            batch = synth_batch(B, O, A, seed=100 * sid + step)
+            eps = synth_eps(2, B, A, seed=7 * sid + step)
+            pg.load_batch(slot, batch); pg.inject_noise(slot, eps[0], eps[1])
+            gg.load_batch(slot, batch)
+            ps[slot].inject_noise(eps_obs=eps[0], eps_next=eps[1])
+            ps[slot].train_from_torch({k: v.cuda() for k, v in batch.items()})
+            gs[slot].train_from_torch({k: v.cuda() for k, v in batch.items()})
+        pg.step(external_eps=True)
+        gg.step()
+    torch.cuda.synchronize()
+    for slot in range(len(ids)):
+        a = pg.nets[slot]
+        pairs = [(a['policy'], ps[slot].policy)] + list(zip(a['qfs'], ps[slot].qfs)) + list(zip(a['tfs'], ps[slot].tfs))
+        b = gg.nets[slot]
+        pairs += [(b['policy'], gs[slot].policy), (b['target_policy'], gs[slot].target_policy)]
+        pairs += list(zip(b['qfs'], gs[slot].qfs)) + list(zip(b['tfs'], gs[slot].tfs))
+        for x, y in pairs:
+            sx, sy = net_cpu(x), net_cpu(y)
+            for k in sx:
+                assert torch.equal(sx[k], sy[k]), (slot, k)
+        assert torch.equal(pg.stats()[slot].cpu(), torch.from_numpy(ps[slot]._engine.stats_host()[0]))
+        assert torch.equal(gg.stats()[slot].cpu(), torch.from_numpy(gs[slot]._engine.stats_host()[0]))
+    assert pg.stats().shape == (3, 11 + 9 * P) and gg.stats().shape == (3, 29)
