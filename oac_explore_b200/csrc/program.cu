@@ -499,7 +499,11 @@ struct Builder {
     // the policy_head kernel just added (fence + ticket + reduction in its last CTA) for a one-CTA kernel on lane 2
     // (measured per step: SAC 123.6 -> 119.4 us, P-OAC 129.6 -> 127.0, G-OAC 131.0 -> 128.9).
     void split_step_tail() {
-        if (!latency_lanes() || getenv("OAC_NO_TAIL_SPLIT")) return;                                      // (env: A/B measurement aid)
+        // many-seed program: the ticket + last-CTA tail costs policy_head 6 us with 8 seeds (12 us with 64); as a kernel of its
+        // own on lane 2 it overlaps the critics' forward.  Pays for small groups (8 seeds: 217.1 -> 213.7 us per step); with
+        // 64 seeds the extra launch and the fork / join cancel it (0.798 vs 0.800 ms), so: up to 16 seeds.
+        const bool small_group = tensor_glue && t.allow_lanes && c.n_seeds <= 16;
+        if (!(latency_lanes() || small_group) || getenv("OAC_NO_TAIL_SPLIT")) return;                      // (env: A/B measurement aid)
         t.stages.back().php.tail_in_own_kernel = 1;
         Stage head = t.stages.back();
         Stage& s = add_stage(ST_STEP_TAIL, "alpha+step_counters"); s.lane = 2; s.ph = head.ph; s.php = head.php;
