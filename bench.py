@@ -315,7 +315,7 @@ class _Single(object):
         batch['buffer'] = self.rb
         self.tr.train(batch)                     # fused step (CUDA graph)
 
-    api = "ReplayBuffer.random_batch(256) + SACTrainer.train(batch) + stream sync + host read of the step scalars, every step"
+    api = "ReplayBuffer.random_batch(256) + SACTrainer.train(batch) + host read of the step's scalars, every step"
 
 
 class _Group(object):
@@ -334,7 +334,7 @@ class _Group(object):
         self.grp.gather(self.rb, np.random.randint(0, N_REPLAY, (self.S, B)))
         self.grp.step()
 
-    api = "SACSeedGroup.gather(replay, host indices [S,256]) + .step() + stream sync + host read of the per-seed scalars, every step"
+    api = "SACSeedGroup.gather(replay, host indices [S,256]) + .step() + host read of the per-seed scalars, every step"
 
 
 def timed_loops(w, K, W, dev, barrier, clocks=None, check_scalar=True):
@@ -356,8 +356,13 @@ def timed_loops(w, K, W, dev, barrier, clocks=None, check_scalar=True):
     barrier()
     ms_dev = ev0.elapsed_time(ev1)
     # end to end: every step, host index draw -> pinned -> update -> the step's scalars (alpha, alpha loss, mean log pi per
-    # seed) land in the engine's mapped pinned host tensor -> synchronise -> the host reads them before the next step
-    host_sc = w.engine.host_scalars
+    # seed, the step's number) land in the engine's mapped pinned host tensor -> the host reads them.
+    #   blocking : synchronise after every step and read its scalars before the next one is issued;
+    #   pipelined: the reference's training loop (rl_algorithm.py:159-165: random_batch -> trainer.train, nothing waits on
+    #              a step) with the per-step host read kept: while step i runs, the host draws and enqueues step i + 1,
+    #              then waits for step i's event and reads ITS scalars (two mapped slots, stamped with the step number).
+    #              Every step's inputs still go host -> device and every step's result is still read inside the region.
+    eng = w.engine
     acc = 0.0
     for _ in range(W):
         w.api_step(); stream.synchronize()
@@ -367,15 +372,35 @@ def timed_loops(w, K, W, dev, barrier, clocks=None, check_scalar=True):
     for _ in range(K):
         w.api_step()
         stream.synchronize()
-        acc += float(host_sc[0, 0])
+        acc += float(eng.step_scalars()[0, 0])
+    ev1.record(stream)
+    barrier()
+    ms_block = max(ev0.elapsed_time(ev1), 1000.0 * (time.perf_counter() - t0))
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    stamps_ok = True
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for i in range(K):
+        w.api_step()
+        done[i & 1].record(stream)
+        if i:
+            done[(i - 1) & 1].synchronize()
+            sc = eng.step_scalars(eng.steps - 1)
+            acc += float(sc[0, 0])
+            stamps_ok &= int(sc[0, 3]) == eng.steps - 1
+    done[(K - 1) & 1].synchronize()
+    sc = eng.step_scalars(eng.steps)
+    acc += float(sc[0, 0])
+    stamps_ok &= int(sc[0, 3]) == eng.steps
     ev1.record(stream)
     barrier()
     ms_e2e = max(ev0.elapsed_time(ev1), 1000.0 * (time.perf_counter() - t0))
     if clocks:
         clocks.mark_load(False)
+    assert stamps_ok, "a pipelined read saw another step's scalars"
     if check_scalar:
         assert acc == acc and acc > 0.0, "the step's scalars never reached the host"
-    return ms_dev, ms_e2e, idx_all
+    return ms_dev, ms_e2e, ms_block, idx_all
 
 
 def stage_profile(engine, iters):
@@ -506,9 +531,9 @@ def run_ours(args):
     else:
         w = _Group([rank + world * i for i in range(S)], rb, gp)
     e = w.engine
-    ms_dev, ms_e2e, idx_all = timed_loops(w, K, W, dev, barrier, clocks, check_scalar=args.algo != "goac")
-    ms_dev, ms_e2e = max_over_ranks([ms_dev, ms_e2e])
-    launches = (e.launches_per_step + 1) * K * 2
+    ms_dev, ms_e2e, ms_block, idx_all = timed_loops(w, K, W, dev, barrier, clocks, check_scalar=args.algo != "goac")
+    ms_dev, ms_e2e, ms_block = max_over_ranks([ms_dev, ms_e2e, ms_block])
+    launches = (e.launches_per_step + 1) * K * 3
 
     # ---------------- BASELINE config 5 at every N: 64 seeds in total, 64 / N per GPU, TF32 ----------------
     batched = None
@@ -518,9 +543,9 @@ def run_ours(args):
         rb.attach(None)
         wg = _Group(ids, rb, GEMM_PATHS["tf32"])
         Kb = max(10, min(K, 200))
-        b_dev, b_e2e, idx_b = timed_loops(wg, Kb, max(3, min(W, 10)), dev, barrier, clocks)
-        b_dev, b_e2e = max_over_ranks([b_dev, b_e2e])
-        launches += (wg.engine.launches_per_step + 1) * Kb * 2
+        b_dev, b_e2e, b_block, idx_b = timed_loops(wg, Kb, max(3, min(W, 10)), dev, barrier, clocks)
+        b_dev, b_e2e, b_block = max_over_ranks([b_dev, b_e2e, b_block])
+        launches += (wg.engine.launches_per_step + 1) * Kb * 3
         # the only collective of the design: every seed's statistics vector, gathered after the timed regions
         stats = allgather_stats(wg.grp.stats(), ids, total)
         assert stats.shape[0] == total and bool(torch.isfinite(stats).all())
@@ -531,7 +556,8 @@ def run_ours(args):
                    "total_seeds": total, "seeds_per_gpu": Sg, "n_gpus": world, "gemm_path": "tf32", "scaling": "strong",
                    "value": total * Kb / (b_dev * 1e-3), "unit": "seed-updates/s", "ms_per_step": ms_b, "steps": Kb,
                    "e2e": {"value": total * Kb / (b_e2e * 1e-3), "unit": "seed-updates/s", "ms_per_step": b_e2e / Kb,
-                           "h2d_bytes_per_step": Sg * B * 8, "d2h_bytes_per_step": Sg * 12, "api": wg.api},
+                           "h2d_bytes_per_step": Sg * B * 8, "d2h_bytes_per_step": Sg * 16, "api": wg.api,
+                           "blocking_value": total * Kb / (b_block * 1e-3), "blocking_ms_per_step": b_block / Kb},
                    "launches_per_step": wg.engine.launches_per_step + 1, "tma_tcgen05_stages": wg.engine.ws_stages,
                    "stats_allgather": {"seeds": total, "floats_per_seed": int(stats.shape[1]),
                                        "collective": "nccl all_gather" if world > 1 else "none (one rank)"},
@@ -639,9 +665,14 @@ def run_ours(args):
                            "cuda_graph": True, "host_cores_per_rank": cores},
                 "clocks": clk,
                 "e2e": {"value": n_seeds * K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": S * B * 8,
-                        "d2h_bytes_per_step": S * 12, "ms_per_step": ms_e2e / K, "api": w.api,
+                        "d2h_bytes_per_step": S * 16, "ms_per_step": ms_e2e / K, "api": w.api,
+                        "blocking_value": n_seeds * K / (ms_block * 1e-3), "blocking_ms_per_step": ms_block / K,
+                        "pipelining": "value: the host enqueues step i+1 (index draw, gather, update) while step i runs, then "
+                                      "waits for step i's event and reads its scalars (two mapped slots stamped with the step "
+                                      "number, checked) -- the reference's loop never blocks on a step (rl_algorithm.py:159-165); "
+                                      "blocking_value: stream synchronise + read after EVERY step before the next is issued",
                         "transfers": "indices: pinned host ring read by the gather kernel (single seed) / pinned -> H2D copy "
-                                     "(seed group); result: 3 scalars per seed stored by the step into mapped pinned host memory"},
+                                     "(seed group); result: 4 scalars per seed stored by the step into mapped pinned host memory"},
                 "gpu_launches": launches,
                 "launches_per_step": e.launches_per_step + 1}
         if roof is not None:

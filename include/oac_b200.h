@@ -41,7 +41,8 @@
 extern "C" {
 #endif
 
-#define OAC_ABI_VERSION 3
+#define OAC_ABI_VERSION 4
+#define OAC_HOST_SCALAR_SLOTS 2
 #define OAC_MAX_NETS 48
 
 enum { OAC_E_INVALID = -1, OAC_E_UNSUPPORTED = -2, OAC_E_NOMEM = -3 };
@@ -132,9 +133,12 @@ typedef struct OacBuffers {
     float* work;      /* [n_seeds, work_floats]  */
     float* io;        /* [n_seeds, io_floats]    */
     int32_t* counters;/* [n_seeds, n_counters]   */
-    float* host_scalars; /* optional (may be NULL): [n_seeds, 16] MAPPED PINNED HOST memory; every step also stores its
-                          * scalars (slot 0 alpha, 1 alpha loss, 2 mean log pi) there, so a caller that wants the step's
-                          * result on the host only has to synchronise the stream (no device-to-host copy call) */
+    float* host_scalars; /* optional (may be NULL): [OAC_HOST_SCALAR_SLOTS, n_seeds, 16] MAPPED PINNED HOST memory; every
+                          * step also stores its scalars (0 alpha, 1 alpha loss, 2 mean log pi, 3 the 1-based number of the
+                          * step that wrote them) into slot (steps taken before it) % 2, so a caller that wants the step's
+                          * result on the host only has to wait for the step (no device-to-host copy call) and may keep
+                          * one further step in flight while it reads (the training loop of rl_algorithm.py:159-165 never
+                          * blocks on a step) */
 } OacBuffers;
 
 typedef struct OacTrainer OacTrainer;   /* opaque */

@@ -136,7 +136,7 @@ def lib():
     L.oac_policy_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.oac_q_forward.argtypes = [vp, C.POINTER(OacNetLayout), vp, i32, i32, u32, vp, vp]
     L.oac_explore.argtypes = [C.POINTER(OacExploreArgs), vp]
-    if L.oac_abi_version() != 3:
+    if L.oac_abi_version() != 4:
         raise RuntimeError("liboac_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -68,7 +68,8 @@ struct PolicyHeadParams {
     int n_opt_counters;      // counters CNT_OPT0 .. CNT_OPT0+n-1 are bumped once per step here
     int iters;               // row groups (of GLUE_SPC rows) per CTA
     int head_from_gemm;      // 1: the head layer ran as a tensor-core GEMM stage; this kernel only samples
-    float* host_scalars;     // optional mapped pinned host copy of the step's scalars, [n_seeds, SC_COUNT]
+    float* host_scalars;     // optional mapped pinned host copy of the step's scalars, [2][n_seeds, SC_COUNT] (slot = step parity)
+    int n_seeds;
     int tail_in_own_kernel;  // 1: policy_head ends at its last store; step_tail_kernel follows on a side lane
 };
 
@@ -114,9 +115,12 @@ __device__ __forceinline__ void step_tail(const PolicyHeadParams& p, int seed) {
             sc[SC_ALPHA] = 0.f;              // the fork's choice (trainer.py:148-149)
             sc[SC_ALPHA_LOSS] = 0.f;
         }
-        if (p.host_scalars != nullptr) {     // zero-copy device -> host: the caller only synchronises
-            float* hs = p.host_scalars + (long long)seed * SC_COUNT;
+        if (p.host_scalars != nullptr) {     // zero-copy device -> host: the caller only waits for the step
+            // two slots, chosen by the parity of the step index, each stamped with the number of the step that wrote it: a
+            // caller that runs one step ahead of the device reads step i's scalars while step i + 1 is in flight
+            float* hs = p.host_scalars + ((long long)(step & 1) * p.n_seeds + seed) * SC_COUNT;
             hs[SC_ALPHA] = sc[SC_ALPHA]; hs[SC_ALPHA_LOSS] = sc[SC_ALPHA_LOSS]; hs[SC_MEAN_LOGPI] = sc[SC_MEAN_LOGPI];
+            hs[SC_STEP_STAMP] = (float)(step + 1);
         }
     }
 }

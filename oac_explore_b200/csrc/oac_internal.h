@@ -42,7 +42,7 @@ enum Counter {
 };
 
 // ---- scalars slot (io[off_scalars + i]) ----
-enum Scalar { SC_ALPHA = 0, SC_ALPHA_LOSS = 1, SC_MEAN_LOGPI = 2, SC_COUNT = 16 };
+enum Scalar { SC_ALPHA = 0, SC_ALPHA_LOSS = 1, SC_MEAN_LOGPI = 2, SC_STEP_STAMP = 3, SC_COUNT = 16 };
 
 // ---- GEMM stage ----
 enum Epilogue {

@@ -467,7 +467,7 @@ struct Builder {
         p.alpha.log_alpha = P(la.off_w0); p.alpha.adam_off = la.off_w0;
         p.alpha.lr = c.policy_lr; p.alpha.target_entropy = c.target_entropy; p.alpha.counter = alpha_counter;
         p.head_from_gemm = tensor_glue ? 1 : 0;
-        p.host_scalars = t.host_scalars;
+        p.host_scalars = t.host_scalars; p.n_seeds = c.n_seeds;
     }
     void fill_chp(Stage& s, int mode, int n_nets) {
         CriticHeadParams& p = s.chp;

@@ -52,9 +52,12 @@ class Engine(object):
         self.params, self.adam_m, self.adam_v = z(L.param_floats), z(L.adam_floats), z(L.adam_floats)
         self.work, self.io = z(L.work_floats), z(L.io_floats)
         self.counters = torch.zeros((S, L.n_counters), dtype=torch.int32, device=self.device)
-        # the step also stores its scalars (alpha, alpha loss, mean log pi) into this mapped pinned host tensor:
-        # valid after a synchronisation of the stream the step ran on
-        self.host_scalars = torch.zeros((S, 16), dtype=torch.float32).pin_memory()
+        # the step also stores its scalars (alpha, alpha loss, mean log pi, its own 1-based step number) into this mapped
+        # pinned host tensor, slot = parity of the steps taken before it: valid once the step has completed (an event or a
+        # stream synchronisation), and still intact while the NEXT step is in flight (``step_scalars``)
+        self.host_scalars = torch.zeros((2, S, 16), dtype=torch.float32).pin_memory()
+        self._host_scalars_np = self.host_scalars.numpy()
+        self.steps = 0               # host mirror of the device's train-step counter (CNT_TRAIN_STEPS, equal for all seeds)
         buf = OacBuffers(_lib.ptr(self.params), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
                          _lib.ptr(self.work), _lib.ptr(self.io), _lib.ptr(self.counters), _lib.ptr(self.host_scalars))
         h = C.c_void_p()
@@ -141,8 +144,22 @@ class Engine(object):
             e[1].copy_(eps_next)
 
     def step(self, external_eps=False):
-        _lib.check(self.lib.oac_trainer_step(self.handle, 1 if external_eps else 0, _lib.current_stream()),
-                   "oac_trainer_step")
+        rc = self.lib.oac_trainer_step(self.handle, 1 if external_eps else 0, _lib.current_stream())
+        if rc:
+            _lib.check(rc, "oac_trainer_step")
+        self.steps += 1
+
+    def set_train_steps(self, n):
+        """Set the device's train-step counter of every seed (snapshot restore) together with its host mirror."""
+        self.counters[:, _lib.CNT_TRAIN_STEPS] = int(n)
+        self.steps = int(n)
+
+    def step_scalars(self, step=None):
+        """[n_seeds, 16] numpy view of the scalars written by the 1-based train step ``step`` (default: the last one
+        enqueued): 0 alpha, 1 alpha loss, 2 mean log pi, 3 the step number.  The caller waits for that step first (event
+        or stream synchronisation); one later step may be in flight meanwhile (two slots)."""
+        step = self.steps if step is None else step
+        return self._host_scalars_np[(step - 1) & 1]
 
     def stats_device(self, out=None):
         """[n_seeds, n_stats] fp32 DEVICE tensor: the ``eval_statistics`` vector of every seed for the last step, reduced
@@ -172,4 +189,5 @@ class Engine(object):
         n = C.c_int32(0)
         _lib.check(self.lib.oac_trainer_profile(self.handle, iters, n_max, ms, isg, fl, names, C.byref(n),
                                                 _lib.current_stream()), "oac_trainer_profile")
+        self.steps = int(self.counters[0, _lib.CNT_TRAIN_STEPS].item())     # the profile loop ran whole steps
         return [(names[i].decode(), float(ms[i]), bool(isg[i]), float(fl[i])) for i in range(n.value)]

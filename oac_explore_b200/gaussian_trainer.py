@@ -159,7 +159,7 @@ class GaussianTrainer(_EngineTrainer):
         self.log_alpha.copy_(torch.as_tensor(ss['log_alpha']).to(self.log_alpha.device).reshape(1))
         self.eval_statistics = ss['eval_statistics']
         self._n_train_steps_total = ss['_n_train_steps_total']
-        self._engine.counters[0, _lib.CNT_TRAIN_STEPS] = int(self._n_train_steps_total)
+        self._engine.set_train_steps(self._n_train_steps_total)
         self._need_to_update_eval_statistics = ss['_need_to_update_eval_statistics']
         self.target_policy.load_state_dict(ss["target_policy_state_dict"])
         self.target_policy_optimizer.load_state_dict(ss["target_policy_opt_state_dict"])

@@ -152,7 +152,7 @@ class ParticleTrainer(_EngineTrainer):
             self.alpha_optimizer.load_state_dict(ss['alpha_optim_state_dict'])
         self.eval_statistics = ss['eval_statistics']
         self._n_train_steps_total = ss['_n_train_steps_total']
-        self._engine.counters[0, _lib.CNT_TRAIN_STEPS] = int(self._n_train_steps_total)
+        self._engine.set_train_steps(self._n_train_steps_total)
         self._need_to_update_eval_statistics = ss['_need_to_update_eval_statistics']
 
 

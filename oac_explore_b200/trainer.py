@@ -104,6 +104,7 @@ class _EngineTrainer(object):
             net._bind(new.net_views(idx), new.params[0], new.net_layout(idx))
         if old is not None:
             new.adam_m.copy_(old.adam_m), new.adam_v.copy_(old.adam_v), new.counters.copy_(old.counters)
+            new.steps = old.steps
             la_old, la_new = old.net_views(self._log_alpha_index), new.net_views(self._log_alpha_index)
             la_new['log_alpha'].copy_(la_old['log_alpha'])
         self._engine = new
@@ -288,5 +289,5 @@ class SACTrainer(_EngineTrainer):
             self.alpha_optimizer.load_state_dict(ss['alpha_optim_state_dict'])
         self.eval_statistics = ss['eval_statistics']
         self._n_train_steps_total = ss['_n_train_steps_total']
-        self._engine.counters[0, _lib.CNT_TRAIN_STEPS] = int(self._n_train_steps_total)
+        self._engine.set_train_steps(self._n_train_steps_total)
         self._need_to_update_eval_statistics = ss['_need_to_update_eval_statistics']

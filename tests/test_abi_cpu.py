@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert set(_lib.EXPORTS) == set(names)
-    assert L.oac_abi_version() == 3
+    assert L.oac_abi_version() == 4
 
 
 def test_ctypes_structs_match_header_sizes():

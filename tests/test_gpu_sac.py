@@ -265,3 +265,49 @@ def test_fused_forward_layers_match_separate_launches(monkeypatch, H):
         a, b = net_cpu(getattr(trainers[0], n)), net_cpu(getattr(trainers[1], n))
         for k in a:
             assert torch.equal(a[k], b[k]), (n, k)
+
+
+def test_step_scalars_ring_one_step_in_flight():
+    """The step's host scalars go to two mapped slots chosen by step parity and stamped with the step number: the host may
+    read step i's scalars (after ITS event) while step i + 1 is already in flight; values equal the blocking read."""
+    O, A, H, B = 17, 6, 64, 64
+    torch.manual_seed(3)
+    tr = make_trainer(O, A, H)
+    batches = [{k: v.cuda() for k, v in synth_batch(B, O, A, seed=40 + s).items()} for s in range(7)]
+    # blocking pass on a twin trainer: the expected per-step alpha
+    torch.manual_seed(3)
+    tw = make_trainer(O, A, H)
+    want = []
+    for s, b in enumerate(batches):
+        eps = synth_eps(2, B, A, seed=900 + s)
+        tw.inject_noise(eps[0], eps[1])
+        tw.train_from_torch(dict(b))
+        torch.cuda.synchronize()
+        sc = tw._engine.step_scalars()
+        assert int(sc[0, 3]) == s + 1
+        want.append((float(sc[0, 0]), float(sc[0, 1]), float(sc[0, 2])))
+    tr._ensure_engine(B)
+    eng = tr._engine
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(), torch.cuda.Event()]
+    got = []
+    for s, b in enumerate(batches):
+        eps = synth_eps(2, B, A, seed=900 + s)
+        tr.inject_noise(eps[0], eps[1])
+        tr.train_from_torch(dict(b))
+        ev[s & 1].record(stream)
+        if s:
+            ev[(s - 1) & 1].synchronize()
+            sc = eng.step_scalars(eng.steps - 1)
+            assert int(sc[0, 3]) == s
+            got.append((float(sc[0, 0]), float(sc[0, 1]), float(sc[0, 2])))
+    ev[(len(batches) - 1) & 1].synchronize()
+    sc = eng.step_scalars()
+    assert int(sc[0, 3]) == len(batches)
+    got.append((float(sc[0, 0]), float(sc[0, 1]), float(sc[0, 2])))
+    assert got == want
+    # a restored step counter moves the host mirror with it
+    eng.set_train_steps(100)
+    tr.train_from_torch(dict(batches[0]))
+    torch.cuda.synchronize()
+    assert int(eng.step_scalars()[0, 3]) == 101 and eng.steps == 101

@@ -16,9 +16,16 @@ for _ in range(200):
 def loop(n):
     acc = 0.0
     for _ in range(n):
-        w.api_step(); stream.synchronize(); acc += float(hs[0, 0])
+        w.api_step(); stream.synchronize(); acc += float(hs[(w.engine.steps - 1) & 1, 0, 0])
     return acc
 t0 = time.perf_counter(); loop(3000); dt = (time.perf_counter() - t0) / 3000
-print("e2e %.1f us/step" % (dt * 1e6))
+print("e2e (blocking) %.1f us/step" % (dt * 1e6))
+stream.synchronize()
+t0 = time.perf_counter()
+for _ in range(400):
+    w.api_step()
+dt = (time.perf_counter() - t0) / 400
+stream.synchronize()
+print("host enqueue only (no wait, 400 steps run ahead) %.1f us/step" % (dt * 1e6))
 pr = cProfile.Profile(); pr.enable(); loop(3000); pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(18)
