@@ -7,7 +7,8 @@
 //     cp.async.bulk.tensor.3d through a per-task tensor map ([seed][row][col] view of the arena), 32 k per
 //     pipeline slot, straight into the canonical UMMA layouts -- SWIZZLE_128B for K-contiguous operands,
 //     SWIZZLE_128B_ATOM_32B for the M/N-contiguous ones (dX and dW products), so transposed copies never
-//     exist.  The maps use the TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 to nearest while it
+//     exist (an M/N-contiguous operand is described as [seed][32-wide atom][k][32]: ONE box fetches all atoms of a tile's
+//     chunk -- per-atom boxes made these stages 1.5x slower than K-major ones).  The maps use the TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 to nearest while it
 //     copies (measured: tools/probes/tma_probe.cu), which removes the MMA's truncation bias without any
 //     rounding pass over shared memory or rounded copies of the weights.  Ragged M / N / K edges are
 //     zero-filled by the TMA bounds check.
@@ -29,6 +30,8 @@ constexpr int WS_BM = 128;
 constexpr int WS_KC = 32;                        // k per pipeline slot = one 128-byte swizzle row
 constexpr int WS_EPI_WARPS = 8;
 constexpr int WS_THREADS = (2 + WS_EPI_WARPS) * 32;
+// Register budget: 10 warps = 3 warps on two of the four SM sub-partitions (16384 registers each), so a thread gets at most
+// 16384 / 96 = 168 registers (a kernel compiled for more fails to launch): the epilogues below are written to stay under it.
 constexpr int WS_SLAB = 64;                      // columns per epilogue slab
 constexpr int WS_SLAB_LD = 68;                   // floats; 16-byte aligned rows, conflict-free v4 stores (lane = row)
 constexpr int WS_MAX_TASKS = 64;
@@ -161,12 +164,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                     const uint32_t bar = smem_u32(&s_full[slot]);
                     mbar_expect_tx(bar, bytes);
                     if (!A_MN) tma_load_3d(sa, ta, c * WS_KC, m0, seed, bar);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < WS_BM / 32; ++i) tma_load_3d(sa + i * 4096, ta, m0 + 32 * i, c * WS_KC, seed, bar);
-                    }
+                    else tma_load_4d(sa, ta, 0, c * WS_KC, m0 >> 5, seed, bar);          // all 32-wide atoms of the tile in one box
                     if (!B_MN) tma_load_3d(sb, tb, c * WS_KC, n0, seed, bar);
-                    else for (int i = 0; i < (bn >> 5); ++i) tma_load_3d(sb + i * 4096, tb, n0 + 32 * i, c * WS_KC, seed, bar);
+                    else tma_load_4d(sb, tb, 0, c * WS_KC, n0 >> 5, seed, bar);
                     if (++slot == wp.n_slots) { slot = 0; ph ^= 1u; }
                 }
             }
@@ -260,18 +260,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
             const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
             for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
                 const int c0 = sl * WS_SLAB;
-                // ReLU-mask epilogue: all 16 mask loads of this lane fly while the accumulator is read back and
-                // transposed (one at a time they cost a DRAM latency each: 21 us per K=1 tile before this)
-                float4 k4[16];
+                // ReLU-mask epilogue.  One mask load at a time costs a DRAM latency each (21 us per K=1 tile, round 1); all 16
+                // float4 of this lane requested before the accumulator read-back hide the latency but, together with the 32
+                // accumulator registers and the 8 prefetched slab rows, exceed the 168-register budget: ptxas spilled into the
+                // store loop and this instantiation spent 12 us per 128 x 256 tile in its epilogue whatever K (5 us in the
+                // forward kernel; ncu source page: the stores waiting on local-memory reloads).  So: two batches of 8 row
+                // pairs, each reduced to sign bits as soon as it is consumed -- batch A flies during the read-back, batch B
+                // during batch A's stores.
+                float4 kq[8];
                 const bool mask_vec = mask != nullptr && (n0 + c0 + c4 + 3 < nlim);
-                if (mask_vec) {
+                auto load_masks = [&](int rp0) {
 #pragma unroll
-                    for (int rp = 0; rp < 16; ++rp) {
-                        const int m = m0 + q * 32 + 2 * rp + rsub;
-                        k4[rp] = (m < M) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n0 + c0 + c4))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < 8; ++r) {
+                        const int m = m0 + q * 32 + 2 * (rp0 + r) + rsub;
+                        kq[r] = (m < M) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n0 + c0 + c4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                }
+                };
+                auto pack_masks = [&]() {
+                    uint32_t b = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        b |= ((kq[r].x > 0.f ? 1u : 0u) | (kq[r].y > 0.f ? 2u : 0u) | (kq[r].z > 0.f ? 4u : 0u) | (kq[r].w > 0.f ? 8u : 0u)) << (4 * r);
+                    return b;
+                };
+                if (mask_vec) load_masks(0);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {                 // 32 columns at a time: 32 live registers
                     if (c0 + 32 * hf >= bn) break;
@@ -338,30 +351,42 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
                             if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
                             else { b4.x = __ldg(bias + n); if (n + 1 < nlim) b4.y = __ldg(bias + n + 1); if (n + 2 < nlim) b4.z = __ldg(bias + n + 2); }
                         }
+                        uint32_t mbits = 0xffffffffu;
+                        if (mask_vec) {
+                            mbits = pack_masks();
+                            asm volatile("" ::: "memory");       // batch B is requested only now: its registers replace batch A's
+                            load_masks(8);
+                        }
+                        auto store_rows = [&](int rp0) {
 #pragma unroll
-                        for (int rp = 0; rp < 16; ++rp) {
-                            const int row = 2 * rp + rsub, m = m0 + q * 32 + row;
-                            if (m >= M) continue;
-                            float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
-                            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                            if (epi == EPI_BIAS_RELU) { x.x = relu(x.x); x.y = relu(x.y); x.z = relu(x.z); x.w = relu(x.w); }
-                            float* dst = C + (long long)m * ldc + n;
-                            if (vec) {
-                                if (mask != nullptr) {
-                                    x.x = k4[rp].x > 0.f ? x.x : 0.f; x.y = k4[rp].y > 0.f ? x.y : 0.f;
-                                    x.z = k4[rp].z > 0.f ? x.z : 0.f; x.w = k4[rp].w > 0.f ? x.w : 0.f;
-                                }
-                                *reinterpret_cast<float4*>(dst) = x;
-                            } else {
+                            for (int r = 0; r < 8; ++r) {
+                                const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
+                                if (m >= M) continue;
+                                float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
+                                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                                if (epi == EPI_BIAS_RELU) { x.x = relu(x.x); x.y = relu(x.y); x.z = relu(x.z); x.w = relu(x.w); }
+                                float* dst = C + (long long)m * ldc + n;
+                                if (vec) {
+                                    if (CAN_MASK) {
+                                        const uint32_t nb = mbits >> (4 * r);
+                                        x.x = (nb & 1u) ? x.x : 0.f; x.y = (nb & 2u) ? x.y : 0.f;
+                                        x.z = (nb & 4u) ? x.z : 0.f; x.w = (nb & 8u) ? x.w : 0.f;
+                                    }
+                                    *reinterpret_cast<float4*>(dst) = x;
+                                } else {
 #pragma unroll
-                                for (int jj = 0; jj < 3; ++jj) {
-                                    if (n + jj >= nlim) continue;
-                                    float y = jj == 0 ? x.x : (jj == 1 ? x.y : x.z);
-                                    if (mask != nullptr) y = __ldg(mask + (long long)m * ldmask + n + jj) > 0.f ? y : 0.f;
-                                    dst[jj] = y;
+                                    for (int jj = 0; jj < 3; ++jj) {
+                                        if (n + jj >= nlim) continue;
+                                        float y = jj == 0 ? x.x : (jj == 1 ? x.y : x.z);
+                                        if (mask != nullptr) y = __ldg(mask + (long long)m * ldmask + n + jj) > 0.f ? y : 0.f;
+                                        dst[jj] = y;
+                                    }
                                 }
                             }
-                        }
+                        };
+                        store_rows(0);
+                        if (mask_vec) mbits = pack_masks();
+                        store_rows(8);
                     }
                 }
                 __syncwarp();                                    // slab is rewritten by the next pass

@@ -43,6 +43,11 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -126,12 +131,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws2_kernel(WsParams wp) {
                     const uint32_t bar = mapa_u32(smem_u32(&s_full[slot]), 0);     // the LEADER's full barrier
                     if (rank == 0) mbar_expect_tx(smem_u32(&s_full[slot]), 2 * bytes);
                     if (!A_MN) tma_load_3d_2sm(sa, ta, c * WS_KC, m0, seed, bar);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < WS_BM / 32; ++i) tma_load_3d_2sm(sa + i * 4096, ta, m0 + 32 * i, c * WS_KC, seed, bar);
-                    }
+                    else tma_load_4d_2sm(sa, ta, 0, c * WS_KC, m0 >> 5, seed, bar);      // all 32-wide atoms of the tile in one box
                     if (!B_MN) tma_load_3d_2sm(sb, tb, c * WS_KC, n0, seed, bar);
-                    else for (int i = 0; i < (bnh >> 5); ++i) tma_load_3d_2sm(sb + i * 4096, tb, n0 + 32 * i, c * WS_KC, seed, bar);
+                    else tma_load_4d_2sm(sb, tb, 0, c * WS_KC, n0 >> 5, seed, bar);
                     if (++slot == wp.n_slots) { slot = 0; ph ^= 1u; }
                 }
             }

@@ -165,6 +165,7 @@ struct Stage {
     // position where it is listed (and for its own lane's earlier stages).  `join` is a bit mask of the side lanes the
     // main lane waits for before this stage (bit 0: lane 1, bit 1: lane 2); everything is joined at the end of the step.
     int lane = 0, join = 0;
+    int sm_budget = 0;          // > 0: the persistent tcgen05 grid of this stage is planned for this many SMs (it shares the chip with a side lane)
     const char* name = "";
 };
 
@@ -198,6 +199,10 @@ struct OacTrainer {
 
 namespace oac {
 
+// floats of slack after the last work-arena buffer: a TMA box over a ragged 32-column atom of an M/N-contiguous operand
+// reads up to 31 floats past the operand's last row (ws_plan)
+constexpr long long WORK_SLACK = 32;
+
 struct Builder {
     OacTrainer& t;
     const OacConfig& c;
@@ -228,8 +233,19 @@ struct Builder {
         sg.lr = lr; sg.counter = CNT_OPT0 + counter;
         pending_segs.push_back(sg);
     }
-    void flush_adam(const char* name) {
-        if (!split_adam || pending_segs.empty()) return;
+    // part of a net: fc0 (weight + bias) or the rest (fc1 .. last bias) -- both are contiguous blocks of the arena
+    void adam_seg_part(int ni, int ti, float lr, int counter, bool fc0) {
+        if (!split_adam) return;
+        const OacNetLayout& n = net(ni);
+        AdamSeg sg;
+        const long long lo = fc0 ? n.off_w0 : n.off_w1, hi = fc0 ? n.off_w1 : n.off_w0 + n.size;
+        sg.off = lo; sg.len = hi - lo; sg.grad_off = grad.off + lo;
+        sg.target_off = ti >= 0 ? net(ti).off_w0 + (lo - n.off_w0) : -1;
+        sg.lr = lr; sg.counter = CNT_OPT0 + counter;
+        pending_segs.push_back(sg);
+    }
+    Stage* flush_adam(const char* name) {
+        if (!split_adam || pending_segs.empty()) return nullptr;
         Stage& s = add_stage(ST_ADAM, name);
         memset(&s.asp, 0, sizeof(s.asp));
         s.asp.n_seg = (int)pending_segs.size();
@@ -237,6 +253,7 @@ struct Builder {
         for (size_t i = 0; i < pending_segs.size(); ++i) { s.asp.seg[i] = pending_segs[i]; tot += pending_segs[i].len >> 2; }
         s.asp.total4 = tot;
         pending_segs.clear();
+        return &s;
     }
     Ref work(long long n) {
         Ref r{AR_WORK, t.work_cursor};
@@ -592,6 +609,14 @@ void Builder::build_sac() {
       // mode A (torch 1.4) multiplies by the POST-step W3 -> separate stage after the critic Adam
       if (mode_b) s.chp.src[0].write_dh2 = s.chp.src[1].write_dh2 = 1;
       s.chp.n_src = 6; fill_chp(s, CM_SAC, 2); }
+    // Small groups on the tensor path, mode A (every stage is ONE round of tiles, i.e. pure per-tile latency: DESIGN 6): the
+    // policy-loss backward through the critics needs only the POST-step fc1 / head weights for its first two stages, and those
+    // gradients are complete after critic_head.  Lane 1: dW(fc1, head) -> their Adam -> pi_dh2 -> pi_dh1, next to the main
+    // lane's qloss_dh1 -> dW(fc0) -> its Adam; the lanes meet at pi_da.  The GEMM stages of the two branches are planned
+    // for half of the SMs each so that they really run side by side.  OAC_GROUP_LANES=0 restores the linear order (A/B aid).
+    static const int gl_max = getenv("OAC_GROUP_LANES") ? atoi(getenv("OAC_GROUP_LANES")) : 16;
+    const bool group_lanes = tensor_glue && split_adam && t.allow_lanes && !mode_b && (H & 3) == 0 && c.n_seeds <= gl_max;
+    const int half = sm_count() / 2;
     if (two_lanes && !mode_b) {
         // mode A: pi_dh2 needs the POST-step head weights, and the head gradient (dq^T h2) is complete after critic_head:
         // head Adam + pi_dh2 leave the critical chain for lane 2 and run next to qloss_dh1 / the fc1 Adam
@@ -599,10 +624,20 @@ void Builder::build_sac() {
           crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 4); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 4); }
         { Stage& s = add_stage(ST_GEMM, "pi_dh2"); s.lane = 2; crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
     }
+    if (group_lanes) {
+        // (listed before qloss_dh1: a side-lane stage waits for the main lane's position where it is listed)
+        { Stage& s = add_stage(ST_GEMM, "critic_adam_fc1+head"); s.lane = 1; s.sm_budget = half;
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 6); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 6);
+          adam_seg_part(q1, t1, c.qf_lr, 1, false); adam_seg_part(q2, t2, c.qf_lr, 2, false); }
+        if (Stage* a = flush_adam("critic_adam_apply_fc1+head")) a->lane = 1;
+        { Stage& s = add_stage(ST_RANK1, "pi_dh2"); s.lane = 1; crit_dh2_rank1(s, q1, ca1, 0); crit_dh2_rank1(s, q2, ca2, 0); }
+        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); s.lane = 1; s.sm_budget = half; crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
+    }
     { Stage& s = add_stage(ST_GEMM, "qloss_dh1"); crit_dh1(s, q1, ca1, B); crit_dh1(s, q2, ca2, B);
+      if (group_lanes) s.sm_budget = half;
       if (mode_b) { crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); } }
     auto policy_grad_stage = [&]() {
-        if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
+        if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); sd.join = group_lanes ? 1 : 0; crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
         Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
         s.join = 3;
         s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic, {ca1.da, ca2.da}));
@@ -618,12 +653,19 @@ void Builder::build_sac() {
           crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 1); }
         { Stage& s = add_stage(ST_GEMM, "critic_adam_fc1");
           crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 2); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 2); }
+    } else if (group_lanes) {
+        { Stage& s = add_stage(ST_GEMM, "critic_adam_fc0"); s.sm_budget = half;
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2, 1);
+          adam_seg_part(q1, t1, c.qf_lr, 1, true); adam_seg_part(q2, t2, c.qf_lr, 2, true); }
+        flush_adam("critic_adam_apply_fc0");
     } else {
-    { Stage& s = add_stage(ST_GEMM, "critic_adam");
-      crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
-    flush_adam("critic_adam_apply");
+        { Stage& s = add_stage(ST_GEMM, "critic_adam");
+          crit_adam(s, q1, t1, ca1, B, 2, c.qf_lr, 1); crit_adam(s, q2, t2, ca2, B, 2, c.qf_lr, 2); }
+        flush_adam("critic_adam_apply");
     }
-    if (!mode_b) {
+    if (!mode_b && group_lanes) {
+        policy_grad_stage();                   // pi_da joins lane 1
+    } else if (!mode_b) {
         if (!two_lanes && tensor_glue && (H & 3) == 0) {
             Stage& s = add_stage(ST_RANK1, "pi_dh2"); crit_dh2_rank1(s, q1, ca1, 0); crit_dh2_rank1(s, q2, ca2, 0);
         } else if (!two_lanes) { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
@@ -825,6 +867,12 @@ static CUtensorMapL2promotion ws_l2_promotion() {
     const int v = e ? atoi(e) : 128;
     return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
+// element type of the operand maps (measurement aid: OAC_WS_F32MAPS=1 copies plain fp32 -- the MMA then truncates -- to
+// see what the in-flight fp32 -> tf32 rounding of the TFLOAT32 type costs)
+static CUtensorMapDataType ws_map_dtype() {
+    const char* e = getenv("OAC_WS_F32MAPS");
+    return (e && e[0] == '1') ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+}
 static int ws_plan(OacTrainer& t, Stage& s) {
     const int seeds = t.cfg.n_seeds;
     // CTA pairs (gemm_ws2.cuh) when every task is made of whole 256-row tiles: each CTA then loads half of the B tile
@@ -845,7 +893,8 @@ static int ws_plan(OacTrainer& t, Stage& s) {
         if (!ws2_all) pair = pair && !s.a_trans && !s.b_trans && kmax >= 320 && tiles256 * seeds >= 2ll * (sm_count() / 2);
     }
     const int BM = pair ? 2 * WS_BM : WS_BM;
-    const int n_units = pair ? sm_count() / 2 : sm_count();    // CTAs or CTA pairs working at once
+    const int sms = s.sm_budget > 0 ? std::min(s.sm_budget, sm_count()) : sm_count();
+    const int n_units = pair ? sms / 2 : sms;                  // CTAs or CTA pairs working at once
     const int gran = (s.b_trans ? 32 : 16) * (pair ? 2 : 1);   // MN-major B tiles come in 32-column TMA boxes (per CTA)
     auto width = [&](const GemmTask& g, int cap) {             // tile width for a column cap: even split, rounded up
         const int lim = ((g.epi == EPI_ADAM || g.epi == EPI_GRAD) && g.has_bias) ? std::min(cap, pair ? 192 : (int)WS_BN_MAX_BIAS) : cap;   // room for the bias MMA's columns
@@ -896,7 +945,7 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     if (s.ws_slots < 2) return set_error(OAC_E_INVALID, "internal: ws ring does not fit");
     s.smem = (size_t)s.ws_slots * s.ws_slot_bytes + WS_ONES_BYTES + WS_SLAB_BYTES + 1024;
     s.ws_grid = pair ? 2 * (int)std::min<long long>((long long)t0 * seeds, n_units)
-                     : (int)std::min<long long>((long long)t0 * seeds, sm_count());
+                     : (int)std::min<long long>((long long)t0 * seeds, sms);
     // tensor maps
     TensorMapEncodeFn enc = tensor_map_encoder();
     std::vector<CUtensorMap> maps(2 * s.gemm.size());
@@ -908,14 +957,26 @@ static int ws_plan(OacTrainer& t, Stage& s) {
             const int ld = op == 0 ? g.lda : g.ldb;
             const int ext = op == 0 ? g.M : g.N;               // M / N extent of this operand
             const long long sstride = std::max<long long>(t.as.stride[r.arena], 4);
-            cuuint64_t dims[3], strides[2];
-            cuuint32_t box[3], es[3] = {1, 1, 1};
-            if (!mn) { dims[0] = (cuuint64_t)g.K; dims[1] = (cuuint64_t)ext; box[0] = WS_KC; box[1] = op == 0 ? WS_BM : (cuuint32_t)(pair ? g.bn / 2 : g.bn); }
-            else     { dims[0] = (cuuint64_t)ext; dims[1] = (cuuint64_t)g.K; box[0] = 32; box[1] = WS_KC; }
-            dims[2] = (cuuint64_t)seeds; box[2] = 1;
-            strides[0] = (cuuint64_t)ld * 4; strides[1] = (cuuint64_t)sstride * 4;
+            cuuint64_t dims[4], strides[3];
+            cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+            const cuuint32_t box_mn = op == 0 ? WS_BM : (cuuint32_t)(pair ? g.bn / 2 : g.bn);   // M / N extent of this CTA's box
+            int rank = 3;
+            if (!mn) {
+                dims[0] = (cuuint64_t)g.K; dims[1] = (cuuint64_t)ext; box[0] = WS_KC; box[1] = box_mn;
+                dims[2] = (cuuint64_t)seeds; box[2] = 1;
+                strides[0] = (cuuint64_t)ld * 4; strides[1] = (cuuint64_t)sstride * 4;
+            } else {
+                // M/N-contiguous operand: [seed][atom of 32 columns][k][32], so ONE box {32, WS_KC, atoms} lands as the
+                // UMMA layout [atom][k][128 B].  A ragged last atom reads up to 31 floats past the extent (the rest of the
+                // row pitch / the next row: finite data inside the arena, see the slack in oac_trainer_layout); those
+                // columns only feed output rows / columns that the epilogue does not store.
+                rank = 4;
+                dims[0] = 32; dims[1] = (cuuint64_t)g.K; dims[2] = (cuuint64_t)((ext + 31) / 32); dims[3] = (cuuint64_t)seeds;
+                box[0] = 32; box[1] = WS_KC; box[2] = box_mn / 32; box[3] = 1;
+                strides[0] = (cuuint64_t)ld * 4; strides[1] = 128; strides[2] = (cuuint64_t)sstride * 4;
+            }
             // TFLOAT32: the TMA unit rounds fp32 -> tf32 (nearest) on the way into shared memory
-            CUresult rc = enc(&maps[2 * i + op], CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, (void*)resolve(t.as, r, 0), dims, strides,
+            CUresult rc = enc(&maps[2 * i + op], ws_map_dtype(), rank, (void*)resolve(t.as, r, 0), dims, strides,
                               box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                               ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -979,7 +1040,7 @@ static int chain_plan(OacTrainer& t, Stage& s) {
             cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)ext, (cuuint64_t)seeds};
             cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)sstride * 4};
             cuuint32_t box[3] = {WS_KC, op == 0 ? (cuuint32_t)WS_BM : (cuuint32_t)g.bn, 1}, es[3] = {1, 1, 1};
-            CUresult rc = enc(&maps[2 * i + op], CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, (void*)resolve(t.as, r, 0), dims, strides, box, es,
+            CUresult rc = enc(&maps[2 * i + op], ws_map_dtype(), 3, (void*)resolve(t.as, r, 0), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (rc != CUDA_SUCCESS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: tensor map");
         }
@@ -1431,7 +1492,7 @@ extern "C" int oac_trainer_layout(const OacConfig* cfg, OacLayout* out) {
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
     else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
     else b.build_goac();
-    tmp.lay.work_floats = tmp.work_cursor;
+    tmp.lay.work_floats = tmp.work_cursor + WORK_SLACK;
     *out = tmp.lay;
     return 0;
 }
@@ -1454,7 +1515,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
     else if (cfg->algo == OAC_ALGO_POAC) b.build_poac();
     else b.build_goac();
-    t->lay.work_floats = t->work_cursor;
+    t->lay.work_floats = t->work_cursor + WORK_SLACK;
     const OacLayout& L = t->lay;
     t->as.base[AR_PARAM] = buf->params;  t->as.stride[AR_PARAM] = L.param_floats;
     t->as.base[AR_ADAM_M] = buf->adam_m; t->as.stride[AR_ADAM_M] = L.adam_floats;
@@ -1718,6 +1779,20 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
     g_debug_kernel = rc ? -1 : (s.use_ws ? (s.ws_pair ? 3 : 2) : (s.use_tc ? 1 : 0));
     if (!rc) rc = launch_stages(t, 0, (cudaStream_t)stream);
     if (!rc && t.tc_dbg) rc = launch_stages(t, 0, (cudaStream_t)stream);      // second (warm) run is the one reported
+    if (const char* reps_env = getenv("OAC_GEMM_DEBUG_REPS")) {                // measurement aid: mean time of this one stage
+        const int reps = atoi(reps_env);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, (cudaStream_t)stream);
+        for (int i = 0; i < reps && !rc; ++i) rc = launch_stages(t, 0, (cudaStream_t)stream);
+        cudaEventRecord(e1, (cudaStream_t)stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[gemm debug] path %d layout (%d,%d) M %d N %d K %d: %.2f us per launch, grid %d, bn %d, slots %d, %.1f TFLOP/s\n", gemm_path,
+                a_trans, b_trans, M, N, K, 1e3 * ms / reps, s.ws_grid, s.gemm[0].bn, s.ws_slots, 2.0 * M * N * K / (1e9 * ms / reps));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     cudaStreamSynchronize((cudaStream_t)stream);
     if (t.tc_dbg) {
         std::vector<long long> h(8 * dbg_n);

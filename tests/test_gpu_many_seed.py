@@ -21,8 +21,9 @@ def test_group_of_eight_tensor_path_vs_fp32_singles():
     grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=1)
     e = grp.engine
     # every GEMM stage runs on the TMA + tcgen05 kernels (the forward layers of this 8-seed group as two strip-fused chains:
-    # gemm_chain.cuh), Adam is a stage of its own, the step tail a one-CTA-per-seed kernel on a side lane
-    assert e.ws_stages >= 12 and e.launches_per_step == 16, (e.ws_stages, e.launches_per_step)
+    # gemm_chain.cuh), Adam is a stage of its own, the step tail a one-CTA-per-seed kernel on a side lane, and the critics'
+    # fc1 / head update + the first two policy-loss dX stages run on a side lane next to qloss_dh1 / the fc0 update
+    assert e.ws_stages >= 12 and e.launches_per_step == 18, (e.ws_stages, e.launches_per_step)
     singles = []
     for sid in ids:
         torch.manual_seed(sid)
