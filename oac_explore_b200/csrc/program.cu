@@ -216,7 +216,9 @@ struct Builder {
         O = c.obs_dim; A = c.act_dim; H = c.hidden; B = c.batch;
         static const long long tg_rows = getenv("OAC_TENSOR_GLUE_ROWS") ? atoll(getenv("OAC_TENSOR_GLUE_ROWS")) : 2048;   // measurement aid
         tensor_glue = c.gemm_path == OAC_GEMM_TF32 && (long long)c.n_seeds * c.batch >= tg_rows;
-        split_adam = tensor_glue && tr.allow_split && tr.allow_ws;
+        // (OAC_SPLIT_MIN_SEEDS: measurement aid -- groups below it keep the Adam update fused into the dW epilogue)
+        static const int split_min = getenv("OAC_SPLIT_MIN_SEEDS") ? atoi(getenv("OAC_SPLIT_MIN_SEEDS")) : 0;
+        split_adam = tensor_glue && tr.allow_split && tr.allow_ws && c.n_seeds >= split_min;
         if (split_adam) grad = work(L.adam_floats);
     }
     // Same regime: the weight-gradient GEMMs store plain gradients (laid out like the trainable prefix of the
@@ -615,7 +617,7 @@ void Builder::build_sac() {
     // lane's qloss_dh1 -> dW(fc0) -> its Adam; the lanes meet at pi_da.  The GEMM stages of the two branches are planned
     // for half of the SMs each so that they really run side by side.  OAC_GROUP_LANES=0 restores the linear order (A/B aid).
     static const int gl_max = getenv("OAC_GROUP_LANES") ? atoi(getenv("OAC_GROUP_LANES")) : 16;
-    const bool group_lanes = tensor_glue && split_adam && t.allow_lanes && !mode_b && (H & 3) == 0 && c.n_seeds <= gl_max;
+    const bool group_lanes = tensor_glue && t.allow_lanes && !mode_b && (H & 3) == 0 && c.n_seeds <= gl_max;
     const int half = sm_count() / 2;
     if (two_lanes && !mode_b) {
         // mode A: pi_dh2 needs the POST-step head weights, and the head gradient (dq^T h2) is complete after critic_head:
