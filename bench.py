@@ -585,6 +585,24 @@ def run_ours(args):
             del scratch
         del wg
         torch.cuda.empty_cache()
+        if world > 1:
+            # the same program with the per-GPU load held at `total` seeds (weak scaling: N x total seeds in all): what the N
+            # GPUs deliver when every one of them has a full group -- the strong-scaling curve above is bounded by the
+            # per-stage floors of small groups, not by anything between the GPUs (there is no data-path collective)
+            idw = [rank * total + i for i in range(total)]
+            ww = _Group(idw, rb, GEMM_PATHS["tf32"])
+            Kw = max(10, min(K, 100))
+            w_dev, w_e2e, w_block, _ = timed_loops(ww, Kw, 3, dev, barrier, clocks)
+            w_dev, w_e2e, w_block = max_over_ranks([w_dev, w_e2e, w_block])
+            launches += (ww.engine.launches_per_step + 1) * Kw * 3
+            batched["weak"] = {"workload": "%d seeds on EVERY GPU (%d in all), same program" % (total, total * world),
+                               "scaling": "weak", "seeds_per_gpu": total, "total_seeds": total * world,
+                               "value": total * world * Kw / (w_dev * 1e-3), "unit": "seed-updates/s",
+                               "ms_per_step": w_dev / Kw, "steps": Kw,
+                               "e2e": {"value": total * world * Kw / (w_e2e * 1e-3), "unit": "seed-updates/s",
+                                       "blocking_value": total * world * Kw / (w_block * 1e-3)}}
+            del ww
+            torch.cuda.empty_cache()
 
     # keep the GPU busy with the headline loop while the clock sampler collects (the timed regions may be shorter than
     # its period); untimed

@@ -944,6 +944,7 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     s.ws_slot_bytes = (int)WS_A_BYTES + (pair ? bn_max / 2 : bn_max) * (WS_KC * 4);
     const int budget = 224 * 1024 - 1024 - (int)WS_ONES_BYTES - (int)WS_SLAB_BYTES;
     s.ws_slots = std::min((int)WS_MAX_SLOTS, budget / s.ws_slot_bytes);
+    if (const char* ms = getenv("OAC_WS_MAX_SLOTS")) s.ws_slots = std::max(2, std::min(s.ws_slots, atoi(ms)));     // measurement aid: ring depth
     if (s.ws_slots < 2) return set_error(OAC_E_INVALID, "internal: ws ring does not fit");
     s.smem = (size_t)s.ws_slots * s.ws_slot_bytes + WS_ONES_BYTES + WS_SLAB_BYTES + 1024;
     s.ws_grid = pair ? 2 * (int)std::min<long long>((long long)t0 * seeds, n_units)

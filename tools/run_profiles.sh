@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/run_profiles.sh'
 set -u
 O=gpurun_out
-T="r02"
+T="${1:-r02b}"
 python bench.py > $O/${T}_bench_single.json 2> $O/${T}_bench_single.err
 python bench.py --impl reference --steps 20 --warmup 5 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err
 python bench.py --seeds-per-gpu 64 --steps 100 --warmup 5 --total-seeds 0 > $O/${T}_bench_64seeds.json 2> $O/${T}_bench_64seeds.err
@@ -17,10 +17,15 @@ python tools/profile_step.py --steps 3 > $O/${T}_plain_single.log 2>&1 && \
 python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_plain_64.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_64seeds_tf32.csv \
       python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_ncu_64.log 2>&1
+python tools/profile_step.py --steps 2 --seeds 8 --gemm-path tf32 > $O/${T}_plain_8.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_8seeds_tf32.csv \
+      python tools/profile_step.py --steps 2 --seeds 8 --gemm-path tf32 > $O/${T}_ncu_8.log 2>&1
 # full captures: the last step's launches of each configuration
 ncu --set full --clock-control none -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head_kernel|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip 32 --launch-count 16 -o $O/${T}_single_fp32 -f \
     python tools/profile_step.py --steps 3 > $O/${T}_full_single.log 2>&1
 ncu --set full --clock-control none -k regex:"gemm_ws|adam_stream|critic_head|policy_head|policy_grad|rank1|replay_gather" --launch-skip 19 --launch-count 19 -o $O/${T}_64seeds_tf32 -f \
     python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_full_64.log 2>&1
+ncu --set full --clock-control none -k regex:"gemm_chain|gemm_ws|adam_stream|critic_head|policy_head|policy_grad|rank1|step_tail|replay_gather" --launch-skip 19 --launch-count 19 -o $O/${T}_8seeds_tf32 -f \
+    python tools/profile_step.py --steps 2 --seeds 8 --gemm-path tf32 > $O/${T}_full_8.log 2>&1
 tail -2 $O/${T}_full_64.log
 ls -la $O/${T}_*.ncu-rep

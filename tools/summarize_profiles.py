@@ -94,6 +94,11 @@ if __name__ == "__main__":
         launch_list(tag + "_launches_single_fp32.csv", 16)
     if have(tag + "_launches_64seeds_tf32.csv"):
         launch_list(tag + "_launches_64seeds_tf32.csv", 19)
+    if have(tag + "_launches_8seeds_tf32.csv"):
+        launch_list(tag + "_launches_8seeds_tf32.csv", 19)
+    if have(tag + "_8seeds_tf32.ncu-rep"):
+        full_report(tag + "_8seeds_tf32.ncu-rep", tag + "_8seeds_tf32_full.txt")
+        tr["8:tf32"] = traffic(tag + "_8seeds_tf32.ncu-rep", ("gemm_ws_kernel", "gemm_ws2_kernel", "gemm_chain_kernel"))
     if have(tag + "_single_fp32.ncu-rep"):
         full_report(tag + "_single_fp32.ncu-rep", tag + "_single_fp32_full.txt")
         tr["1:fp32"] = traffic(tag + "_single_fp32.ncu-rep", ("gemm_sk_kernel", "gemm_fwd2_kernel"))
