@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                 const bool to_tmem = l + 1 < NL;                 // the next layer reads this one from tensor memory
                 float* __restrict__ C = resolve(sp.as, T.C, seed);
                 const float* __restrict__ bias = resolve(sp.as, T.bias, seed);
+                uint8_t* __restrict__ bits_out = (T.ldbits > 0 && relu_) ? reinterpret_cast<uint8_t*>(resolve(sp.as, T.bits, seed)) : nullptr;
                 mbar_wait_relaxed(&s_dfull[l], par);
                 tc_fence_after();
                 const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (l == 1 ? 256u : 0u);
@@ -258,6 +259,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                             if (m >= M) continue;
                             const float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
                             float* dst = C + (long long)m * ldc + n;
+                            // sign bits of these four columns (one byte) for the masked dX epilogues (gemm_ws.cuh): written here,
+                            // off the path the next layer's MMAs wait on
+                            if (bits_out != nullptr && vec)
+                                bits_out[(long long)m * T.ldbits + (n >> 2)] =
+                                    (uint8_t)((x.x > 0.f ? 1u : 0u) | (x.y > 0.f ? 2u : 0u) | (x.z > 0.f ? 4u : 0u) | (x.w > 0.f ? 8u : 0u));
                             if (vec) *reinterpret_cast<float4*>(dst) = x;
                             else {
                                 dst[0] = x.x;

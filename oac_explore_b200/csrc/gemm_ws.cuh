@@ -98,7 +98,228 @@ __device__ __forceinline__ void adam_core(float g, float& p, float& m, float& v,
     if (has_tgt) tgt = fmaf(tgt, s.one_m_tau, p * s.tau);
 }
 
-template <bool A_MN, bool B_MN>
+// Sign bits of a hidden activation ("mask bits"): the forward epilogues (here and in gemm_chain.cuh) also store, for every
+// row and every group of 4 columns, one BYTE whose bit j says h[row][4 g + j] > 0 (what a lane of the coalesced epilogue
+// domain holds: a float4).  The masked dX epilogues and the rank-1 pass read these bytes (64 B per 256-wide row) instead
+// of the fp32 activation (1 KB): 16 registers of loads in flight per lane instead of 64, and 1/16 of the mask traffic.
+// Epilogue of ONE accumulator tile (rows m0 + 32 q .. + 31 of this warp's TMEM lane quarter, the 64-column slabs sl = hsel,
+// hsel + 2, ..): tcgen05.ld -> per-warp slab -> coalesced float4 rows -> bias / ReLU (+ mask bits) | ReLU-derivative mask |
+// gradient store | Adam (+ Polyak).  Shared by gemm_ws_kernel and its CTA-pair variant (gemm_ws2.cuh).
+template <bool A_MN, bool B_MN, bool MASK_BITS = false>
+__device__ __forceinline__ void ws_tile_epilogue(const StageParams& sp, const GemmTask& T, int seed, int m0, int n0, int tn,
+                                                 uint32_t t_base, float* slab, int q, int hsel, int lane) {
+    float* __restrict__ m1 = sp.as.base[AR_ADAM_M];
+    float* __restrict__ m2 = sp.as.base[AR_ADAM_V];
+    float* __restrict__ pb0 = sp.as.base[AR_PARAM];
+    const int rsub = lane >> 4, c4 = (lane & 15) << 2;
+    const int bn = T.bn, M = T.M, N = T.N, epi = T.epi, ldc = T.ldc;
+    const int nlim = min(N, n0 + bn);
+    float* __restrict__ C = resolve(sp.as, T.C, seed);
+    // the operand layouts pin the epilogue class (dW products are the only (MN, MN) tasks, masked dX products
+    // the only (K, MN) ones): dead epilogues are compiled out, which keeps their registers out of the live set
+    constexpr bool CAN_ADAM = A_MN && B_MN, CAN_MASK = !A_MN && B_MN, CAN_BITS = !A_MN && !B_MN;
+    const bool is_adam = CAN_ADAM && epi == EPI_ADAM;
+    const bool is_grad = CAN_ADAM && epi == EPI_GRAD;        // plain store of dW; Adam streams later (adam_stream.cuh)
+    AdamScalars s;
+    float inv_bc2 = 1.f;
+    float* __restrict__ am = nullptr; float* __restrict__ av = nullptr; float* __restrict__ tg = nullptr;
+    if (is_adam) {
+        const int32_t* cnt = sp.as.counters + seed * sp.as.n_counters;
+        s = make_adam_scalars_fast(sp.hyper, T.lr, cnt[T.counter], cnt[CNT_TRAIN_STEPS]);
+        inv_bc2 = 1.0f / s.bc2_sqrt;
+        am = m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off;
+        av = m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off;
+        if (T.target_off >= 0 && s.do_polyak) tg = pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off;
+    }
+    const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
+    const float* __restrict__ mask = (CAN_MASK && epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
+    constexpr bool mask_bits = CAN_MASK && MASK_BITS;     // a stage's tasks all carry the same kind of mask (ws_plan)
+    const int ldmask = T.ldmask;
+    // forward layer whose sign bits a later stage wants
+    uint8_t* __restrict__ bits_out = (CAN_BITS && T.ldbits > 0 && epi == EPI_BIAS_RELU)
+                                         ? reinterpret_cast<uint8_t*>(resolve(sp.as, T.bits, seed)) : nullptr;
+    const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
+    for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
+        const int c0 = sl * WS_SLAB;
+        const int n = n0 + c0 + c4;
+        // ReLU-mask epilogue.  One mask load at a time costs a DRAM latency each (21 us per K=1 tile, round 1), so the
+        // loads are requested before the accumulator read-back.  Mask BITS: 16 words per lane (8 lanes share a word).
+        // fp32 masks (activations of a stage that stores no bits): all 16 float4 of a lane together with the 32
+        // accumulator registers and the prefetched slab rows exceed the 168-register budget -- ptxas spilled into the
+        // store loop and this instantiation spent 12 us per 128 x 256 tile in its epilogue whatever K (5 us in the
+        // forward kernel; ncu source page: stores waiting on local-memory reloads) -- hence two batches of 8 row pairs,
+        // each reduced to sign bits as soon as it is consumed: batch A flies during the read-back, batch B during A's stores.
+        uint32_t kw[mask_bits ? 16 : 1];
+        float4 kq[mask_bits ? 1 : 8];
+        const bool mask_vec = !mask_bits && mask != nullptr && (n + 3 < nlim);
+        auto load_masks = [&](int rp0) {
+            if constexpr (!mask_bits) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int m = m0 + q * 32 + 2 * (rp0 + r) + rsub;
+                    kq[r] = (m < M) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        auto pack_masks = [&]() {
+            uint32_t b = 0;
+            if constexpr (!mask_bits) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    b |= ((kq[r].x > 0.f ? 1u : 0u) | (kq[r].y > 0.f ? 2u : 0u) | (kq[r].z > 0.f ? 4u : 0u) | (kq[r].w > 0.f ? 8u : 0u)) << (4 * r);
+            }
+            return b;
+        };
+        if (mask_bits) {
+            if (mask != nullptr) {
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(mask) + (n >> 2);
+#pragma unroll
+                for (int rp = 0; rp < 16; ++rp) {
+                    const int m = m0 + q * 32 + 2 * rp + rsub;
+                    kw[mask_bits ? rp : 0] = (m < M && n < nlim) ? (uint32_t)__ldg(wsrc + (long long)m * ldmask) : 0u;
+                }
+            }
+        } else if (mask_vec) load_masks(0);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                 // 32 columns at a time: 32 live registers
+            if (c0 + 32 * hf >= bn) break;
+            float v[32];
+            tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf), &v[0]);
+            if (c0 + 32 * hf + 16 < bn) tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf + 16), &v[16]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(slab + lane * WS_SLAB_LD + 32 * hf + 4 * i) =
+                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        __syncwarp();
+        const bool vec = n + 3 < nlim;
+        if (is_adam) {
+            if (n < nlim) {
+                constexpr int RB = 4;                    // row pairs per batch: 4 x 4 float4 loads in flight per lane
+                for (int rp0 = 0; rp0 < 16; rp0 += RB) {
+                    float4 x[RB], p4[RB], a4[RB], v4[RB], t4[RB];
+                    long long eo[RB];
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
+                        eo[r] = (m < M) ? (long long)m * ldc + n : -1;
+                        x[r] = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
+                        if (eo[r] >= 0 && vec) {
+                            p4[r] = *reinterpret_cast<const float4*>(C + eo[r]);
+                            a4[r] = *reinterpret_cast<const float4*>(am + eo[r]);
+                            v4[r] = *reinterpret_cast<const float4*>(av + eo[r]);
+                            if (tg) t4[r] = *reinterpret_cast<const float4*>(tg + eo[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        if (eo[r] < 0) continue;
+                        if (vec) {
+                            const bool ht = tg != nullptr;
+                            adam_core(x[r].x, p4[r].x, a4[r].x, v4[r].x, t4[r].x, ht, s, inv_bc2);
+                            adam_core(x[r].y, p4[r].y, a4[r].y, v4[r].y, t4[r].y, ht, s, inv_bc2);
+                            adam_core(x[r].z, p4[r].z, a4[r].z, v4[r].z, t4[r].z, ht, s, inv_bc2);
+                            adam_core(x[r].w, p4[r].w, a4[r].w, v4[r].w, t4[r].w, ht, s, inv_bc2);
+                            *reinterpret_cast<float4*>(C + eo[r]) = p4[r];
+                            *reinterpret_cast<float4*>(am + eo[r]) = a4[r];
+                            *reinterpret_cast<float4*>(av + eo[r]) = v4[r];
+                            if (ht) *reinterpret_cast<float4*>(tg + eo[r]) = t4[r];
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 3; ++jj) {             // a partial float4 holds at most 3 live columns
+                                if (n + jj >= nlim) continue;
+                                const float xj = jj == 0 ? x[r].x : (jj == 1 ? x[r].y : x[r].z);
+                                const long long ee = eo[r] + jj;
+                                float pp = C[ee], mm = am[ee], vv = av[ee], tt = tg ? tg[ee] : 0.f;
+                                adam_core(xj, pp, mm, vv, tt, tg != nullptr, s, inv_bc2);
+                                C[ee] = pp; am[ee] = mm; av[ee] = vv;
+                                if (tg) tg[ee] = tt;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias != nullptr && n < nlim) {
+                if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                else { b4.x = __ldg(bias + n); if (n + 1 < nlim) b4.y = __ldg(bias + n + 1); if (n + 2 < nlim) b4.z = __ldg(bias + n + 2); }
+            }
+            uint32_t mbits = 0xffffffffu;
+            if (mask_vec) {
+                mbits = pack_masks();
+                asm volatile("" ::: "memory");           // batch B is requested only now: its registers replace batch A's
+                load_masks(8);
+            }
+            auto store_rows = [&](int rp0) {
+                if (n >= nlim) return;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
+                    if (m >= M) continue;
+                    float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
+                    x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                    if (epi == EPI_BIAS_RELU) { x.x = relu(x.x); x.y = relu(x.y); x.z = relu(x.z); x.w = relu(x.w); }
+                    float* dst = C + (long long)m * ldc + n;
+                    if (vec) {
+                        if (CAN_MASK && mask != nullptr) {
+                            const uint32_t nb = mask_bits ? kw[mask_bits ? rp0 + r : 0] : mbits >> (4 * r);
+                            x.x = (nb & 1u) ? x.x : 0.f; x.y = (nb & 2u) ? x.y : 0.f;
+                            x.z = (nb & 4u) ? x.z : 0.f; x.w = (nb & 8u) ? x.w : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(dst) = x;
+                        if (CAN_BITS && bits_out != nullptr)
+                            bits_out[(long long)m * T.ldbits + (n >> 2)] =
+                                (uint8_t)((x.x > 0.f ? 1u : 0u) | (x.y > 0.f ? 2u : 0u) | (x.z > 0.f ? 4u : 0u) | (x.w > 0.f ? 8u : 0u));
+                    } else {
+                        uint32_t nib = 0;
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj) {
+                            if (n + jj >= nlim) continue;
+                            float y = jj == 0 ? x.x : (jj == 1 ? x.y : x.z);
+                            if (CAN_MASK && mask != nullptr) {
+                                const bool on = mask_bits ? ((kw[mask_bits ? rp0 + r : 0] >> jj) & 1u) != 0u
+                                                          : __ldg(mask + (long long)m * ldmask + n + jj) > 0.f;
+                                y = on ? y : 0.f;
+                            }
+                            nib |= (y > 0.f ? 1u : 0u) << jj;
+                            dst[jj] = y;
+                        }
+                        if (CAN_BITS && bits_out != nullptr) bits_out[(long long)m * T.ldbits + (n >> 2)] = (uint8_t)nib;
+                    }
+                }
+            };
+            store_rows(0);
+            if (mask_vec) mbits = pack_masks();
+            store_rows(8);
+        }
+        __syncwarp();                                    // slab is rewritten by the next pass
+    }
+    // bias block of a dW task: column sums of dY sit in the spare TMEM columns (every column is the row sum)
+    if (is_grad && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
+        const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
+        const int m = m0 + q * 32 + lane;
+        if (m < M) resolve(sp.as, T.bias, seed)[m] = T.train_bias ? gsum : 0.f;      // a frozen bias gets a zero gradient
+    }
+    if (is_adam && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
+        const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
+        const int m = m0 + q * 32 + lane;
+        if (m < M) {
+            float* pb = resolve(sp.as, T.bias, seed) + m;
+            float* tgb = T.target_bias_off >= 0 ? pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_bias_off + m : nullptr;
+            if (T.train_bias) {
+                adam_update(gsum, pb, m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_bias_off + m,
+                            m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_bias_off + m, tgb, s);
+            } else if (tgb != nullptr && s.do_polyak) {
+                *tgb = __fadd_rn(__fmul_rn(*tgb, s.one_m_tau), __fmul_rn(*pb, s.tau));
+            }
+        }
+    }
+}
+
+template <bool A_MN, bool B_MN, bool MASK_BITS = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
     extern __shared__ __align__(1024) uint8_t ws_smem[];
     __shared__ __align__(8) uint64_t s_full[WS_MAX_SLOTS], s_empty[WS_MAX_SLOTS], s_tfull[2], s_tempty[2];
@@ -220,197 +441,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
         const int hsel = e >> 2;                                 // two warps per quarter alternate over the slabs
         float* slab = slabs + e * (32 * WS_SLAB_LD);
-        float* __restrict__ m1 = sp.as.base[AR_ADAM_M];
-        float* __restrict__ m2 = sp.as.base[AR_ADAM_V];
-        float* __restrict__ pb0 = sp.as.base[AR_PARAM];
-        const int rsub = lane >> 4, c4 = (lane & 15) << 2;
         int tl = 0;
         for (int g = blockIdx.x; g < wp.total_tiles; g += gridDim.x, ++tl) {
             int seed, j, tm, tn;
             decode(g, seed, j, tm, tn);
             const GemmTask& T = tasks[j];
-            const int bn = T.bn, M = T.M, N = T.N, epi = T.epi, ldc = T.ldc;
-            const int m0 = tm * WS_BM, n0 = tn * bn;
-            const int nlim = min(N, n0 + bn);
             const int buf = tl & 1;
-            float* __restrict__ C = resolve(sp.as, T.C, seed);
-            // the operand layouts pin the epilogue class (dW products are the only (MN, MN) tasks, masked dX products
-            // the only (K, MN) ones): dead epilogues are compiled out, which keeps their registers out of the live set
-            constexpr bool CAN_ADAM = A_MN && B_MN, CAN_MASK = !A_MN && B_MN;
-            const bool is_adam = CAN_ADAM && epi == EPI_ADAM;
-            const bool is_grad = CAN_ADAM && epi == EPI_GRAD;        // plain store of dW; Adam streams later (adam_stream.cuh)
-            AdamScalars s;
-            float inv_bc2 = 1.f;
-            float* __restrict__ am = nullptr; float* __restrict__ av = nullptr; float* __restrict__ tg = nullptr;
-            if (is_adam) {
-                const int32_t* cnt = sp.as.counters + seed * sp.as.n_counters;
-                s = make_adam_scalars_fast(sp.hyper, T.lr, cnt[T.counter], cnt[CNT_TRAIN_STEPS]);
-                inv_bc2 = 1.0f / s.bc2_sqrt;
-                am = m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off;
-                av = m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off;
-                if (T.target_off >= 0 && s.do_polyak) tg = pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off;
-            }
-            const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
-            const float* __restrict__ mask = (CAN_MASK && epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
-            const int ldmask = T.ldmask;
-
             mbar_wait_relaxed(&s_tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-            const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
-            for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
-                const int c0 = sl * WS_SLAB;
-                // ReLU-mask epilogue.  One mask load at a time costs a DRAM latency each (21 us per K=1 tile, round 1); all 16
-                // float4 of this lane requested before the accumulator read-back hide the latency but, together with the 32
-                // accumulator registers and the 8 prefetched slab rows, exceed the 168-register budget: ptxas spilled into the
-                // store loop and this instantiation spent 12 us per 128 x 256 tile in its epilogue whatever K (5 us in the
-                // forward kernel; ncu source page: the stores waiting on local-memory reloads).  So: two batches of 8 row
-                // pairs, each reduced to sign bits as soon as it is consumed -- batch A flies during the read-back, batch B
-                // during batch A's stores.
-                float4 kq[8];
-                const bool mask_vec = mask != nullptr && (n0 + c0 + c4 + 3 < nlim);
-                auto load_masks = [&](int rp0) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int m = m0 + q * 32 + 2 * (rp0 + r) + rsub;
-                        kq[r] = (m < M) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n0 + c0 + c4))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                };
-                auto pack_masks = [&]() {
-                    uint32_t b = 0;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        b |= ((kq[r].x > 0.f ? 1u : 0u) | (kq[r].y > 0.f ? 2u : 0u) | (kq[r].z > 0.f ? 4u : 0u) | (kq[r].w > 0.f ? 8u : 0u)) << (4 * r);
-                    return b;
-                };
-                if (mask_vec) load_masks(0);
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {                 // 32 columns at a time: 32 live registers
-                    if (c0 + 32 * hf >= bn) break;
-                    float v[32];
-                    tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf), &v[0]);
-                    if (c0 + 32 * hf + 16 < bn) tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf + 16), &v[16]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(slab + lane * WS_SLAB_LD + 32 * hf + 4 * i) =
-                            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
-                __syncwarp();
-                const int n = n0 + c0 + c4;
-                if (n < nlim) {
-                    const bool vec = n + 3 < nlim;
-                    if (is_adam) {
-                        constexpr int RB = 4;                    // row pairs per batch: 4 x 4 float4 loads in flight per lane
-                        for (int rp0 = 0; rp0 < 16; rp0 += RB) {
-                            float4 x[RB], p4[RB], a4[RB], v4[RB], t4[RB];
-                            long long eo[RB];
-#pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
-                                eo[r] = (m < M) ? (long long)m * ldc + n : -1;
-                                x[r] = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
-                                if (eo[r] >= 0 && vec) {
-                                    p4[r] = *reinterpret_cast<const float4*>(C + eo[r]);
-                                    a4[r] = *reinterpret_cast<const float4*>(am + eo[r]);
-                                    v4[r] = *reinterpret_cast<const float4*>(av + eo[r]);
-                                    if (tg) t4[r] = *reinterpret_cast<const float4*>(tg + eo[r]);
-                                }
-                            }
-#pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                if (eo[r] < 0) continue;
-                                if (vec) {
-                                    const bool ht = tg != nullptr;
-                                    adam_core(x[r].x, p4[r].x, a4[r].x, v4[r].x, t4[r].x, ht, s, inv_bc2);
-                                    adam_core(x[r].y, p4[r].y, a4[r].y, v4[r].y, t4[r].y, ht, s, inv_bc2);
-                                    adam_core(x[r].z, p4[r].z, a4[r].z, v4[r].z, t4[r].z, ht, s, inv_bc2);
-                                    adam_core(x[r].w, p4[r].w, a4[r].w, v4[r].w, t4[r].w, ht, s, inv_bc2);
-                                    *reinterpret_cast<float4*>(C + eo[r]) = p4[r];
-                                    *reinterpret_cast<float4*>(am + eo[r]) = a4[r];
-                                    *reinterpret_cast<float4*>(av + eo[r]) = v4[r];
-                                    if (ht) *reinterpret_cast<float4*>(tg + eo[r]) = t4[r];
-                                } else {
-#pragma unroll
-                                    for (int jj = 0; jj < 3; ++jj) {             // a partial float4 holds at most 3 live columns
-                                        if (n + jj >= nlim) continue;
-                                        const float xj = jj == 0 ? x[r].x : (jj == 1 ? x[r].y : x[r].z);
-                                        const long long ee = eo[r] + jj;
-                                        float pp = C[ee], mm = am[ee], vv = av[ee], tt = tg ? tg[ee] : 0.f;
-                                        adam_core(xj, pp, mm, vv, tt, tg != nullptr, s, inv_bc2);
-                                        C[ee] = pp; am[ee] = mm; av[ee] = vv;
-                                        if (tg) tg[ee] = tt;
-                                    }
-                                }
-                            }
-                        }
-                    } else {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bias != nullptr) {
-                            if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-                            else { b4.x = __ldg(bias + n); if (n + 1 < nlim) b4.y = __ldg(bias + n + 1); if (n + 2 < nlim) b4.z = __ldg(bias + n + 2); }
-                        }
-                        uint32_t mbits = 0xffffffffu;
-                        if (mask_vec) {
-                            mbits = pack_masks();
-                            asm volatile("" ::: "memory");       // batch B is requested only now: its registers replace batch A's
-                            load_masks(8);
-                        }
-                        auto store_rows = [&](int rp0) {
-#pragma unroll
-                            for (int r = 0; r < 8; ++r) {
-                                const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
-                                if (m >= M) continue;
-                                float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
-                                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                                if (epi == EPI_BIAS_RELU) { x.x = relu(x.x); x.y = relu(x.y); x.z = relu(x.z); x.w = relu(x.w); }
-                                float* dst = C + (long long)m * ldc + n;
-                                if (vec) {
-                                    if (CAN_MASK) {
-                                        const uint32_t nb = mbits >> (4 * r);
-                                        x.x = (nb & 1u) ? x.x : 0.f; x.y = (nb & 2u) ? x.y : 0.f;
-                                        x.z = (nb & 4u) ? x.z : 0.f; x.w = (nb & 8u) ? x.w : 0.f;
-                                    }
-                                    *reinterpret_cast<float4*>(dst) = x;
-                                } else {
-#pragma unroll
-                                    for (int jj = 0; jj < 3; ++jj) {
-                                        if (n + jj >= nlim) continue;
-                                        float y = jj == 0 ? x.x : (jj == 1 ? x.y : x.z);
-                                        if (mask != nullptr) y = __ldg(mask + (long long)m * ldmask + n + jj) > 0.f ? y : 0.f;
-                                        dst[jj] = y;
-                                    }
-                                }
-                            }
-                        };
-                        store_rows(0);
-                        if (mask_vec) mbits = pack_masks();
-                        store_rows(8);
-                    }
-                }
-                __syncwarp();                                    // slab is rewritten by the next pass
-            }
-            // bias block of a dW task: column sums of dY sit in the spare TMEM columns (every column is the row sum)
-            if (is_grad && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
-                const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
-                const int m = m0 + q * 32 + lane;
-                if (m < M) resolve(sp.as, T.bias, seed)[m] = T.train_bias ? gsum : 0.f;      // a frozen bias gets a zero gradient
-            }
-            if (is_adam && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
-                const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
-                const int m = m0 + q * 32 + lane;
-                if (m < M) {
-                    float* pb = resolve(sp.as, T.bias, seed) + m;
-                    float* tgb = T.target_bias_off >= 0 ? pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_bias_off + m : nullptr;
-                    if (T.train_bias) {
-                        adam_update(gsum, pb, m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_bias_off + m,
-                                    m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_bias_off + m, tgb, s);
-                    } else if (tgb != nullptr && s.do_polyak) {
-                        *tgb = __fadd_rn(__fmul_rn(*tgb, s.one_m_tau), __fmul_rn(*pb, s.tau));
-                    }
-                }
-            }
+            ws_tile_epilogue<A_MN, B_MN, MASK_BITS>(sp, T, seed, tm * WS_BM, tn * T.bn, tn, t_base, slab, q, hsel, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_tempty[buf]);

@@ -187,173 +187,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws2_kernel(WsParams wp) {
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
         const int hsel = e >> 2;                                 // two warps per quarter alternate over the slabs
         float* slab = slabs + e * (32 * WS_SLAB_LD);
-        float* __restrict__ m1 = sp.as.base[AR_ADAM_M];
-        float* __restrict__ m2 = sp.as.base[AR_ADAM_V];
-        float* __restrict__ pb0 = sp.as.base[AR_PARAM];
-        const int rsub = lane >> 4, c4 = (lane & 15) << 2;
         int tl = 0;
         const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&s_tempty[0]), 0), mapa_u32(smem_u32(&s_tempty[1]), 0)};
         for (int g = cl_id; g < wp.total_tiles; g += n_cl, ++tl) {
             int seed, j, tm, tn;
             decode(g, seed, j, tm, tn);
             const GemmTask& T = tasks[j];
-            const int bn = T.bn, M = T.M, N = T.N, epi = T.epi, ldc = T.ldc;
-            const int m0 = tm * (2 * WS_BM) + (int)rank * WS_BM, n0 = tn * bn;        // this CTA's 128 rows, all bn columns
-            const int nlim = min(N, n0 + bn);
+            const int m0 = tm * (2 * WS_BM) + (int)rank * WS_BM, n0 = tn * T.bn;      // this CTA's 128 rows, all bn columns
             const int buf = tl & 1;
-            float* __restrict__ C = resolve(sp.as, T.C, seed);
-            // the operand layouts pin the epilogue class (dW products are the only (MN, MN) tasks, masked dX products
-            // the only (K, MN) ones): dead epilogues are compiled out, which keeps their registers out of the live set
-            constexpr bool CAN_ADAM = A_MN && B_MN, CAN_MASK = !A_MN && B_MN;
-            const bool is_adam = CAN_ADAM && epi == EPI_ADAM;
-            const bool is_grad = CAN_ADAM && epi == EPI_GRAD;        // plain store of dW; Adam streams later (adam_stream.cuh)
-            AdamScalars s;
-            float inv_bc2 = 1.f;
-            float* __restrict__ am = nullptr; float* __restrict__ av = nullptr; float* __restrict__ tg = nullptr;
-            if (is_adam) {
-                const int32_t* cnt = sp.as.counters + seed * sp.as.n_counters;
-                s = make_adam_scalars_fast(sp.hyper, T.lr, cnt[T.counter], cnt[CNT_TRAIN_STEPS]);
-                inv_bc2 = 1.0f / s.bc2_sqrt;
-                am = m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_off;
-                av = m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_off;
-                if (T.target_off >= 0 && s.do_polyak) tg = pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_off;
-            }
-            const float* __restrict__ bias = (epi == EPI_BIAS || epi == EPI_BIAS_RELU) ? resolve(sp.as, T.bias, seed) : nullptr;
-            const float* __restrict__ mask = (CAN_MASK && epi == EPI_MASK) ? resolve(sp.as, T.mask, seed) : nullptr;
-            const int ldmask = T.ldmask;
-
             mbar_wait_relaxed(&s_tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-            const bool rows_live = m0 + q * 32 < M;              // warp-uniform: nothing to write for this quarter
-            for (int sl = hsel; sl * WS_SLAB < nlim - n0 && rows_live; sl += 2) {
-                const int c0 = sl * WS_SLAB;
-                // ReLU-mask epilogue: all 16 mask loads of this lane fly while the accumulator is read back and
-                // transposed (one at a time they cost a DRAM latency each: 21 us per K=1 tile before this)
-                float4 k4[16];
-                const bool mask_vec = mask != nullptr && (n0 + c0 + c4 + 3 < nlim);
-                if (mask_vec) {
-#pragma unroll
-                    for (int rp = 0; rp < 16; ++rp) {
-                        const int m = m0 + q * 32 + 2 * rp + rsub;
-                        k4[rp] = (m < M) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldmask + n0 + c0 + c4))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {                 // 32 columns at a time: 32 live registers
-                    if (c0 + 32 * hf >= bn) break;
-                    float v[32];
-                    tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf), &v[0]);
-                    if (c0 + 32 * hf + 16 < bn) tmem_ld16_nowait(t_base + (uint32_t)(c0 + 32 * hf + 16), &v[16]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(slab + lane * WS_SLAB_LD + 32 * hf + 4 * i) =
-                            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
-                __syncwarp();
-                const int n = n0 + c0 + c4;
-                if (n < nlim) {
-                    const bool vec = n + 3 < nlim;
-                    if (is_adam) {
-                        constexpr int RB = 4;                    // row pairs per batch: 4 x 4 float4 loads in flight per lane
-                        for (int rp0 = 0; rp0 < 16; rp0 += RB) {
-                            float4 x[RB], p4[RB], a4[RB], v4[RB], t4[RB];
-                            long long eo[RB];
-#pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                const int row = 2 * (rp0 + r) + rsub, m = m0 + q * 32 + row;
-                                eo[r] = (m < M) ? (long long)m * ldc + n : -1;
-                                x[r] = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
-                                if (eo[r] >= 0 && vec) {
-                                    p4[r] = *reinterpret_cast<const float4*>(C + eo[r]);
-                                    a4[r] = *reinterpret_cast<const float4*>(am + eo[r]);
-                                    v4[r] = *reinterpret_cast<const float4*>(av + eo[r]);
-                                    if (tg) t4[r] = *reinterpret_cast<const float4*>(tg + eo[r]);
-                                }
-                            }
-#pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                if (eo[r] < 0) continue;
-                                if (vec) {
-                                    const bool ht = tg != nullptr;
-                                    adam_core(x[r].x, p4[r].x, a4[r].x, v4[r].x, t4[r].x, ht, s, inv_bc2);
-                                    adam_core(x[r].y, p4[r].y, a4[r].y, v4[r].y, t4[r].y, ht, s, inv_bc2);
-                                    adam_core(x[r].z, p4[r].z, a4[r].z, v4[r].z, t4[r].z, ht, s, inv_bc2);
-                                    adam_core(x[r].w, p4[r].w, a4[r].w, v4[r].w, t4[r].w, ht, s, inv_bc2);
-                                    *reinterpret_cast<float4*>(C + eo[r]) = p4[r];
-                                    *reinterpret_cast<float4*>(am + eo[r]) = a4[r];
-                                    *reinterpret_cast<float4*>(av + eo[r]) = v4[r];
-                                    if (ht) *reinterpret_cast<float4*>(tg + eo[r]) = t4[r];
-                                } else {
-#pragma unroll
-                                    for (int jj = 0; jj < 3; ++jj) {             // a partial float4 holds at most 3 live columns
-                                        if (n + jj >= nlim) continue;
-                                        const float xj = jj == 0 ? x[r].x : (jj == 1 ? x[r].y : x[r].z);
-                                        const long long ee = eo[r] + jj;
-                                        float pp = C[ee], mm = am[ee], vv = av[ee], tt = tg ? tg[ee] : 0.f;
-                                        adam_core(xj, pp, mm, vv, tt, tg != nullptr, s, inv_bc2);
-                                        C[ee] = pp; am[ee] = mm; av[ee] = vv;
-                                        if (tg) tg[ee] = tt;
-                                    }
-                                }
-                            }
-                        }
-                    } else {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bias != nullptr) {
-                            if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-                            else { b4.x = __ldg(bias + n); if (n + 1 < nlim) b4.y = __ldg(bias + n + 1); if (n + 2 < nlim) b4.z = __ldg(bias + n + 2); }
-                        }
-#pragma unroll
-                        for (int rp = 0; rp < 16; ++rp) {
-                            const int row = 2 * rp + rsub, m = m0 + q * 32 + row;
-                            if (m >= M) continue;
-                            float4 x = *reinterpret_cast<const float4*>(slab + row * WS_SLAB_LD + c4);
-                            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                            if (epi == EPI_BIAS_RELU) { x.x = relu(x.x); x.y = relu(x.y); x.z = relu(x.z); x.w = relu(x.w); }
-                            float* dst = C + (long long)m * ldc + n;
-                            if (vec) {
-                                if (mask != nullptr) {
-                                    x.x = k4[rp].x > 0.f ? x.x : 0.f; x.y = k4[rp].y > 0.f ? x.y : 0.f;
-                                    x.z = k4[rp].z > 0.f ? x.z : 0.f; x.w = k4[rp].w > 0.f ? x.w : 0.f;
-                                }
-                                *reinterpret_cast<float4*>(dst) = x;
-                            } else {
-#pragma unroll
-                                for (int jj = 0; jj < 3; ++jj) {
-                                    if (n + jj >= nlim) continue;
-                                    float y = jj == 0 ? x.x : (jj == 1 ? x.y : x.z);
-                                    if (mask != nullptr) y = __ldg(mask + (long long)m * ldmask + n + jj) > 0.f ? y : 0.f;
-                                    dst[jj] = y;
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();                                    // slab is rewritten by the next pass
-            }
-            // bias block of a dW task: column sums of dY sit in the spare TMEM columns (every column is the row sum)
-            if (is_grad && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
-                const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
-                const int m = m0 + q * 32 + lane;
-                if (m < M) resolve(sp.as, T.bias, seed)[m] = T.train_bias ? gsum : 0.f;      // a frozen bias gets a zero gradient
-            }
-            if (is_adam && T.has_bias && tn == 0 && hsel == 0 && rows_live) {
-                const float gsum = tmem_ld1(t_base + WS_BIAS_COL);
-                const int m = m0 + q * 32 + lane;
-                if (m < M) {
-                    float* pb = resolve(sp.as, T.bias, seed) + m;
-                    float* tgb = T.target_bias_off >= 0 ? pb0 + (long long)seed * sp.as.stride[AR_PARAM] + T.target_bias_off + m : nullptr;
-                    if (T.train_bias) {
-                        adam_update(gsum, pb, m1 + (long long)seed * sp.as.stride[AR_ADAM_M] + T.adam_bias_off + m,
-                                    m2 + (long long)seed * sp.as.stride[AR_ADAM_V] + T.adam_bias_off + m, tgb, s);
-                    } else if (tgb != nullptr && s.do_polyak) {
-                        *tgb = __fadd_rn(__fmul_rn(*tgb, s.one_m_tau), __fmul_rn(*pb, s.tau));
-                    }
-                }
-            }
+            ws_tile_epilogue<A_MN, B_MN>(sp, T, seed, m0, n0, tn, t_base, slab, q, hsel, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader[buf]);      // the leader's MMA lane waits for both CTAs' epilogues

@@ -202,6 +202,7 @@ struct Rank1Task {
     Ref dq;  int dq_ld;        // [rows, dq_ld]: gradient w.r.t. the head outputs
     Ref w3;  int n_heads;      // [n_heads, cols]
     Ref mask; int ldmask;      // [rows, ldmask]: the activation whose ReLU is differentiated
+    int mask_bits;             // 1: `mask` holds its sign bits instead (one byte per 4 columns, gemm_ws.cuh), ldmask = bytes per row
     Ref out; int ldo;          // [rows, ldo]
     int rows, cols;            // cols % 4 == 0, every leading dimension % 4 == 0, 16-byte aligned bases (checked by the host)
 };
@@ -217,15 +218,25 @@ __global__ void __launch_bounds__(RANK1_THREADS) rank1_mask_kernel(const Rank1Ta
     const int rg = idx / c4n, c = (idx - rg * c4n) << 2;
     const int row0 = rg * RANK1_ROWS;
     if (row0 >= T.rows) return;
-    const float* mask = as.base[T.mask.arena] + (long long)seed * as.stride[T.mask.arena] + T.mask.off + c;
+    const float* mask = as.base[T.mask.arena] + (long long)seed * as.stride[T.mask.arena] + T.mask.off + (T.mask_bits ? 0 : c);
     const float* dq = as.base[T.dq.arena] + (long long)seed * as.stride[T.dq.arena] + T.dq.off;
     const float* w = as.base[T.w3.arena] + (long long)seed * as.stride[T.w3.arena] + T.w3.off + c;
     float* out = as.base[T.out.arena] + (long long)seed * as.stride[T.out.arena] + T.out.off + c;
     float4 m[RANK1_ROWS];
+    if (T.mask_bits) {
+        // one byte per (row, 4 columns): bit j = column c + j
+        const uint8_t* mw = reinterpret_cast<const uint8_t*>(mask) + (c >> 2);
 #pragma unroll
-    for (int r = 0; r < RANK1_ROWS; ++r)
-        m[r] = (row0 + r < T.rows) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)(row0 + r) * T.ldmask))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < RANK1_ROWS; ++r) {
+            const uint32_t w = (row0 + r < T.rows) ? (uint32_t)__ldg(mw + (long long)(row0 + r) * T.ldmask) : 0u;
+            m[r] = make_float4((w & 1u) ? 1.f : 0.f, (w & 2u) ? 1.f : 0.f, (w & 4u) ? 1.f : 0.f, (w & 8u) ? 1.f : 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < RANK1_ROWS; ++r)
+            m[r] = (row0 + r < T.rows) ? __ldg(reinterpret_cast<const float4*>(mask + (long long)(row0 + r) * T.ldmask))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float4 acc[RANK1_ROWS];
 #pragma unroll
     for (int r = 0; r < RANK1_ROWS; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);

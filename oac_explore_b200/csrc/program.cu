@@ -33,6 +33,7 @@ namespace oac {
 
 static int sm_count();
 constexpr int OAC_E_CHAIN_UNAVAILABLE = -101;     // internal: finalize() asks for a rebuild without strip-fused forward chains
+constexpr int OAC_E_BITS_UNAVAILABLE = -102;      // internal: finalize() asks for a rebuild without sign-bit masks
 constexpr int OAC_E_SPLIT_UNAVAILABLE = -100;      // internal: finalize() asks for a rebuild without gradient-store stages
 static inline int pad4(int x) { return (x + 3) & ~3; }
 static inline long long pad4ll(long long x) { return (x + 3) & ~3ll; }
@@ -150,6 +151,7 @@ struct Stage {
     int use_tc = 0, bn = 0, tmem_cols = 0, n_main = 1;     // tcgen05 path
     // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
     int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
+    int ws_mask_bits = 0;       // every task of this masked dX stage reads sign-bit words (gemm_ws_kernel<.., .., true>)
     int ws_pair = 0;            // CTA-pair kernel (gemm_ws2.cuh: tcgen05.mma.cta_group::2, 256-row tiles)
     int chain = 0;              // > 0: strip-fused forward chain of this many layers (gemm_chain.cuh); tasks are layer-major
     int chain_strips0[WS_MAX_TASKS + 1];
@@ -191,6 +193,7 @@ struct OacTrainer {
     float* host_scalars = nullptr;   // OacBuffers::host_scalars
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_ws2 = true;     // OAC_NO_WS2=1: single-CTA tiles only, no CTA pairs (A/B measurement aid)
+    bool allow_bits = true;    // OAC_NO_MASK_BITS=1: masked dX epilogues read the fp32 activations instead of sign-bit words (A/B measurement aid)
     bool allow_chain = true;   // OAC_NO_CHAIN=1: one launch per forward layer instead of strip-fused chains (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
     bool allow_lanes = true;   // OAC_NO_LANES=1: strictly linear stage order (A/B measurement aid)
@@ -219,11 +222,32 @@ struct Builder {
         // (OAC_SPLIT_MIN_SEEDS: measurement aid -- groups below it keep the Adam update fused into the dW epilogue)
         static const int split_min = getenv("OAC_SPLIT_MIN_SEEDS") ? atoi(getenv("OAC_SPLIT_MIN_SEEDS")) : 0;
         split_adam = tensor_glue && tr.allow_split && tr.allow_ws && c.n_seeds >= split_min;
+        use_bits = tensor_glue && tr.allow_ws && tr.allow_bits && (H % 64) == 0;
         if (split_adam) grad = work(L.adam_floats);
     }
     // Same regime: the weight-gradient GEMMs store plain gradients (laid out like the trainable prefix of the
     // parameter arena) and a streaming kernel applies Adam + Polyak to whole nets (adam_stream.cuh).
     bool split_adam;
+    // Sign bits of the hidden activations (gemm_ws.cuh): forward stages on the TMA + tcgen05 path store one
+    // byte per row and 4 columns next to h1 / h2, the masked dX stages and the rank-1 pass read those instead of the fp32
+    // activation.  Registered per activation buffer; fwd() / dx() translate a Ref into the buffer to the matching words.
+    bool use_bits = false;
+    struct BitMap { Ref h; long long len; Ref bits; };
+    std::vector<BitMap> bitmaps;
+    void add_bits(Ref h, long long rows) {
+        if (!use_bits) return;
+        BitMap b; b.h = h; b.len = rows * H; b.bits = work(rows * (H / 16));      // H / 4 bytes per row
+        bitmaps.push_back(b);
+    }
+    // words of the rows starting at `r` (a row-aligned Ref into a registered activation), or false
+    bool bits_of(Ref r, Ref* out) const {
+        for (const BitMap& b : bitmaps)
+            if (r.arena == b.h.arena && r.off >= b.h.off && r.off < b.h.off + b.len && ((r.off - b.h.off) % H) == 0) {
+                *out = Ref{b.bits.arena, b.bits.off + (r.off - b.h.off) / H * (H / 16)};
+                return true;
+            }
+        return false;
+    }
     Ref grad{AR_WORK, 0};
     std::vector<AdamSeg> pending_segs;
     void adam_seg(int ni, int ti, float lr, int counter) {
@@ -286,6 +310,8 @@ struct Builder {
         g.B = w; g.ldb = ldw; g.b_trans = 0;
         g.C = y; g.ldc = ldy; g.M = M; g.N = N; g.K = K;
         g.epi = relu_ ? EPI_BIAS_RELU : EPI_BIAS; g.bias = b;
+        Ref bw;
+        if (relu_ && N == H && ldy == H && bits_of(y, &bw)) { g.bits = bw; g.ldbits = H / 4; }
         s.gemm.push_back(g);
     }
     // dX[M,Kin] = (dY[M,Nout] W[Nout,Kin]) * (mask > 0)      (mask.arena < 0: no mask)
@@ -295,6 +321,8 @@ struct Builder {
         g.B = w; g.ldb = ldw; g.b_trans = 1;
         g.C = out; g.ldc = ldo; g.M = M; g.N = Kin; g.K = Nout;
         g.epi = use_mask ? EPI_MASK : EPI_STORE; g.mask = mask; g.ldmask = ldmask;
+        Ref bw;
+        if (use_mask && Kin == H && ldmask == H && bits_of(mask, &bw)) { g.mask = bw; g.ldmask = H / 4; g.mask_bits = 1; }
         s.gemm.push_back(g);
     }
     // W[Nout,Kin] <- Adam(dY[rows,Nout]^T X[rows,Kin]); bias <- Adam(colsum dY)
@@ -320,6 +348,7 @@ struct Builder {
     PolAct alloc_pol(int nblk) {
         PolAct a; a.rows = nblk * B;
         a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
+        add_bits(a.h1, a.rows); add_bits(a.h2, a.rows);
         a.head = work((long long)a.rows * pad4(2 * A));
         a.save = work((long long)a.rows * 4 * A);
         return a;
@@ -328,6 +357,7 @@ struct Builder {
     CritAct alloc_crit(int nblk, int heads) {
         CritAct a; a.rows = nblk * B;
         a.h1 = work((long long)a.rows * H); a.h2 = work((long long)a.rows * H);
+        add_bits(a.h1, a.rows); add_bits(a.h2, a.rows);
         a.q = work((long long)a.rows * heads);
         a.dq = work((long long)a.rows * pad4(heads));         // leading dimension pad4(heads): TMA needs 16-byte row strides
         a.dh2 = work((long long)a.rows * H); a.dh1 = work((long long)a.rows * H);
@@ -397,6 +427,8 @@ struct Builder {
         r.dq = Ref{a.dq.arena, a.dq.off + (long long)row0 * pad4(n.n_out)}; r.dq_ld = pad4(n.n_out);
         r.w3 = P(n.off_w2); r.n_heads = n.n_out;
         r.mask = Ref{a.h2.arena, a.h2.off + ro}; r.ldmask = H;
+        Ref bw;
+        if (bits_of(r.mask, &bw)) { r.mask = bw; r.ldmask = H / 4; r.mask_bits = 1; }
         r.out = Ref{a.dh2.arena, a.dh2.off + ro}; r.ldo = H;
         r.rows = B; r.cols = H;
         s.r1.push_back(r);
@@ -939,6 +971,13 @@ static int ws_plan(OacTrainer& t, Stage& s) {
         g.tile0 = t0; t0 += g.tiles_m * g.tiles_n;
         bn_max = std::max(bn_max, g.bn);
     }
+    int n_mb = 0;
+    for (auto& g : s.gemm) {
+        if ((g.ldbits > 0 || g.mask_bits) && (g.bn & 31)) return set_error(OAC_E_BITS_UNAVAILABLE, "sign-bit masks need 32-column aligned tiles");
+        n_mb += g.mask_bits ? 1 : 0;
+    }
+    if (n_mb != 0 && (n_mb != (int)s.gemm.size() || pair)) return set_error(OAC_E_BITS_UNAVAILABLE, "sign-bit masks: mixed stage");
+    s.ws_mask_bits = n_mb != 0;
     s.ws_tiles_per_seed = t0;
     s.ws_pair = pair ? 1 : 0;
     s.ws_slot_bytes = (int)WS_A_BYTES + (pair ? bn_max / 2 : bn_max) * (WS_KC * 4);
@@ -1133,6 +1172,8 @@ static int finalize(OacTrainer& t) {
                     if (int e = ws_plan(t, s)) return e;
                     continue;
                 }
+                for (auto& g : s.gemm)
+                    if (g.ldbits > 0 || g.mask_bits) return set_error(OAC_E_BITS_UNAVAILABLE, "sign-bit masks need the TMA path");
                 for (auto& g : s.gemm)
                     if (g.epi == EPI_GRAD) return set_error(OAC_E_SPLIT_UNAVAILABLE, "gradient-store stages need the TMA path");
                 // tcgen05 path: 128 x BN tiles.  Pick the largest BN that still fills the chip.
@@ -1374,6 +1415,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                     return 0;
                 }
                 if (!s.a_trans && !s.b_trans) launch_pdl(gemm_ws_kernel<false, false>, wg, wb, s.smem, st, wp);
+                else if (!s.a_trans && s.ws_mask_bits) launch_pdl(gemm_ws_kernel<false, true, true>, wg, wb, s.smem, st, wp);
                 else if (!s.a_trans) launch_pdl(gemm_ws_kernel<false, true>, wg, wb, s.smem, st, wp);
                 else launch_pdl(gemm_ws_kernel<true, true>, wg, wb, s.smem, st, wp);
                 OAC_CUDA(cudaGetLastError());
@@ -1513,6 +1555,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     { const char* nl = getenv("OAC_NO_LANES"); t->allow_lanes = !(nl && nl[0] == '1'); }
     { const char* n2 = getenv("OAC_NO_WS2"); t->allow_ws2 = !(n2 && n2[0] == '1'); }
     { const char* nc = getenv("OAC_NO_CHAIN"); t->allow_chain = !(nc && nc[0] == '1'); }
+    { const char* nb = getenv("OAC_NO_MASK_BITS"); t->allow_bits = !(nb && nb[0] == '1'); }
     { const char* nk = getenv("OAC_NO_SK_TMA"); t->allow_sk_tma = !(nk && nk[0] == '1'); }
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
@@ -1556,6 +1599,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_ws((const void*)gemm_ws_kernel<false, false>);
         opt_ws((const void*)gemm_ws_kernel<false, true>);
         opt_ws((const void*)gemm_ws_kernel<true, true>);
+        opt_ws((const void*)gemm_ws_kernel<false, true, true>);
         opt_ws((const void*)gemm_ws2_kernel<false, false>);
         opt_ws((const void*)gemm_ws2_kernel<false, true>);
         opt_ws((const void*)gemm_ws2_kernel<true, true>);
@@ -1567,29 +1611,20 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         if (e != cudaSuccess) { delete t; return set_cuda_error(e, "cudaFuncSetAttribute"); }
     }
     int fe = finalize(*t);
-    if (fe == OAC_E_CHAIN_UNAVAILABLE) {
-        // a forward chain cannot be fused (tensor maps unavailable / misaligned buffers / shapes): one launch per layer
+    // A feature of the tensor-core program that this configuration cannot have (tensor maps unavailable / misaligned buffers /
+    // shapes) is switched off and the program is rebuilt: strip-fused forward chains -> one launch per layer, sign-bit masks
+    // -> fp32 activations as masks, gradient-store stages + streaming Adam -> fused Adam epilogues.
+    for (int attempt = 0; attempt < 3 && (fe == OAC_E_CHAIN_UNAVAILABLE || fe == OAC_E_BITS_UNAVAILABLE || fe == OAC_E_SPLIT_UNAVAILABLE); ++attempt) {
+        if (fe == OAC_E_CHAIN_UNAVAILABLE) t->allow_chain = false;
+        else if (fe == OAC_E_BITS_UNAVAILABLE) t->allow_bits = false;
+        else t->allow_split = false;
         for (void* p : t->dev_allocs) cudaFree(p);
         t->dev_allocs.clear(); t->stages.clear(); t->work_cursor = 0;
-        t->allow_chain = false;
         Builder b2(*t);
         if (cfg->algo == OAC_ALGO_SAC) b2.build_sac();
         else if (cfg->algo == OAC_ALGO_POAC) b2.build_poac();
         else b2.build_goac();
-        if (t->work_cursor > t->lay.work_floats) { oac_trainer_destroy(t); return set_error(OAC_E_INVALID, "internal: work arena"); }
-        fe = finalize(*t);
-    }
-    if (fe == OAC_E_SPLIT_UNAVAILABLE) {
-        // no TMA path for a gradient-store stage (tensor maps unavailable / misaligned buffers): rebuild the program
-        // with the fused Adam epilogues
-        for (void* p : t->dev_allocs) cudaFree(p);
-        t->dev_allocs.clear(); t->stages.clear(); t->work_cursor = 0;
-        t->allow_split = false;
-        Builder b2(*t);
-        if (cfg->algo == OAC_ALGO_SAC) b2.build_sac();
-        else if (cfg->algo == OAC_ALGO_POAC) b2.build_poac();
-        else b2.build_goac();
-        if (t->work_cursor > t->lay.work_floats) { oac_trainer_destroy(t); return set_error(OAC_E_INVALID, "internal: work arena"); }
+        if (t->work_cursor + WORK_SLACK > t->lay.work_floats) { oac_trainer_destroy(t); return set_error(OAC_E_INVALID, "internal: work arena"); }
         fe = finalize(*t);
     }
     if (fe) { oac_trainer_destroy(t); return fe; }
@@ -1770,6 +1805,7 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);

@@ -103,3 +103,25 @@ def test_poac_goac_large_batch_tensor_path(share):
             if gref is None:
                 continue
             assert rel_err(m[k].cpu() / 0.1, gref) <= 3e-2, (gname, k, rel_err(m[k].cpu() / 0.1, gref))
+
+
+def test_sign_bit_masks_equal_fp32_masks(monkeypatch):
+    """The masked dX stages read sign-bit words written by the forward epilogues (gemm_ws / gemm_ws2 / gemm_chain) instead
+    of the fp32 activations: same mask, so the whole step must be BITWISE the same as with OAC_NO_MASK_BITS=1 -- for the
+    strip-fused chains of a small group and for the per-layer stages (CTA pairs included) of a larger one."""
+    from oac_explore_b200.seed_group import SACSeedGroup
+    O, A, H, B = 376, 17, 256, 256
+    for S in (8, 32):
+        res = []
+        for no_bits in ("0", "1"):
+            monkeypatch.setenv("OAC_NO_MASK_BITS", no_bits)
+            grp = SACSeedGroup(list(range(S)), O, A, hidden=H, batch=B, gemm_path=1, policy_lr=3e-4, qf_lr=3e-4)
+            for step in range(2):
+                for slot in range(S):
+                    grp.load_batch(slot, synth_batch(B, O, A, seed=1000 + 10 * step + slot))
+                    e_ = synth_eps(2, B, A, seed=2000 + 10 * step + slot)
+                    grp.inject_noise(slot, e_[0], e_[1])
+                grp.step(external_eps=True)
+            torch.cuda.synchronize()
+            res.append((grp.engine.params.clone(), grp.engine.adam_v.clone(), grp.stats().clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2]), S

@@ -28,4 +28,8 @@ ncu --set full --clock-control none -k regex:"gemm_ws|adam_stream|critic_head|po
 ncu --set full --clock-control none -k regex:"gemm_chain|gemm_ws|adam_stream|critic_head|policy_head|policy_grad|rank1|step_tail|replay_gather" --launch-skip 19 --launch-count 19 -o $O/${T}_8seeds_tf32 -f \
     python tools/profile_step.py --steps 2 --seeds 8 --gemm-path tf32 > $O/${T}_full_8.log 2>&1
 tail -2 $O/${T}_full_64.log
-ls -la $O/${T}_*.ncu-rep
+# gpurun brings back at most 64 MiB: keep the raw metric pages (what tools/summarize_profiles.py reads), drop the reports
+for r in single_fp32 64seeds_tf32 8seeds_tf32; do
+  if [ -f $O/${T}_$r.ncu-rep ]; then ncu -i $O/${T}_$r.ncu-rep --page raw --csv > $O/${T}_${r}_raw.csv 2>/dev/null; rm -f $O/${T}_$r.ncu-rep; fi
+done
+ls -la $O/${T}_*

@@ -44,9 +44,17 @@ def launch_list(name, per_step):
     print("\n".join(out[-8:]))
 
 
-def full_report(rep, out_name):
+def raw_page(rep):
+    """raw metric page of a report: the exported <name>_raw.csv (tools/run_profiles.sh) or, if the report itself is here, ncu -i"""
     path = os.path.join(G, rep)
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    csv_path = path.replace(".ncu-rep", "_raw.csv")
+    if os.path.exists(csv_path):
+        return open(csv_path).read()
+    return subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
+def full_report(rep, out_name):
+    txt = raw_page(rep)
     rows = list(csv.reader(txt.splitlines()))
     hdr = rows[0]
     out = ["# %s (ncu --set full --clock-control none), one line block per profiled launch" % rep]
@@ -63,8 +71,7 @@ def full_report(rep, out_name):
 
 def traffic(rep, kernel_substr):
     """dram read+write bytes per launch of the longest launch of the named kernel in a --set full report."""
-    path = os.path.join(G, rep)
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = raw_page(rep)
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     best = None
@@ -86,7 +93,7 @@ def traffic(rep, kernel_substr):
 if __name__ == "__main__":
     import json
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01n"
-    have = lambda n: os.path.exists(os.path.join(G, n))
+    have = lambda n: os.path.exists(os.path.join(G, n)) or os.path.exists(os.path.join(G, n.replace(".ncu-rep", "_raw.csv")))
     tpath = os.path.join(P, "traffic.json")
     tr = json.load(open(tpath)) if os.path.exists(tpath) else {}
     # a configuration whose kernels did not change since an earlier tag keeps that tag's files (and its traffic entry)
