@@ -105,7 +105,10 @@ __device__ __forceinline__ void adam_core(float g, float& p, float& m, float& v,
 // Epilogue of ONE accumulator tile (rows m0 + 32 q .. + 31 of this warp's TMEM lane quarter, the 64-column slabs sl = hsel,
 // hsel + 2, ..): tcgen05.ld -> per-warp slab -> coalesced float4 rows -> bias / ReLU (+ mask bits) | ReLU-derivative mask |
 // gradient store | Adam (+ Polyak).  Shared by gemm_ws_kernel and its CTA-pair variant (gemm_ws2.cuh).
-template <bool A_MN, bool B_MN, bool MASK_BITS = false>
+// VARIANT: (K, MN) stages -- 1: the masks are sign bits; (MN, MN) stages -- 1: the fused Adam (+ Polyak) epilogue is compiled in
+// (few-seed programs; the many-seed program stores gradients, and keeping the Adam path's ~90 registers out of that
+// instantiation keeps its store loop free of spills).
+template <bool A_MN, bool B_MN, bool VARIANT = false>
 __device__ __forceinline__ void ws_tile_epilogue(const StageParams& sp, const GemmTask& T, int seed, int m0, int n0, int tn,
                                                  uint32_t t_base, float* slab, int q, int hsel, int lane) {
     float* __restrict__ m1 = sp.as.base[AR_ADAM_M];
@@ -117,9 +120,10 @@ __device__ __forceinline__ void ws_tile_epilogue(const StageParams& sp, const Ge
     float* __restrict__ C = resolve(sp.as, T.C, seed);
     // the operand layouts pin the epilogue class (dW products are the only (MN, MN) tasks, masked dX products
     // the only (K, MN) ones): dead epilogues are compiled out, which keeps their registers out of the live set
-    constexpr bool CAN_ADAM = A_MN && B_MN, CAN_MASK = !A_MN && B_MN, CAN_BITS = !A_MN && !B_MN;
+    constexpr bool CAN_ADAM = A_MN && B_MN && VARIANT, CAN_GRAD = A_MN && B_MN, CAN_MASK = !A_MN && B_MN, CAN_BITS = !A_MN && !B_MN;
+    constexpr bool MASK_BITS = VARIANT;
     const bool is_adam = CAN_ADAM && epi == EPI_ADAM;
-    const bool is_grad = CAN_ADAM && epi == EPI_GRAD;        // plain store of dW; Adam streams later (adam_stream.cuh)
+    const bool is_grad = CAN_GRAD && epi == EPI_GRAD;        // plain store of dW; Adam streams later (adam_stream.cuh)
     AdamScalars s;
     float inv_bc2 = 1.f;
     float* __restrict__ am = nullptr; float* __restrict__ av = nullptr; float* __restrict__ tg = nullptr;
@@ -319,7 +323,7 @@ __device__ __forceinline__ void ws_tile_epilogue(const StageParams& sp, const Ge
     }
 }
 
-template <bool A_MN, bool B_MN, bool MASK_BITS = false>
+template <bool A_MN, bool B_MN, bool VARIANT = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
     extern __shared__ __align__(1024) uint8_t ws_smem[];
     __shared__ __align__(8) uint64_t s_full[WS_MAX_SLOTS], s_empty[WS_MAX_SLOTS], s_tfull[2], s_tempty[2];
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(WsParams wp) {
             mbar_wait_relaxed(&s_tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-            ws_tile_epilogue<A_MN, B_MN, MASK_BITS>(sp, T, seed, tm * WS_BM, tn * T.bn, tn, t_base, slab, q, hsel, lane);
+            ws_tile_epilogue<A_MN, B_MN, VARIANT>(sp, T, seed, tm * WS_BM, tn * T.bn, tn, t_base, slab, q, hsel, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_tempty[buf]);

@@ -151,6 +151,7 @@ struct Stage {
     int use_tc = 0, bn = 0, tmem_cols = 0, n_main = 1;     // tcgen05 path
     // warp-specialised persistent tcgen05 path (gemm_ws.cuh)
     int use_ws = 0, ws_tiles_per_seed = 0, ws_slots = 0, ws_slot_bytes = 0, ws_grid = 0;
+    int ws_adam = 0;            // a dW stage with fused Adam epilogues (gemm_ws_kernel<true, true, true>)
     int ws_mask_bits = 0;       // every task of this masked dX stage reads sign-bit words (gemm_ws_kernel<.., .., true>)
     int ws_pair = 0;            // CTA-pair kernel (gemm_ws2.cuh: tcgen05.mma.cta_group::2, 256-row tiles)
     int chain = 0;              // > 0: strip-fused forward chain of this many layers (gemm_chain.cuh); tasks are layer-major
@@ -978,6 +979,7 @@ static int ws_plan(OacTrainer& t, Stage& s) {
     }
     if (n_mb != 0 && (n_mb != (int)s.gemm.size() || pair)) return set_error(OAC_E_BITS_UNAVAILABLE, "sign-bit masks: mixed stage");
     s.ws_mask_bits = n_mb != 0;
+    for (auto& g : s.gemm) if (g.epi == EPI_ADAM) s.ws_adam = 1;
     s.ws_tiles_per_seed = t0;
     s.ws_pair = pair ? 1 : 0;
     s.ws_slot_bytes = (int)WS_A_BYTES + (pair ? bn_max / 2 : bn_max) * (WS_KC * 4);
@@ -1417,6 +1419,7 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                 if (!s.a_trans && !s.b_trans) launch_pdl(gemm_ws_kernel<false, false>, wg, wb, s.smem, st, wp);
                 else if (!s.a_trans && s.ws_mask_bits) launch_pdl(gemm_ws_kernel<false, true, true>, wg, wb, s.smem, st, wp);
                 else if (!s.a_trans) launch_pdl(gemm_ws_kernel<false, true>, wg, wb, s.smem, st, wp);
+                else if (s.ws_adam) launch_pdl(gemm_ws_kernel<true, true, true>, wg, wb, s.smem, st, wp);
                 else launch_pdl(gemm_ws_kernel<true, true>, wg, wb, s.smem, st, wp);
                 OAC_CUDA(cudaGetLastError());
                 return 0;
@@ -1600,6 +1603,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_ws((const void*)gemm_ws_kernel<false, true>);
         opt_ws((const void*)gemm_ws_kernel<true, true>);
         opt_ws((const void*)gemm_ws_kernel<false, true, true>);
+        opt_ws((const void*)gemm_ws_kernel<true, true, true>);
         opt_ws((const void*)gemm_ws2_kernel<false, false>);
         opt_ws((const void*)gemm_ws2_kernel<false, true>);
         opt_ws((const void*)gemm_ws2_kernel<true, true>);
@@ -1806,6 +1810,7 @@ extern "C" int oac_gemm_debug(int32_t gemm_path, int32_t a_trans, int32_t b_tran
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute((const void*)gemm_ws_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute((const void*)gemm_ws2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
