@@ -210,8 +210,10 @@ constexpr int RANK1_THREADS = 256;
 constexpr int RANK1_ROWS = 4;      // rows per thread: four independent 16-byte mask loads in flight per thread
 
 // one thread = one 4-column group of RANK1_ROWS consecutive rows (the head row slice w is shared by them)
-__global__ void __launch_bounds__(RANK1_THREADS) rank1_mask_kernel(const Rank1Task* __restrict__ tasks, ArenaSet as) {
-    const Rank1Task T = tasks[blockIdx.y];
+// (the task is read in place: a by-value copy of the struct lived in local memory -- 96 bytes of stack and 94 registers, two
+// CTAs per SM -- and the pass ran at 1.6 TB/s of stores, latency-bound: ncu r02b_64seeds_tf32_full.txt)
+__global__ void __launch_bounds__(RANK1_THREADS, 3) rank1_mask_kernel(const Rank1Task* __restrict__ tasks, ArenaSet as) {
+    const Rank1Task& T = tasks[blockIdx.y];
     const int seed = blockIdx.z;
     const int c4n = T.cols >> 2;
     const int idx = blockIdx.x * RANK1_THREADS + threadIdx.x;

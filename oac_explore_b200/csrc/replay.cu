@@ -87,6 +87,59 @@ __global__ void __launch_bounds__(GATHER_THREADS) replay_gather_kernel(GatherArg
     }
 }
 
+// Many sampled rows per launch (seed groups: 16 384 rows for 64 seeds): one WARP per transition, every 16-byte piece of its
+// obs and next_obs rows requested before the first store (six loads in flight per lane at O = 376), 8 transitions per CTA.
+// The one-CTA-per-row kernel above leaves each CTA with two dependent memory latencies (index, then row) and ~3 KB in
+// flight: at 16 resident CTAs per SM it moved 3.8 TB/s of read + written bytes (ncu: r02_64seeds_tf32_full.txt).
+constexpr int GW_WARPS = 8, GW_MAX_IT = 4;      // rows of up to 32 * 4 float4 = 512 floats
+__global__ void __launch_bounds__(GW_WARPS * 32) replay_gather_warp_kernel(GatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * GW_WARPS + (threadIdx.x >> 5);       // sample within the batch
+    const int s = blockIdx.y;                                       // seed
+    const int B = a.batch, O = a.st.obs_dim, A = a.st.act_dim;
+    if (i >= B) return;
+    const long long r = __ldg(a.idx + (long long)s * B + i);
+    const long long so = (long long)s * a.dst.seed_stride;
+    float* x = a.dst.x + so;
+    const int ld = a.dst.x_ld;
+    auto xrow = [&](int block) -> float* { return block < 0 ? nullptr : x + ((long long)block * B + i) * ld; };
+    const int n4 = O >> 2;
+    const float4* so4 = reinterpret_cast<const float4*>(a.st.obs + r * O);
+    const float4* sn4 = reinterpret_cast<const float4*>(a.st.next_obs + r * O);
+    float4 vo[GW_MAX_IT], vn[GW_MAX_IT];
+#pragma unroll
+    for (int k = 0; k < GW_MAX_IT; ++k) {
+        const int j = lane + 32 * k;
+        if (j < n4) { vo[k] = __ldg(so4 + j); vn[k] = __ldg(sn4 + j); }
+    }
+    float av = 0.f, rw = 0.f, tm = 0.f, cn = 0.f;
+    if (lane < A) av = __ldg(a.st.actions + r * A + lane);           // A <= 32 (checked by the host)
+    if (lane == 0) {
+        rw = __ldg(a.st.rewards + r); tm = __ldg(a.st.terminals + r);
+        if (a.st.counts && a.dst.counts) cn = a.st.counts[r];
+    }
+    float4* d0 = reinterpret_cast<float4*>(xrow(a.dst.obs_blocks[0]));
+    float4* d1 = reinterpret_cast<float4*>(xrow(a.dst.obs_blocks[1]));
+    float4* d2 = reinterpret_cast<float4*>(xrow(a.dst.obs_blocks[2]));
+    float4* dn = reinterpret_cast<float4*>(xrow(a.dst.next_block));
+#pragma unroll
+    for (int k = 0; k < GW_MAX_IT; ++k) {
+        const int j = lane + 32 * k;
+        if (j < n4) {
+            d0[j] = vo[k];
+            if (d1) d1[j] = vo[k];
+            if (d2) d2[j] = vo[k];
+            dn[j] = vn[k];
+        }
+    }
+    if (lane < A) xrow(a.dst.act_block)[O + lane] = av;
+    if (lane == 0) {
+        a.dst.rewards[so + i] = rw;
+        a.dst.terminals[so + i] = tm;
+        if (a.st.counts && a.dst.counts) a.dst.counts[so + i] = cn;
+    }
+}
+
 // counts[idx] += 1 once per DISTINCT index (numpy fancy-index "+=", replay_buffer.py:195).  The index array may live in
 // mapped pinned HOST memory (the single-seed path reads it in place): it is staged into shared memory with ONE coalesced
 // pass, and the earlier-duplicate scan of every sample then runs on shared memory (it used to re-read idx[] from its home
@@ -181,7 +234,14 @@ extern "C" int oac_replay_gather(const OacReplayStore* store, const int64_t* ind
     if (store->counts && seeds > 1) return set_error(OAC_E_UNSUPPORTED, "counts with a store shared by several seeds");
     GatherArgs a{*store, *dst, indices, batch};
     cudaStream_t st = (cudaStream_t)stream;
-    replay_gather_kernel<<<dim3(batch, seeds), GATHER_THREADS, 0, st>>>(a);
+    // seed groups (thousands of rows per launch) take the warp-per-row kernel when every row is made of whole, aligned
+    // 16-byte pieces; a single trainer's 256 rows keep one CTA per row (latency: more SMs per row)
+    const bool al16 = ((reinterpret_cast<uintptr_t>(store->obs) | reinterpret_cast<uintptr_t>(store->next_obs) |
+                        reinterpret_cast<uintptr_t>(dst->x)) & 15) == 0;
+    const bool warp_rows = (long long)batch * seeds >= 2048 && (store->obs_dim & 3) == 0 && (dst->x_ld & 3) == 0 &&
+                           (dst->seed_stride & 3) == 0 && al16 && store->obs_dim <= 128 * GW_MAX_IT && store->act_dim <= 32;
+    if (warp_rows) replay_gather_warp_kernel<<<dim3((batch + GW_WARPS - 1) / GW_WARPS, seeds), GW_WARPS * 32, 0, st>>>(a);
+    else replay_gather_kernel<<<dim3(batch, seeds), GATHER_THREADS, 0, st>>>(a);
     OAC_CUDA(cudaGetLastError());
     if (store->counts) {
         launch_counts_bump(store->counts, indices, batch, st);

@@ -64,6 +64,34 @@ def test_group_gather_shared_store():
     assert torch.isfinite(grp.stats()).all()
 
 
+@pytest.mark.parametrize("O,A", [(376, 17), (44, 6), (11, 3)])
+def test_group_gather_many_rows_bit_exact(O, A):
+    """>= 2048 sampled rows per launch take the warp-per-row gather kernel (16-byte pieces, rows of whole float4); other
+    shapes fall back to one CTA per row.  Either way every X block / IO slot is a bit-exact copy of the store rows."""
+    from oac_explore_b200.seed_group import SACSeedGroup
+    from oac_explore_b200.replay_buffer import ReplayBuffer
+    B, H, N, S = 256, 32, 5000, 9
+    rb = ReplayBuffer(N, Box(O), Box(A))
+    g = torch.Generator(device='cuda').manual_seed(1)
+    rb._observations.normal_(generator=g); rb._next_obs.normal_(generator=g)
+    rb._actions.uniform_(-1, 1, generator=g); rb._rewards.normal_(generator=g)
+    rb._terminals.copy_((torch.rand(rb._terminals.shape, generator=g, device='cuda') < 0.1).float())
+    rb._size = N
+    grp = SACSeedGroup(list(range(S)), O, A, hidden=H, batch=B, gemm_path=0)
+    idx = np.random.RandomState(3).randint(0, N, (S, B))
+    grp.gather(rb, idx)
+    torch.cuda.synchronize()
+    e = grp.engine
+    for s in range(S):
+        it = torch.from_numpy(idx[s]).cuda()
+        assert torch.equal(e.x_block(2, seed=s)[:, :O], rb._observations[it])
+        assert torch.equal(e.x_block(1, seed=s)[:, :O], rb._observations[it])
+        assert torch.equal(e.x_block(2, seed=s)[:, O:O + A], rb._actions[it])
+        assert torch.equal(e.x_block(3, seed=s)[:, :O], rb._next_obs[it])
+        assert torch.equal(e.io_view(e.lay.off_rewards, (B,), seed=s), rb._rewards[it].reshape(-1))
+        assert torch.equal(e.io_view(e.lay.off_terminals, (B,), seed=s), rb._terminals[it].reshape(-1))
+
+
 @pytest.mark.parametrize("share", [True, False])
 def test_particle_and_gaussian_groups_equal_singles(share):
     """P-OAC and G-OAC seeds batched in one engine (ParticleSeedGroup / GaussianSeedGroup) == the same seeds trained one by
