@@ -19,6 +19,12 @@
 // converted accumulator back while the next layer's MMAs run): every consumer of a stored hidden activation either rounds
 // it to tf32 itself (TFLOAT32 tensor maps of the dW products: rounding is idempotent) or only tests its sign (ReLU masks),
 // except the critic head's fp32 dot product, which then sees tf32-rounded h2 rows (covered by the oracle's tf32 model).
+//
+// The same machine runs two BACKWARD chains of the many-seed program (B_MN = true: the weights are read [out, in], i.e. M/N-
+// contiguous, through one 4-d TMA box per chunk; epilogues apply ReLU-derivative masks from the sign bytes instead of bias /
+// ReLU):
+//   policy-loss gradient through a critic:  dh1 = (dh2 W2) * 1[h1 > 0]  ->  da = dh1 W0[:, O:O+A]     (dh1 never leaves the SM)
+//   policy backward:                        dh2 = (dhead Wh) * 1[h2 > 0] -> dh1 = (dh2 W2) * 1[h1 > 0]  (both stored: dW operands)
 #pragma once
 #include "gemm_ws.cuh"
 
@@ -56,6 +62,7 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t a_tmem, u
         ::"r"(tmem_d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
+template <bool B_MN>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams cp) {
     extern __shared__ __align__(1024) uint8_t ws_smem[];
     __shared__ __align__(8) uint64_t s_full[WS_MAX_SLOTS], s_empty[WS_MAX_SLOTS];
@@ -118,7 +125,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                         const uint32_t bar = smem_u32(&s_full[slot]);
                         mbar_expect_tx(bar, bytes);
                         if (l == 0) tma_load_3d(sa, ta, c * WS_KC, m0, seed, bar);
-                        tma_load_3d(sb, tb, c * WS_KC, 0, seed, bar);
+                        if (!B_MN) tma_load_3d(sb, tb, c * WS_KC, 0, seed, bar);
+                        else tma_load_4d(sb, tb, 0, c * WS_KC, 0, seed, bar);            // all 32-wide atoms of the chunk in one box
                         if (++slot == cp.n_slots) { slot = 0; ph ^= 1u; }
                     }
                 }
@@ -150,19 +158,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                     }
                     if (l == 2) mbar_wait_relaxed(&s_aready[1], par);
                     tc_fence_after();
-                    const uint32_t idesc = umma_idesc_tf32(WS_BM, bn, false, false);
+                    const uint32_t idesc = umma_idesc_tf32(WS_BM, bn, false, B_MN);
                     for (int c = 0; c < nch; ++c) {
                         mbar_wait_relaxed(&s_full[slot], ph);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(ring + (size_t)slot * cp.slot_bytes), sb = sa + WS_A_BYTES;
                         const int ksteps = (min(WS_KC, K - c * WS_KC) + 7) >> 3;
                         uint64_t ad = umma_desc(sa, 16, 1024, 2);
-                        uint64_t bd = umma_desc(sb, 16, 1024, 2);
+                        uint64_t bd = B_MN ? umma_desc(sb, 4096, 512, 1) : umma_desc(sb, 16, 1024, 2);
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
                             if (l == 0) umma_tf32(d, ad, bd, idesc, acc);
                             else umma_tf32_ta(d, a_t + (uint32_t)(c * WS_KC + ks * 8), bd, idesc, acc);
-                            ad += 2u; bd += 2u;
+                            ad += 2u; bd += B_MN ? 64u : 2u;
                         }
                         umma_commit(&s_empty[slot]);
                         if (++slot == cp.n_slots) { slot = 0; ph ^= 1u; }
@@ -191,15 +199,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                 const bool relu_ = T.epi == EPI_BIAS_RELU;
                 const bool to_tmem = l + 1 < NL;                 // the next layer reads this one from tensor memory
                 float* __restrict__ C = resolve(sp.as, T.C, seed);
-                const float* __restrict__ bias = resolve(sp.as, T.bias, seed);
-                uint8_t* __restrict__ bits_out = (T.ldbits > 0 && relu_) ? reinterpret_cast<uint8_t*>(resolve(sp.as, T.bits, seed)) : nullptr;
+                const float* __restrict__ bias = (!B_MN && (T.epi == EPI_BIAS_RELU || T.epi == EPI_BIAS)) ? resolve(sp.as, T.bias, seed) : nullptr;
+                uint8_t* __restrict__ bits_out = (!B_MN && T.ldbits > 0 && relu_) ? reinterpret_cast<uint8_t*>(resolve(sp.as, T.bits, seed)) : nullptr;
+                const bool rows_live = m0 + q * 32 < M;
+                // backward chains: the sign bytes of this thread's row (lane = row), 8 bytes per 32 columns, requested before
+                // the accumulator is waited for: km[2 * i + hf] covers columns 64 * (hsel + 2 i) + 32 hf .. + 31
+                uint2 km[4];
+                const bool masked = B_MN && T.epi == EPI_MASK;
+                if (masked) {
+                    const int m = m0 + q * 32 + lane;
+                    const uint8_t* mrow = reinterpret_cast<const uint8_t*>(resolve(sp.as, T.mask, seed)) + (long long)m * T.ldmask;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int cb = 64 * (hsel + 2 * (i >> 1)) + 32 * (i & 1);
+                        km[i] = (rows_live && m < M && cb < bn) ? __ldg(reinterpret_cast<const uint2*>(mrow + (cb >> 2))) : make_uint2(0u, 0u);
+                    }
+                }
+                auto masked_val = [&](float x, const uint2& k, int i) {      // column i (0..31) of the group: byte i >> 2, bit i & 3
+                    const uint32_t w = (i < 16) ? k.x : k.y;
+                    return ((w >> (((i & 15) >> 2) * 8 + (i & 3))) & 1u) ? x : 0.f;
+                };
                 mbar_wait_relaxed(&s_dfull[l], par);
                 tc_fence_after();
                 const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (l == 1 ? 256u : 0u);
-                const bool rows_live = m0 + q * 32 < M;
                 if (to_tmem) {
                     // ---- phase A: convert the accumulator in place (bias, ReLU, tf32 rounding): the next layer's MMAs can start ----
-                    for (int sl = hsel; sl * WS_SLAB < bn; sl += 2) {
+                    auto convert_slab = [&](int si) {                    // this warp's slabs: hsel, hsel + 2
+                        const int sl = hsel + 2 * si;
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             const int cb = sl * WS_SLAB + 32 * hf;
@@ -210,13 +236,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                             uint32_t r[32];
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
-                                float x = v[i] + __ldg(bias + cb + i);                    // uniform address: one broadcast load
-                                if (relu_) x = relu(x);
+                                float x = v[i];
+                                if (!B_MN) {
+                                    x += __ldg(bias + cb + i);                            // uniform address: one broadcast load
+                                    if (relu_) x = relu(x);
+                                } else if (masked) x = masked_val(x, km[2 * si + hf], i);
                                 r[i] = to_tf32_rna(x);
                             }
                             tmem_st16(t_base + (uint32_t)cb, &r[0]);
                             tmem_st16(t_base + (uint32_t)(cb + 16), &r[16]);
                         }
+                    };
+                    if (B_MN) {                                          // (static slab index: the mask registers are not addressable)
+                        if (hsel * WS_SLAB < bn) convert_slab(0);
+                        if ((hsel + 2) * WS_SLAB < bn) convert_slab(1);
+                    } else {
+                        for (int si = 0; (hsel + 2 * si) * WS_SLAB < bn; ++si) convert_slab(si);
                     }
                     tmem_st_wait();
                     tc_fence_before();
@@ -225,7 +260,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                 }
                 // ---- phase B: accumulator (converted: the stored activation is the tf32-rounded one every consumer would round it
                 // to anyway -- TFLOAT32 tensor maps, sign tests) -> slab -> coalesced global store; overlaps the next layer's MMAs ----
-                for (int sl = hsel; sl * WS_SLAB < bn; sl += 2) {
+                auto store_slab = [&](int si) {
+                    const int sl = hsel + 2 * si;
                     const int c0 = sl * WS_SLAB;
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -239,8 +275,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const int n = cb + i;
-                                float x = v[i] + ((n < N) ? __ldg(bias + n) : 0.f);
-                                if (relu_) x = relu(x);
+                                float x = v[i];
+                                if (!B_MN) {
+                                    x += (n < N) ? __ldg(bias + n) : 0.f;
+                                    if (relu_) x = relu(x);
+                                } else if (masked) x = masked_val(x, km[2 * si + hf], i);
                                 v[i] = x;
                             }
                         }
@@ -273,6 +312,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_chain_kernel(ChainParams c
                         }
                     }
                     __syncwarp();
+                };
+                if (!T.no_store) {
+                    if (B_MN) {
+                        if (hsel * WS_SLAB < bn) store_slab(0);
+                        if ((hsel + 2) * WS_SLAB < bn) store_slab(1);
+                    } else {
+                        for (int si = 0; (hsel + 2 * si) * WS_SLAB < bn; ++si) store_slab(si);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -67,6 +67,7 @@ struct GemmTask {
     int mask_bits;     // EPI_MASK: `mask` holds sign bits (one byte per 4 columns, gemm_ws.cuh), ldmask = bytes per row
     Ref bits;          // EPI_BIAS_RELU on the TMA + tcgen05 path: also store the sign bits of C here (ldbits > 0)
     int ldbits;        // bytes per row (N / 4), 0 = none
+    int no_store;      // strip-fused chains: the output only feeds the next layer (tensor memory), nothing is written
     // EPI_ADAM
     long long adam_off;       // offset of C inside the Adam arenas (same as C.off: trainable prefix)
     long long adam_bias_off;

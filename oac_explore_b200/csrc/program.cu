@@ -154,6 +154,7 @@ struct Stage {
     int ws_adam = 0;            // a dW stage with fused Adam epilogues (gemm_ws_kernel<true, true, true>)
     int ws_mask_bits = 0;       // every task of this masked dX stage reads sign-bit words (gemm_ws_kernel<.., .., true>)
     int ws_pair = 0;            // CTA-pair kernel (gemm_ws2.cuh: tcgen05.mma.cta_group::2, 256-row tiles)
+    int chain_bwd = 0;          // the chain is a backward one: M/N-contiguous weights, mask / store epilogues (gemm_chain_kernel<true>)
     int chain = 0;              // > 0: strip-fused forward chain of this many layers (gemm_chain.cuh); tasks are layer-major
     int chain_strips0[WS_MAX_TASKS + 1];
     int sk_tma = 0;             // latency-regime FFMA tile with TMA-staged operands (tensor maps in ws_tmaps)
@@ -194,6 +195,7 @@ struct OacTrainer {
     float* host_scalars = nullptr;   // OacBuffers::host_scalars
     bool allow_ws = true;      // OAC_NO_WS=1 forces the per-tile tcgen05 kernel (A/B measurement aid)
     bool allow_ws2 = true;     // OAC_NO_WS2=1: single-CTA tiles only, no CTA pairs (A/B measurement aid)
+    bool allow_bwd_chain = true;   // OAC_NO_BWD_CHAIN=1: one launch per dX layer instead of the two strip-fused backward chains (A/B measurement aid)
     bool allow_bits = true;    // OAC_NO_MASK_BITS=1: masked dX epilogues read the fp32 activations instead of sign-bit words (A/B measurement aid)
     bool allow_chain = true;   // OAC_NO_CHAIN=1: one launch per forward layer instead of strip-fused chains (A/B measurement aid)
     bool allow_split = true;   // many-seed tensor-core path: gradient store + streaming Adam instead of the fused epilogue
@@ -649,9 +651,16 @@ void Builder::build_sac() {
     // gradients are complete after critic_head.  Lane 1: dW(fc1, head) -> their Adam -> pi_dh2 -> pi_dh1, next to the main
     // lane's qloss_dh1 -> dW(fc0) -> its Adam; the lanes meet at pi_da.  The GEMM stages of the two branches are planned
     // for half of the SMs each so that they really run side by side.  OAC_GROUP_LANES=0 restores the linear order (A/B aid).
+    // Strip-fused BACKWARD chains on the tensor pipe (gemm_chain.cuh, B_MN): pi_dh1 > pi_da (the policy-loss gradient through a
+    // critic: dh1 never leaves the SM) and policy_dh2 > policy_dh1; the masks are the sign bytes of the forward pass.
+    const bool bwd_chain = fuse_chain() && use_bits && t.allow_bwd_chain && !mode_b;
+    // (measured, B200: 64 seeds pi_dh1 + pi_da 43.4 -> 31.0 us, policy_dh2 + policy_dh1 26.4 -> 17.3 us, step 0.727 -> 0.709 ms.
+    // In a small group pi_dh1 already hides on a side lane -- group_lanes below -- and the fused pair would put its 19 us on the
+    // critical path instead of pi_da's 12.6: there only the policy pair is fused.)
     static const int gl_max = getenv("OAC_GROUP_LANES") ? atoi(getenv("OAC_GROUP_LANES")) : 16;
     const bool group_lanes = tensor_glue && t.allow_lanes && !mode_b && (H & 3) == 0 && c.n_seeds <= gl_max;
     const int half = sm_count() / 2;
+    const bool pi_chain = bwd_chain && !group_lanes;
     if (two_lanes && !mode_b) {
         // mode A: pi_dh2 needs the POST-step head weights, and the head gradient (dq^T h2) is complete after critic_head:
         // head Adam + pi_dh2 leave the critical chain for lane 2 and run next to qloss_dh1 / the fc1 Adam
@@ -672,12 +681,19 @@ void Builder::build_sac() {
       if (group_lanes) s.sm_budget = half;
       if (mode_b) { crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); } }
     auto policy_grad_stage = [&]() {
-        if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); sd.join = group_lanes ? 1 : 0; crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
+        if (pi_chain) {
+            Stage& sd = add_stage(ST_GEMM, "pi_dh1>da"); sd.chain = 2; sd.chain_bwd = 1;
+            crit_dh1(sd, q1, ca1, 0); sd.gemm.back().no_store = 1; crit_dh1(sd, q2, ca2, 0); sd.gemm.back().no_store = 1;
+            crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0);
+        } else if (tensor_glue) { Stage& sd = add_stage(ST_GEMM, "pi_da"); sd.join = group_lanes ? 1 : 0; crit_da(sd, q1, ca1, 0); crit_da(sd, q2, ca2, 0); }
         Stage& s = add_stage(ST_POLICY_GRAD, tensor_glue ? "policy_grad" : "policy_grad+da+dh2");
         s.join = 3;
         s.pg.push_back(pg_task({{q1, ca1.dh1}, {q2, ca2.dh1}}, pol, pa, 0, pg, !c.deterministic, {ca1.da, ca2.da}));
         fill_pgp(s);
-        if (tensor_glue) { Stage& s2 = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s2, pol, pa, 0, pg); }
+        if (bwd_chain) {
+            Stage& s2 = add_stage(ST_GEMM, "policy_dh2>dh1"); s2.chain = 2; s2.chain_bwd = 1;
+            pol_dh2(s2, pol, pa, 0, pg); pol_dh1(s2, pol, pa, 0, pg);
+        } else if (tensor_glue) { Stage& s2 = add_stage(ST_GEMM, "policy_dh2"); pol_dh2(s2, pol, pa, 0, pg); }
     };
     // NB mode B reads fc0.weight's action columns too: its policy_grad stage runs before the critic Adam
     if (mode_b) policy_grad_stage();
@@ -704,10 +720,10 @@ void Builder::build_sac() {
         if (!two_lanes && tensor_glue && (H & 3) == 0) {
             Stage& s = add_stage(ST_RANK1, "pi_dh2"); crit_dh2_rank1(s, q1, ca1, 0); crit_dh2_rank1(s, q2, ca2, 0);
         } else if (!two_lanes) { Stage& s = add_stage(ST_GEMM, "pi_dh2"); crit_dh2(s, q1, ca1, 0); crit_dh2(s, q2, ca2, 0); }
-        { Stage& s = add_stage(ST_GEMM, "pi_dh1"); s.join = 2; crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
+        if (!pi_chain) { Stage& s = add_stage(ST_GEMM, "pi_dh1"); s.join = 2; crit_dh1(s, q1, ca1, 0); crit_dh1(s, q2, ca2, 0); }
         policy_grad_stage();
     }
-    { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
+    if (!bwd_chain) { Stage& s = add_stage(ST_GEMM, "policy_dh1"); pol_dh1(s, pol, pa, 0, pg); }
     { Stage& s = add_stage(ST_GEMM, "policy_adam"); pol_adam(s, pol, pa, 0, 2, pg, c.policy_lr, 0); }
     flush_adam("policy_adam_apply");
 }
@@ -1042,23 +1058,33 @@ static int ws_plan(OacTrainer& t, Stage& s) {
 static int chain_plan(OacTrainer& t, Stage& s) {
     const int seeds = t.cfg.n_seeds;
     const int NL = s.chain, NC = (int)s.gemm.size() / NL;
-    if (NL < 2 || NL > CH_MAX_LAYERS || NC < 1 || NC * NL != (int)s.gemm.size() || NC > WS_MAX_TASKS || !ws_eligible(t, s))
-        return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: shape");
+    const bool bwd = s.chain_bwd != 0;
+    if (NL < 2 || NL > CH_MAX_LAYERS || (bwd && NL != 2) || NC < 1 || NC * NL != (int)s.gemm.size() || NC > WS_MAX_TASKS || !ws_eligible(t, s))
+        return set_error(OAC_E_CHAIN_UNAVAILABLE, "chain: shape");
     int strips = 0;
     for (int c = 0; c < NC; ++c) {
         const GemmTask& g0 = s.gemm[c];
         for (int l = 0; l < NL; ++l) {
             GemmTask& g = s.gemm[l * NC + c];
             const bool last = l == NL - 1;
-            if (g.a_trans || g.b_trans || g.M != g0.M || (g.M % WS_BM) != 0) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: layout");
+            if (g.a_trans || (g.b_trans != 0) != bwd || g.M != g0.M || (g.M % WS_BM) != 0) return set_error(OAC_E_CHAIN_UNAVAILABLE, "chain: layout");
             if (l > 0) {      // reads the previous layer's output in full
                 const GemmTask& pv = s.gemm[(l - 1) * NC + c];
-                if (g.K != pv.N || g.A.arena != pv.C.arena || g.A.off != pv.C.off || g.K != 256) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: link");
+                if (g.K != pv.N || g.A.arena != pv.C.arena || g.A.off != pv.C.off || g.K != 256) return set_error(OAC_E_CHAIN_UNAVAILABLE, "chain: link");
             }
-            if (!last && (g.N != 256 || g.epi != EPI_BIAS_RELU)) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: hidden layer");
-            if (g.epi != EPI_BIAS_RELU && g.epi != EPI_BIAS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: epilogue");
-            if (g.N > 256) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: width");
-            g.bn = last ? std::max(16, (g.N + 15) / 16 * 16) : 256;
+            if (g.N > 256) return set_error(OAC_E_CHAIN_UNAVAILABLE, "chain: width");
+            if (!bwd) {
+                if (!last && (g.N != 256 || g.epi != EPI_BIAS_RELU)) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: hidden layer");
+                if (g.epi != EPI_BIAS_RELU && g.epi != EPI_BIAS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: epilogue");
+                g.bn = last ? std::max(16, (g.N + 15) / 16 * 16) : 256;
+            } else {
+                // masks are sign bytes (one uint2 per row and 32 columns, lane = row), stores are plain
+                if (!last && (g.N != 256 || g.epi != EPI_MASK)) return set_error(OAC_E_CHAIN_UNAVAILABLE, "backward chain: hidden layer");
+                if (g.epi != EPI_MASK && g.epi != EPI_STORE) return set_error(OAC_E_CHAIN_UNAVAILABLE, "backward chain: epilogue");
+                if (g.epi == EPI_MASK && (!g.mask_bits || (g.ldmask & 7) || g.N != 256)) return set_error(OAC_E_CHAIN_UNAVAILABLE, "backward chain: mask");
+                if (last && g.no_store) return set_error(OAC_E_CHAIN_UNAVAILABLE, "backward chain: nothing stored");
+                g.bn = last ? std::max(32, (g.N + 31) / 32 * 32) : 256;       // M/N-contiguous B: whole 32-column atoms
+            }
             g.tiles_m = g.M / WS_BM; g.tiles_n = 1; g.tile0 = strips;
         }
         s.chain_strips0[c] = strips;
@@ -1069,7 +1095,7 @@ static int chain_plan(OacTrainer& t, Stage& s) {
     s.ws_slot_bytes = (int)WS_A_BYTES + 256 * (WS_KC * 4);
     const int budget = 224 * 1024 - 1024 - (int)WS_SLAB_BYTES;
     s.ws_slots = std::min((int)WS_MAX_SLOTS, budget / s.ws_slot_bytes);
-    if (s.ws_slots < 2) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: ring");
+    if (s.ws_slots < 2) return set_error(OAC_E_CHAIN_UNAVAILABLE, "chain: ring");
     s.smem = (size_t)s.ws_slots * s.ws_slot_bytes + WS_SLAB_BYTES + 1024;
     s.ws_grid = (int)std::min<long long>((long long)strips * seeds, sm_count());
     TensorMapEncodeFn enc = tensor_map_encoder();
@@ -1081,12 +1107,22 @@ static int chain_plan(OacTrainer& t, Stage& s) {
             const int ld = op == 0 ? g.lda : g.ldb;
             const int ext = op == 0 ? g.M : g.N;
             const long long sstride = std::max<long long>(t.as.stride[r.arena], 4);
-            cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)ext, (cuuint64_t)seeds};
-            cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)sstride * 4};
-            cuuint32_t box[3] = {WS_KC, op == 0 ? (cuuint32_t)WS_BM : (cuuint32_t)g.bn, 1}, es[3] = {1, 1, 1};
-            CUresult rc = enc(&maps[2 * i + op], ws_map_dtype(), 3, (void*)resolve(t.as, r, 0), dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (rc != CUDA_SUCCESS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "forward chain: tensor map");
+            CUresult rc;
+            if (op == 1 && bwd) {
+                // M/N-contiguous weights: [seed][atom of 32 columns][k][32], one box = all atoms of the tile (ws_plan)
+                cuuint64_t dims[4] = {32, (cuuint64_t)g.K, (cuuint64_t)((ext + 31) / 32), (cuuint64_t)seeds};
+                cuuint64_t strides[3] = {(cuuint64_t)ld * 4, 128, (cuuint64_t)sstride * 4};
+                cuuint32_t box[4] = {32, WS_KC, (cuuint32_t)(g.bn / 32), 1}, es[4] = {1, 1, 1, 1};
+                rc = enc(&maps[2 * i + op], ws_map_dtype(), 4, (void*)resolve(t.as, r, 0), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            } else {
+                cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)ext, (cuuint64_t)seeds};
+                cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)sstride * 4};
+                cuuint32_t box[3] = {WS_KC, op == 0 ? (cuuint32_t)WS_BM : (cuuint32_t)g.bn, 1}, es[3] = {1, 1, 1};
+                rc = enc(&maps[2 * i + op], ws_map_dtype(), 3, (void*)resolve(t.as, r, 0), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, ws_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+            if (rc != CUDA_SUCCESS) return set_error(OAC_E_CHAIN_UNAVAILABLE, "chain: tensor map");
         }
     }
     if (int e = upload(t, maps.data(), maps.size(), &s.ws_tmaps)) return e;
@@ -1394,7 +1430,8 @@ static int launch_stage(OacTrainer& t, Stage& s, int use_external_eps, cudaStrea
                 cp.n_layers = s.chain; cp.n_chains = (int)s.gemm.size() / s.chain;
                 for (int i = 0; i <= WS_MAX_TASKS; ++i) cp.strips0[i] = i <= cp.n_chains ? s.chain_strips0[i] : 0;
                 cp.n_seeds = seeds; cp.total_items = s.ws_tiles_per_seed * seeds; cp.n_slots = s.ws_slots; cp.slot_bytes = s.ws_slot_bytes;
-                launch_pdl(gemm_chain_kernel, dim3(s.ws_grid), dim3(WS_THREADS), s.smem, st, cp);
+                if (s.chain_bwd) launch_pdl(gemm_chain_kernel<true>, dim3(s.ws_grid), dim3(WS_THREADS), s.smem, st, cp);
+                else launch_pdl(gemm_chain_kernel<false>, dim3(s.ws_grid), dim3(WS_THREADS), s.smem, st, cp);
                 OAC_CUDA(cudaGetLastError());
                 return 0;
             }
@@ -1559,6 +1596,7 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
     { const char* n2 = getenv("OAC_NO_WS2"); t->allow_ws2 = !(n2 && n2[0] == '1'); }
     { const char* nc = getenv("OAC_NO_CHAIN"); t->allow_chain = !(nc && nc[0] == '1'); }
     { const char* nb = getenv("OAC_NO_MASK_BITS"); t->allow_bits = !(nb && nb[0] == '1'); }
+    { const char* nb = getenv("OAC_NO_BWD_CHAIN"); t->allow_bwd_chain = !(nb && nb[0] == '1'); }
     { const char* nk = getenv("OAC_NO_SK_TMA"); t->allow_sk_tma = !(nk && nk[0] == '1'); }
     Builder b(*t);
     if (cfg->algo == OAC_ALGO_SAC) b.build_sac();
@@ -1607,7 +1645,8 @@ extern "C" int oac_trainer_create(const OacConfig* cfg, const OacBuffers* buf, O
         opt_ws((const void*)gemm_ws2_kernel<false, false>);
         opt_ws((const void*)gemm_ws2_kernel<false, true>);
         opt_ws((const void*)gemm_ws2_kernel<true, true>);
-        opt_ws((const void*)gemm_chain_kernel);
+        opt_ws((const void*)gemm_chain_kernel<false>);
+        opt_ws((const void*)gemm_chain_kernel<true>);
         opt_in((const void*)policy_head_kernel<1>);
         opt_in((const void*)policy_head_kernel<4>);
         opt_in((const void*)policy_grad_kernel<1>);

@@ -22,8 +22,9 @@ def test_group_of_eight_tensor_path_vs_fp32_singles():
     e = grp.engine
     # every GEMM stage runs on the TMA + tcgen05 kernels (the forward layers of this 8-seed group as two strip-fused chains:
     # gemm_chain.cuh), Adam is a stage of its own, the step tail a one-CTA-per-seed kernel on a side lane, and the critics'
-    # fc1 / head update + the first two policy-loss dX stages run on a side lane next to qloss_dh1 / the fc0 update
-    assert e.ws_stages >= 12 and e.launches_per_step == 18, (e.ws_stages, e.launches_per_step)
+    # fc1 / head update + the first two policy-loss dX stages run on a side lane next to qloss_dh1 / the fc0 update;
+    # policy_dh2 > policy_dh1 is a strip-fused backward chain
+    assert e.ws_stages >= 12 and e.launches_per_step == 17, (e.ws_stages, e.launches_per_step)
     singles = []
     for sid in ids:
         torch.manual_seed(sid)
@@ -111,6 +112,7 @@ def test_sign_bit_masks_equal_fp32_masks(monkeypatch):
     strip-fused chains of a small group and for the per-layer stages (CTA pairs included) of a larger one."""
     from oac_explore_b200.seed_group import SACSeedGroup
     O, A, H, B = 376, 17, 256, 256
+    monkeypatch.setenv("OAC_NO_BWD_CHAIN", "1")       # (the backward chains exist with sign bytes only and round ties differently)
     for S in (8, 32):
         res = []
         for no_bits in ("0", "1"):
@@ -125,3 +127,35 @@ def test_sign_bit_masks_equal_fp32_masks(monkeypatch):
             torch.cuda.synchronize()
             res.append((grp.engine.params.clone(), grp.engine.adam_v.clone(), grp.stats().clone()))
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2]), S
+
+
+@pytest.mark.parametrize("S", [8, 32])
+def test_backward_chains_equal_per_layer_stages(monkeypatch, S):
+    """policy_dh2 > policy_dh1 (every group) and pi_dh1 > pi_da (groups without the side-lane schedule) as strip-fused backward
+    chains (gemm_chain_kernel<true>: the intermediate gradient handed on in tensor memory, masks from the sign bytes) compute
+    the same products as the per-layer dX stages.  Not bitwise: the handed-on gradient is rounded to tf32 by cvt.rna where
+    the per-layer path lets the TFLOAT32 tensor map round it (ties differ), so the first step's gradients (Adam's first
+    moment / 0.1) agree norm-wise to 1e-4, and so do the weights after two steps (Adam's first updates are +-lr whatever the
+    gradient's size: a handful of sign-ambiguous elements move by 2 lr)."""
+    from oac_explore_b200.seed_group import SACSeedGroup
+    O, A, H, B = 376, 17, 256, 256
+    res, launches = [], []
+    for off in ("0", "1"):
+        monkeypatch.setenv("OAC_NO_BWD_CHAIN", off)
+        grp = SACSeedGroup(list(range(S)), O, A, hidden=H, batch=B, gemm_path=1, policy_lr=3e-4, qf_lr=3e-4)
+        launches.append(grp.engine.launches_per_step)
+        snaps = []
+        for step in range(2):
+            for slot in range(S):
+                grp.load_batch(slot, synth_batch(B, O, A, seed=3000 + 10 * step + slot))
+                e_ = synth_eps(2, B, A, seed=4000 + 10 * step + slot)
+                grp.inject_noise(slot, e_[0], e_[1])
+            grp.step(external_eps=True)
+            torch.cuda.synchronize()
+            snaps.append(grp.engine.adam_m.clone())
+        res.append((grp.engine.params.clone(), snaps[0], grp.stats().clone()))
+    assert launches[0] == launches[1] - (1 if S <= 16 else 2), launches
+    for s_ in range(S):
+        assert rel_err(res[0][1][s_].cpu(), res[1][1][s_].cpu()) <= 1e-4, (s_, rel_err(res[0][1][s_].cpu(), res[1][1][s_].cpu()))
+        assert rel_err(res[0][0][s_].cpu(), res[1][0][s_].cpu()) <= 1e-4, (s_, rel_err(res[0][0][s_].cpu(), res[1][0][s_].cpu()))
+    assert torch.allclose(res[0][2], res[1][2], rtol=1e-4, atol=1e-5)

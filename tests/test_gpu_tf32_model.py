@@ -251,8 +251,8 @@ def test_strip_fused_forward_chain_vs_model_and_unfused(monkeypatch):
     monkeypatch.setenv("OAC_NO_CHAIN", "1")
     ref_grp = SACSeedGroup(ids, O, A, hidden=H, batch=B, gemm_path=1)
     monkeypatch.delenv("OAC_NO_CHAIN")
-    # 3 launches fewer: policy l1 > l2 > l3 and critic l1 > l2 are one launch each
-    assert grp.engine.launches_per_step == ref_grp.engine.launches_per_step - 3, (grp.engine.launches_per_step, ref_grp.engine.launches_per_step)
+    # 4 launches fewer: policy l1 > l2 > l3, critic l1 > l2 and (backward) policy_dh2 > policy_dh1 are one launch each
+    assert grp.engine.launches_per_step == ref_grp.engine.launches_per_step - 4, (grp.engine.launches_per_step, ref_grp.engine.launches_per_step)
     states, outs = {}, {}
     for sid in (0, 5):
         torch.manual_seed(sid)
