@@ -583,6 +583,14 @@ struct Builder {
             }
         }
         { Stage& s = add_stage(ST_GEMM, n1); l1(s); }
+        // several rounds of strips: only the cheap head layer rides on its predecessor (l2 > head: h2 goes on through tensor
+        // memory, the head's 34-column MMAs run while h2 is being stored) -- OAC_TAIL_CHAIN=0 keeps the three launches
+        static const bool tail_chain = !(getenv("OAC_TAIL_CHAIN") && getenv("OAC_TAIL_CHAIN")[0] == '0');
+        if (layers == 3 && fuse_chain() && tail_chain) {
+            Stage& s = add_stage(ST_GEMM, "policy_l2>l3"); s.chain = 2;
+            l2(s); l3(s);
+            return;
+        }
         { Stage& s = add_stage(ST_GEMM, n2); l2(s); }
         if (layers == 3 && tensor_glue) { Stage& s = add_stage(ST_GEMM, n3); l3(s); }
     }
