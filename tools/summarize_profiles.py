@@ -97,12 +97,16 @@ if __name__ == "__main__":
     tpath = os.path.join(P, "traffic.json")
     tr = json.load(open(tpath)) if os.path.exists(tpath) else {}
     # a configuration whose kernels did not change since an earlier tag keeps that tag's files (and its traffic entry)
+    per = {"single": 16, "64seeds": 19, "8seeds": 19}
+    if have(tag + "_launches_per_step.txt"):
+        w = open(os.path.join(G, tag + "_launches_per_step.txt")).read().split()
+        per = {w[i]: int(w[i + 1]) for i in range(0, len(w), 2)}
     if have(tag + "_launches_single_fp32.csv"):
-        launch_list(tag + "_launches_single_fp32.csv", 16)
+        launch_list(tag + "_launches_single_fp32.csv", per["single"])
     if have(tag + "_launches_64seeds_tf32.csv"):
-        launch_list(tag + "_launches_64seeds_tf32.csv", 19)
+        launch_list(tag + "_launches_64seeds_tf32.csv", per["64seeds"])
     if have(tag + "_launches_8seeds_tf32.csv"):
-        launch_list(tag + "_launches_8seeds_tf32.csv", 19)
+        launch_list(tag + "_launches_8seeds_tf32.csv", per["8seeds"])
     if have(tag + "_8seeds_tf32.ncu-rep"):
         full_report(tag + "_8seeds_tf32.ncu-rep", tag + "_8seeds_tf32_full.txt")
         tr["8:tf32"] = traffic(tag + "_8seeds_tf32.ncu-rep", ("gemm_ws_kernel", "gemm_ws2_kernel", "gemm_chain_kernel"))
