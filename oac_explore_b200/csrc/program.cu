@@ -1334,7 +1334,11 @@ static int finalize(OacTrainer& t) {
             }
             s.chp.as = t.as;
             {
-                bool ok = s.chp.mode == CM_SAC && t.cfg.hidden == 256 && t.cfg.gemm_path == OAC_GEMM_TF32 && (long long)seeds * t.cfg.batch >= 2048 &&
+                // the lean SAC kernel (one self-contained warp per sample: glue_many.cuh) also wins in the single-seed latency
+                // regime: critic_head 8.3 -> 6.2 us, step 118.9 -> 115.8 us (OAC_CH_LEAN_ALL=0 keeps the generic kernel there)
+                static const bool lean_all = !(getenv("OAC_CH_LEAN_ALL") && getenv("OAC_CH_LEAN_ALL")[0] == '0');
+                bool ok = s.chp.mode == CM_SAC && t.cfg.hidden == 256 &&
+                          (lean_all || (t.cfg.gemm_path == OAC_GEMM_TF32 && (long long)seeds * t.cfg.batch >= 2048)) &&
                           s.chp.n_src == 6 && !getenv("OAC_NO_GLUE_MANY");
                 for (int i = 0; i < s.chp.n_src && ok; ++i) ok = s.chp.src[i].n_heads == 1;
                 for (int a = 0; a < AR_COUNT && ok; ++a) ok = (t.as.stride[a] & 3) == 0 && al16(t.as.base[a]);
