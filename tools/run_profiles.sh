@@ -25,7 +25,7 @@ per_step() { echo $(( $(grep -o '[0-9]* launches/step' $1 | grep -o '^[0-9]*') +
 L1=$(per_step $O/${T}_plain_single.log); L64=$(per_step $O/${T}_plain_64.log); L8=$(per_step $O/${T}_plain_8.log)
 echo "single $L1 64seeds $L64 8seeds $L8" > $O/${T}_launches_per_step.txt
 # full captures: the last step's launches of each configuration
-ncu --set full --clock-control none -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head_kernel|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip $((2 * L1)) --launch-count $L1 -o $O/${T}_single_fp32 -f \
+ncu --set full --clock-control none -k regex:"gemm_sk_kernel|gemm_fwd2_kernel|critic_head|policy_head_kernel|step_tail_kernel|policy_grad_kernel|replay_gather_kernel" --launch-skip $((2 * L1)) --launch-count $L1 -o $O/${T}_single_fp32 -f \
     python tools/profile_step.py --steps 3 > $O/${T}_full_single.log 2>&1
 ncu --set full --clock-control none -k regex:"gemm_chain|gemm_ws|adam_stream|critic_head|policy_head|policy_grad|rank1|step_tail|replay_gather" --launch-skip $L64 --launch-count $L64 -o $O/${T}_64seeds_tf32 -f \
     python tools/profile_step.py --steps 2 --seeds 64 --gemm-path tf32 > $O/${T}_full_64.log 2>&1

@@ -100,7 +100,7 @@ if __name__ == "__main__":
     per = {"single": 16, "64seeds": 19, "8seeds": 19}
     if have(tag + "_launches_per_step.txt"):
         w = open(os.path.join(G, tag + "_launches_per_step.txt")).read().split()
-        per = {w[i]: int(w[i + 1]) for i in range(0, len(w), 2)}
+        per.update({w[i]: int(w[i + 1]) for i in range(0, len(w), 2)})
     if have(tag + "_launches_single_fp32.csv"):
         launch_list(tag + "_launches_single_fp32.csv", per["single"])
     if have(tag + "_launches_64seeds_tf32.csv"):
