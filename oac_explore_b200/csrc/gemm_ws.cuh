@@ -7,11 +7,12 @@
 //     cp.async.bulk.tensor.3d through a per-task tensor map ([seed][row][col] view of the arena), 32 k per
 //     pipeline slot, straight into the canonical UMMA layouts -- SWIZZLE_128B for K-contiguous operands,
 //     SWIZZLE_128B_ATOM_32B for the M/N-contiguous ones (dX and dW products), so transposed copies never
-//     exist (an M/N-contiguous operand is described as [seed][32-wide atom][k][32]: ONE box fetches all atoms of a tile's
-//     chunk -- per-atom boxes made these stages 1.5x slower than K-major ones).  The maps use the TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 to nearest while it
-//     copies (measured: tools/probes/tma_probe.cu), which removes the MMA's truncation bias without any
-//     rounding pass over shared memory or rounded copies of the weights.  Ragged M / N / K edges are
-//     zero-filled by the TMA bounds check.
+//     exist (an M/N-contiguous operand is described as [seed][32-wide atom][k][32]: ONE 4-d box fetches all atoms of a
+//     tile's chunk instead of one box instruction per atom; ragged last atoms read the rest of the row pitch: ws_plan).
+//     The maps use the TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 to nearest while it copies (measured:
+//     tools/probes/tma_probe.cu; as fast as plain fp32 maps), which removes the MMA's truncation bias without any
+//     rounding pass over shared memory or rounded copies of the weights.  Ragged M / K edges are zero-filled by the TMA
+//     bounds check.
 //   * warp 1 (one lane) issues tcgen05.mma into one of TWO TMEM accumulators (2 x 256 columns) and
 //     signals slot reuse / accumulator completion with tcgen05.commit -> mbarrier;
 //   * warps 2..9 are the epilogue: tcgen05.ld (lane = row) -> per-warp shared slab -> float4 accesses with
