@@ -1,5 +1,6 @@
+"""Single-seed OAC step at Humanoid shapes: graph-replayed step time and the stage-by-stage profile (measurement aid)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from oac_explore_b200.replay_buffer import ReplayBuffer
