@@ -64,12 +64,16 @@ class SACSeedGroup(object):
         ids = torch.tensor(self.seed_ids, dtype=torch.int64)
         self.engine.counters[:, _lib.CNT_RNG_LO] = (ids & 0x7fffffff).to(torch.int32).to(self.engine.device)
         self.engine.counters[:, _lib.CNT_RNG_HI] = (ids >> 31).to(torch.int32).to(self.engine.device)
-        # index upload: the host runs ahead of the stream (a step takes longer than drawing the next indices), so the
-        # pinned staging buffers form a ring and a slot is only rewritten after the copy that read it has completed
+        # index upload: the host runs ahead of the step stream (a step takes longer than drawing the next indices), so the pinned
+        # staging buffers AND their device copies form a ring; the host -> device copy of step i + 1 runs on a copy stream of its
+        # own while step i computes (on the step stream it sat between two steps: ~10 us per step of a small group), and a ring
+        # slot is only rewritten after the gather that read its device copy has completed
         self._idx_ring = [torch.zeros((S, batch), dtype=torch.int64).pin_memory() for _ in range(self._IDX_RING)]
-        self._idx_events = [None] * self._IDX_RING
+        self._idx_dev_ring = [torch.zeros((S, batch), dtype=torch.int64, device=self.engine.device) for _ in range(self._IDX_RING)]
+        self._idx_copied = [torch.cuda.Event() for _ in range(self._IDX_RING)]
+        self._idx_consumed = [None] * self._IDX_RING
         self._idx_slot = 0
-        self._idx_dev = torch.zeros((S, batch), dtype=torch.int64, device=self.engine.device)
+        self._copy_stream = torch.cuda.Stream(device=self.engine.device)
 
     _IDX_RING = 4
 
@@ -79,20 +83,25 @@ class SACSeedGroup(object):
 
     def gather(self, replay, indices):
         """indices: [S, B] int64 (host numpy or device tensor) -> one gather launch for all seeds."""
+        k = None
         if isinstance(indices, np.ndarray):
             k = self._idx_slot
             self._idx_slot = (k + 1) % self._IDX_RING
-            if self._idx_events[k] is not None:
-                self._idx_events[k].synchronize()          # the copy that last read this pinned slot is done
+            if self._idx_consumed[k] is not None:
+                self._idx_consumed[k].synchronize()         # the gather that read this slot's device copy is done
             host = self._idx_ring[k]
             host.numpy()[...] = indices
-            # _idx_dev itself is safe to overwrite: the copy is stream-ordered after the previous gather that read it
-            self._idx_dev.copy_(host, non_blocking=True)
-            ev = self._idx_events[k] or torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            self._idx_events[k] = ev
-            indices = self._idx_dev
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(self._copy_stream):
+                self._idx_dev_ring[k].copy_(host, non_blocking=True)
+                self._idx_copied[k].record(self._copy_stream)
+            main.wait_event(self._idx_copied[k])
+            indices = self._idx_dev_ring[k]
         replay.gather_into(self.engine, indices, self.B, seed=0, n_seeds=self.n_seeds)
+        if k is not None:
+            ev = self._idx_consumed[k] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._idx_consumed[k] = ev
 
     def load_batch(self, seed_slot, batch):
         f = lambda t: t.to(self.engine.device, torch.float32)
