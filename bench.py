@@ -11,7 +11,7 @@ A "step" is one pass of the hot path over one batch: ReplayBuffer.random_batch(2
           reference-matching numerics) with the inputs (the index stream) already in HBM when the timed region starts:
           K x (gather kernel + step graph) between two CUDA events, max over ranks.
   e2e   : the same metric through the public, reference-facing API with HOST inputs:
-          replay_buffer.random_batch(B) (np.random indices -> pinned host memory, read by the gather kernel) +
+          replay_buffer.random_batch(B) (np.random indices -> pinned host memory -> async H2D on a copy stream) +
           trainer.train(batch) + a host read of the step's scalars, every step, inside the timed region.
   batched_seeds : BASELINE config 5 at EVERY N: 64 independent seeds in total, 64 / N per GPU (seed s on GPU s % N, the
           reference's rule, main.py:575-576), batched as grouped GEMMs on the TMA + tcgen05 kind::tf32 path: value
@@ -311,7 +311,7 @@ class _Single(object):
         self.engine.step()
 
     def api_step(self):
-        batch = self.rb.random_batch(B)          # host np.random indices -> pinned ring, read by the gather kernel
+        batch = self.rb.random_batch(B)          # host np.random indices -> pinned ring -> device ring (copy stream) -> gather
         batch['buffer'] = self.rb
         self.tr.train(batch)                     # fused step (CUDA graph)
 
@@ -689,8 +689,8 @@ def run_ours(args):
                                       "waits for step i's event and reads its scalars (two mapped slots stamped with the step "
                                       "number, checked) -- the reference's loop never blocks on a step (rl_algorithm.py:159-165); "
                                       "blocking_value: stream synchronise + read after EVERY step before the next is issued",
-                        "transfers": "indices: pinned host ring read by the gather kernel (single seed) / pinned -> H2D copy "
-                                     "(seed group); result: 4 scalars per seed stored by the step into mapped pinned host memory"},
+                        "transfers": "indices: pinned host ring -> asynchronous H2D copy on a copy stream (overlaps the previous step); "
+                                     "result: 4 scalars per seed stored by the step into mapped pinned host memory"},
                 "gpu_launches": launches,
                 "launches_per_step": e.launches_per_step + 1}
         if roof is not None:

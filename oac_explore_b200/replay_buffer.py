@@ -170,11 +170,14 @@ class ReplayBuffer(object):
     def _draw_indices(self, batch_size):
         return np.random.randint(0, self._size, batch_size)
 
-    # The gather kernel reads the int64 indices straight from pinned host memory (unified addressing: a pinned
-    # allocation is device-accessible under the same pointer), so a batch costs no host->device copy call.  The host
-    # runs ahead of the device (nothing on this path synchronises), so the indices go through a ring of pinned slots;
-    # a slot group is only reused after the gathers that read it have completed (one event per group).
+    # The host runs ahead of the device (nothing on this path synchronises), so the indices go through a ring of pinned
+    # slots; a slot group is only reused after the gathers that read it have completed (one event per group).  Every slot
+    # has a device twin, filled by an asynchronous copy on a COPY STREAM of its own while the previous update still runs:
+    # the gather then reads its indices from HBM (reading them in place from the pinned slot -- unified addressing -- puts a
+    # PCIe round trip at the head of every step's dependency chain; that form is still used when the stream is idle, i.e.
+    # when there is nothing to overlap with, and always with ``zero_copy_indices = True``).
     _RING_GROUPS, _RING_GROUP_SLOTS = 4, 256
+    zero_copy_indices = False
 
     def _upload_indices(self, indices):
         n = len(indices)
@@ -186,6 +189,9 @@ class ReplayBuffer(object):
             slots = self._RING_GROUPS * self._RING_GROUP_SLOTS
             self._idx_host = torch.zeros((slots, n), dtype=torch.int64).pin_memory()
             self._idx_np = self._idx_host.numpy()
+            self._idx_dev = torch.zeros((slots, n), dtype=torch.int64, device=self._device)
+            self._idx_copy_stream = torch.cuda.Stream(device=self._device)
+            self._idx_copied = [torch.cuda.Event() for _ in range(8)]
             self._idx_slot = 0
             self._idx_events = [None] * self._RING_GROUPS
         slot = self._idx_slot
@@ -195,7 +201,17 @@ class ReplayBuffer(object):
         self._idx_np[slot, :n] = indices
         self._idx_last_slot = slot
         self._idx_slot = (slot + 1) % (self._RING_GROUPS * self._RING_GROUP_SLOTS)
-        return self._idx_host[slot]
+        main = torch.cuda.current_stream()
+        if self.zero_copy_indices or main.query():
+            # nothing is running that the copy could overlap (a caller that synchronises after every update): the gather
+            # reads the pinned slot in place, which costs one PCIe round trip but no copy launch + cross-stream wait
+            return self._idx_host[slot]
+        ev = self._idx_copied[slot & 7]
+        with torch.cuda.stream(self._idx_copy_stream):
+            self._idx_dev[slot].copy_(self._idx_host[slot], non_blocking=True)
+            ev.record(self._idx_copy_stream)
+        main.wait_event(ev)
+        return self._idx_dev[slot]
 
     def _indices_consumed(self):
         """Call after the kernel reading the last uploaded slot has been launched."""

@@ -92,11 +92,15 @@ class SACSeedGroup(object):
             host = self._idx_ring[k]
             host.numpy()[...] = indices
             main = torch.cuda.current_stream()
-            with torch.cuda.stream(self._copy_stream):
-                self._idx_dev_ring[k].copy_(host, non_blocking=True)
-                self._idx_copied[k].record(self._copy_stream)
-            main.wait_event(self._idx_copied[k])
-            indices = self._idx_dev_ring[k]
+            if main.query():
+                indices = host          # idle stream (a caller that synchronises every step): nothing to overlap a copy with --
+                                        # the gather reads the pinned slot in place (unified addressing)
+            else:
+                with torch.cuda.stream(self._copy_stream):
+                    self._idx_dev_ring[k].copy_(host, non_blocking=True)
+                    self._idx_copied[k].record(self._copy_stream)
+                main.wait_event(self._idx_copied[k])
+                indices = self._idx_dev_ring[k]
         replay.gather_into(self.engine, indices, self.B, seed=0, n_seeds=self.n_seeds)
         if k is not None:
             ev = self._idx_consumed[k] or torch.cuda.Event()
